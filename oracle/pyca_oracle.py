@@ -1,0 +1,238 @@
+"""CPU oracle for the PyCA ``Automaton.step()`` hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file restates, in plain functional torch/numpy on the CPU, the arithmetic
+of the reference's ``step()`` for the five models in scope.  Nothing under
+``pyca_b200/`` imports it: only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` do, and only as the
+checker / the timed CPU arm.
+
+Pinning status: the reference ships no tests or golden vectors,
+so the oracle is pinned against the reference ITSELF: ``tests/golden/generate.py``
+imports the unmodified reference headless in the build container, runs its
+``step()`` on seeded inputs and commits inputs+outputs as ``tests/golden/*.npz``;
+``tests/test_oracle_golden.py`` checks every function below against those
+fixtures (bit-exact for Game of Life, <=1e-6 for the float models; the float
+functions use the same torch primitives as the reference -- ``fft2``, ``unfold``,
+``conv2d``, ``Linear`` -- in the same order).
+
+Reference lines followed (relative to the PyCA tree):
+  gol_step              pyca/automata/models/ca2d.py:195-209, :221-225
+  sanitize_params       pyca/automata/models/lenia/leniaparams.py:68-87
+  lenia_kernel          pyca/automata/models/lenia/lenia.py:289-362 (ring kernels; k_arbi out of scope)
+  kernel_fft            pyca/automata/models/lenia/lenia.py:364-380
+  fft_conv              pyca/automata/models/lenia/lenia.py:453-469
+  growth                pyca/automata/models/lenia/lenia.py:419-428
+  lenia_step            pyca/automata/models/lenia/lenia.py:430-451
+  mace_affinity         pyca/automata/models/lenia/macelenia.py:122-159 (food off)
+  mace_step             pyca/automata/models/lenia/macelenia.py:89-120
+  xchan_step            pyca/automata/models/lenia/mace_lenia_xchan.py:59-76
+  nca_perception        pyca/automata/models/nca.py:306-344
+  nca_live_mask         pyca/automata/models/nca.py:226-237
+  nca_step              pyca/automata/models/nca.py:239-263
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------- #
+# Game of Life / outer-totalistic CA2D
+# --------------------------------------------------------------------------- #
+def rule_mask(rule) -> int:
+    """'23' -> 0b1100 (ca2d.py:80-88).  Ints pass through."""
+    if isinstance(rule, str):
+        return sum(1 << int(ch) for ch in rule)
+    return int(rule)
+
+
+def gol_step(world: np.ndarray, s_mask=0b1100, b_mask=0b1000) -> np.ndarray:
+    """One periodic Moore-neighbourhood outer-totalistic step on an (H,W) 0/1 array.
+
+    ca2d.py:195-209: count = sum of the 8 rolled copies; next = bit `count` of
+    s_mask where the cell is alive else of b_mask."""
+    w = np.asarray(world).astype(np.int32)
+    cnt = np.zeros_like(w)
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            if dy or dx:
+                cnt += np.roll(w, (dy, dx), axis=(0, 1))
+    s = (int(s_mask) >> cnt) & 1
+    b = (int(b_mask) >> cnt) & 1
+    return np.where(w == 1, s, b).astype(np.int32)
+
+
+def gol_run(world, steps, s_mask=0b1100, b_mask=0b1000):
+    w = np.asarray(world).astype(np.int32)
+    for _ in range(steps):
+        w = gol_step(w, s_mask, b_mask)
+    return w
+
+
+# --------------------------------------------------------------------------- #
+# Lenia family: parameters and kernels (cold path)
+# --------------------------------------------------------------------------- #
+def sanitize_params(p: dict) -> dict:
+    """leniaparams.py:68-87: clamp ranges, weights >= 0 and normalised over dim 1."""
+    q = dict(p)
+    if "mu" in q:
+        q["mu"] = torch.clamp(q["mu"], -2, 2)
+    if "sigma" in q:
+        q["sigma"] = torch.clamp(q["sigma"], 1e-4, 1.0)
+    if "beta" in q:
+        q["beta"] = torch.clamp(q["beta"], 0, None)
+    if "mu_k" in q:
+        q["mu_k"] = torch.clamp(q["mu_k"], 0.0, 2.0)
+    if "sigma_k" in q:
+        q["sigma_k"] = torch.clamp(q["sigma_k"], 1e-4, 1.0)
+    w = torch.clamp(q["weights"], 0, None)
+    n = w.sum(dim=1, keepdim=True)
+    q["weights"] = torch.where(n > 1.0e-6, w / n, 0)
+    return q
+
+
+def lenia_kernel(beta, mu_k, sigma_k, k_size: int) -> torch.Tensor:
+    """Ring kernels on the full k x k square, normalised to sum 1 (lenia.py:289-362).
+
+    beta/mu_k/sigma_k: (B, C*k_mult, C, rings).  Returns (B, C*k_mult, C, k, k)."""
+    ax = torch.linspace(-1, 1, k_size).to(beta.device)
+    gx, gy = torch.meshgrid(ax, ax, indexing="xy")
+    r = torch.sqrt(gx**2 + gy**2)
+    rr = r[None, None, None, None].expand(*beta.shape, -1, -1)
+    rings = torch.exp(-(((rr - mu_k[..., None, None]) / sigma_k[..., None, None]) ** 2) / 2)
+    K = torch.sum(beta[..., None, None] * rings, dim=3)
+    tot = torch.sum(K, dim=(-1, -2), keepdim=True)
+    tot = torch.where(tot < 1e-6, 1, tot)
+    return K / tot
+
+
+def kernel_fft(K: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """Zero-pad to (h,w), centre on the origin, fft2 (lenia.py:364-380)."""
+    k = K.shape[-1]
+    Kp = F.pad(K, [0, w - k, 0, h - k])
+    Kp = Kp.roll((-(k // 2), -(k // 2)), dims=(-1, -2))
+    return torch.fft.fft2(Kp)
+
+
+def fft_conv(state: torch.Tensor, Kf: torch.Tensor, k_mult: int = 1) -> torch.Tensor:
+    """Periodic convolution of every source channel with every kernel (lenia.py:453-469).
+
+    state (B,C,H,W); Kf (B,C*k_mult,C,H,W) complex.  Returns U (B,C*k_mult,C,H,W) with
+    U[b, i*k_mult+m, j] = K[b, i*k_mult+m, j] (*) state[b, i]."""
+    B, C, H, W = state.shape
+    S = torch.fft.fft2(state)[:, :, None, None]
+    prod = S * Kf.reshape(B, C, k_mult, C, H, W)
+    prod = prod.reshape(B, C * k_mult, C, H, W)
+    return torch.real(torch.fft.ifft2(prod))
+
+
+def growth(U, mu, sigma):
+    """Gaussian growth 2*exp(-((u-mu)^2/sigma^2)/2)-1 (lenia.py:419-428)."""
+    m = mu[..., None, None]
+    s = sigma[..., None, None]
+    return 2 * torch.exp(-((U - m) ** 2 / s**2) / 2) - 1
+
+
+def lenia_affinity(state, K, mu, sigma, weights, Kf=None):
+    """Weighted source-sum of growths: (B,C,H,W) (lenia.py:436-446 / macelenia.py:144-150)."""
+    B, C, H, W = state.shape
+    k_mult = K.shape[1] // C
+    if Kf is None:
+        Kf = kernel_fft(K, H, W)
+    U = fft_conv(state, Kf, k_mult)
+    return (growth(U, mu, sigma) * weights[..., None, None]).sum(dim=1)
+
+
+def lenia_step(state, K, mu, sigma, weights, dt=0.1, Kf=None):
+    """lenia.py:430-451."""
+    dx = lenia_affinity(state, K, mu, sigma, weights, Kf)
+    return torch.clamp(state + dt * dx, 0, 1)
+
+
+def _sum3x3_unfold(x):
+    """Circular 3x3 box sum exactly as the reference does it: pad + unfold + sum
+    (macelenia.py:107-109)."""
+    B, C, H, W = x.shape
+    p = F.pad(x, (1, 1, 1, 1), mode="circular")
+    return F.unfold(p, kernel_size=(3, 3)).reshape(B, C, 9, H, W)
+
+
+def mace_redistribute(state, aff, b):
+    """macelenia.py:103-118: E=exp(b*Aff); Z=sum3x3(E); new = E * sum3x3(state/Z)."""
+    E = torch.exp(b * aff)
+    Z = _sum3x3_unfold(E).sum(dim=2)
+    give = _sum3x3_unfold(state / Z)
+    return (E[:, :, None] * give).sum(dim=2)
+
+
+def mace_step(state, K, mu, sigma, weights, b=8.0, Kf=None):
+    """macelenia.py:72-120 with food off.  Returns (new_state, Aff)."""
+    aff = lenia_affinity(state, K, mu, sigma, weights, Kf)
+    return mace_redistribute(state, aff, b), aff
+
+
+def xchan_mix(state, aff, b, alpha):
+    """mace_lenia_xchan.py:68-76."""
+    mx = torch.max(aff, dim=1, keepdim=True)[0]
+    num = torch.exp(b * (aff - mx))
+    p = num / num.sum(dim=1, keepdim=True)
+    target = state.sum(dim=1, keepdim=True) * p
+    return state - (state - target) * alpha
+
+
+def xchan_step(state, K, mu, sigma, weights, b=6.0, alpha=0.03, Kf=None):
+    """mace_lenia_xchan.py:59-66 with food off."""
+    new, aff = mace_step(state, K, mu, sigma, weights, b, Kf)
+    return xchan_mix(new, aff, b, alpha)
+
+
+# float64 direct evaluation, for noise-floor reporting (not a restatement of reference lines)
+def lenia_affinity_f64(state, K, mu, sigma, weights):
+    s64 = state.double()
+    K64, mu64, sg64, w64 = K.double(), mu.double(), sigma.double(), weights.double()
+    return lenia_affinity(s64, K64, mu64, sg64, w64)
+
+
+# --------------------------------------------------------------------------- #
+# Neural CA inference
+# --------------------------------------------------------------------------- #
+def sobel_kernels(n_states: int) -> torch.Tensor:
+    """(2n,1,3,3): n copies of sobel-x/8 then n copies of sobel-y/8 (nca.py:316-325)."""
+    sx = torch.tensor([[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]], dtype=torch.float)[None, None] / 8.0
+    sy = torch.tensor([[-1, -2, -1], [0, 0, 0], [1, 2, 1]], dtype=torch.float)[None, None] / 8.0
+    return torch.cat([sx.expand(n_states, -1, -1, -1), sy.expand(n_states, -1, -1, -1)], dim=0)
+
+
+def nca_perception(state):
+    """(B,n,H,W) -> (B,3n,H,W): grouped circular sobel conv then the state (nca.py:328-344).
+    With groups=n and 2n output channels, output o reads input channel o//2."""
+    n = state.shape[1]
+    kern = sobel_kernels(n).to(state.dtype)
+    p = F.pad(state, (1, 1, 1, 1), mode="circular")
+    return torch.cat([F.conv2d(p, kern, groups=n), state], dim=1)
+
+
+def nca_live_mask(state):
+    """nca.py:226-237."""
+    a = F.pad(state[:, 3:4], (1, 1, 1, 1), mode="circular")
+    return F.max_pool2d(a, kernel_size=3, stride=1) > 0.1
+
+
+def nca_step(state, W1, b1, W2, b2, update_mask):
+    """nca.py:239-263 for one step; `update_mask` (B,1,H,W) bool replaces the in-step
+    ``torch.rand(B,1,H,W) <= 0.5`` (nca.py:256) so both sides consume the same draw."""
+    feat = nca_perception(state).permute(0, 2, 3, 1)
+    hid = F.relu(F.linear(feat, W1, b1))
+    dx = F.linear(hid, W2, b2).permute(0, 3, 1, 2)
+    alive0 = nca_live_mask(state)
+    new = torch.sigmoid(dx) * update_mask
+    alive = alive0 & nca_live_mask(new)
+    return torch.clamp(new * alive, 0, 1)
+
+
+def nca_draw_mask(B, H, W, seed):
+    """The mask the reference would draw with ``torch.manual_seed(seed)`` set right before
+    ``forward`` (nca.py:256): one ``torch.rand(B,1,H,W)`` call on the CPU generator."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(B, 1, H, W, generator=g) <= 0.5

@@ -1,0 +1,203 @@
+"""Generate the golden fixtures in this directory FROM THE UNMODIFIED REFERENCE.
+
+Run in the build container only (needs ``/root/reference``):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/generate.py
+
+Every fixture is {seeded input, parameters, output of the reference's own
+``step()``}.  The reference code is imported headless through ``ref_loader``;
+no arithmetic is stubbed.  Outputs are ``.npz`` files (numpy arrays only) so
+they load on the GPU box without the reference or ``torch.load`` pickles.
+
+Files written
+  gol.npz                       CA2D worlds before / after n reference steps (several shapes + rules)
+  params_<family>_<name>.npz    raw parameter dict of a demo_data file + the reference's kernel K
+  lenia_<name>.npz              Lenia C=3 single step (+ C=1 slice of the same file)
+  mace_<name>.npz               MaCELenia single step (+ Aff)
+  xchan_<name>.npz              MaCELeniaXChan single step (+ Aff)
+  xchan_realstate.npz           XChan step on a crop of a real saved state (values >> 1)
+  nca_<model>.npz               NeuralCA weights + one forward step with the seeded update mask
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from ref_loader import load_reference  # noqa: E402
+
+REF = load_reference()
+DEMO = os.path.join(REF.root, "demo_data")
+torch.set_grad_enabled(False)
+
+
+def np_(t):
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **{k: np_(v) for k, v in arrs.items()})
+    print(f"wrote {name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+# ------------------------------------------------------------------ GoL
+def gen_gol():
+    out = {}
+    cases = [  # (H, W, s_rule, b_rule, steps)
+        (16, 16, "23", "3", 1),
+        (33, 70, "23", "3", 8),     # W not a multiple of 32
+        (250, 250, "23", "3", 16),  # simulate.py default world (BASELINE configs[0])
+        (64, 96, "1357", "1357", 5),    # replicator
+        (40, 31, "45678", "3", 7),      # coral; W < 32
+        (37, 129, "012345678", "0", 3),   # B0: dead cells with 0 neighbours are born
+        (8, 257, "238", "357", 9),
+    ]
+    for ci, (H, W, s, b, steps) in enumerate(cases):
+        torch.manual_seed(100 + ci)
+        a = REF.CA2D((H, W), s_num=s, b_num=b)
+        a.world = (torch.rand(H, W) < 0.45).to(torch.int)
+        w0 = a.world.clone()
+        for _ in range(steps):
+            a.step()
+        assert a.world.dtype == torch.int32
+        out[f"c{ci}_w0"] = w0.to(torch.uint8)
+        out[f"c{ci}_w1"] = a.world.to(torch.uint8)
+        out[f"c{ci}_meta"] = np.array([H, W, a.s_num, a.b_num, steps], dtype=np.int64)
+    # the reference's own init (centred random square, int16 world; ca2d.py:227-246)
+    torch.manual_seed(7)
+    a = REF.CA2D((250, 250))
+    w0 = a.world.clone()
+    assert w0.dtype == torch.int16
+    for _ in range(32):
+        a.step()
+    ci = len(cases)
+    out[f"c{ci}_w0"] = w0.to(torch.uint8)
+    out[f"c{ci}_w1"] = a.world.to(torch.uint8)
+    out[f"c{ci}_meta"] = np.array([250, 250, a.s_num, a.b_num, 32], dtype=np.int64)
+    out["ncases"] = np.array(ci + 1)
+    save("gol.npz", **out)
+
+
+# ------------------------------------------------------------------ Lenia family
+PARAM_KEYS = ["mu", "sigma", "beta", "mu_k", "sigma_k", "weights"]
+
+
+def is_plain(d):
+    return not d.get("k_arbi", False) and not d.get("g_arbi", False)
+
+
+def pick(folder, n):
+    files = sorted(f for f in os.listdir(os.path.join(DEMO, folder)) if f.endswith(".pt"))
+    chosen = []
+    for f in files:
+        d = torch.load(os.path.join(DEMO, folder, f), weights_only=True, map_location="cpu")
+        if is_plain(d):
+            chosen.append(f)
+        if len(chosen) == n:
+            break
+    return chosen
+
+
+def raw_params(folder, f):
+    d = torch.load(os.path.join(DEMO, folder, f), weights_only=True, map_location="cpu")
+    out = {k: d[k] for k in PARAM_KEYS}
+    out["k_size"] = np.array(d["k_size"])
+    if "alpha" in d:
+        out["alpha"] = np.array(float(d["alpha"]))
+    return d, out
+
+
+def gen_lenia_family():
+    H, W = 48, 64
+    for folder, cls, tag, n in [
+        ("demo_lenia", REF.Lenia, "lenia", 5),
+        ("demo_macelenia", REF.MaCELenia, "mace", 5),
+        ("demo_macelenia_xchan", REF.MaCELeniaXChan, "xchan", 6),
+    ]:
+        for fi, f in enumerate(pick(folder, n)):
+            name = f[:-3]
+            d, raw = raw_params(folder, f)
+            params = REF.LeniaParams(from_file=os.path.join(DEMO, folder, f))
+            g = torch.Generator().manual_seed(1000 + fi)
+            s0 = torch.rand(1, 3, H, W, generator=g)
+            if tag != "lenia":
+                s0 = s0 * (torch.rand(1, 3, H, W, generator=g) < 0.6)  # some empty cells
+            auto = cls((H, W), params=params, state_init=s0.clone())
+            save(f"params_{tag}_{name}.npz", K=auto.k, mu_s=auto.mu, sigma_s=auto.sigma, weights_s=auto.weights, **raw)
+            extra = {}
+            if tag == "lenia":
+                auto.step()
+                # C=1 slice of the same file (BASELINE configs[1]: single-channel Lenia)
+                d1 = {k: (v[:, :1, :1] if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+                p1 = REF.LeniaParams(param_dict=d1, channels=1)
+                a1 = REF.Lenia((H, W), num_channels=1, params=p1, state_init=s0[:, :1].clone())
+                a1.step()
+                extra = dict(c1_out=a1.state, c1_K=a1.k, c1_mu=a1.mu, c1_sigma=a1.sigma, c1_weights=a1.weights)
+                aff = auto.state.new_zeros(0)
+            elif tag == "mace":
+                aff = auto._compute_affinity()
+                auto.step()
+            else:
+                aff = auto._compute_affinity()
+                auto.step()
+                extra = dict(b=np.array(float(auto.b)), alpha_used=np.array(float(auto.alpha)))
+            if tag == "mace":
+                extra = dict(b=np.array(float(auto.b)))
+            save(f"{tag}_{name}.npz", state_in=s0, state_out=auto.state, aff=aff, dt=np.array(auto.dt), **extra)
+
+    # realistic high-dynamic-range state: crop of a real saved MaCE-XChan state
+    f = "arborical_asbestosis.pt"
+    st = torch.load(os.path.join(DEMO, "demo_macelenia_xchan/state_saves/gilded_wok__state.pt"), weights_only=True, map_location="cpu")
+    full = st["state"]
+    crop = full[:, :, 150:150 + 64, 180:180 + 64].contiguous()
+    pd = {k: v for k, v in st.items() if k != "state"}
+    params = REF.LeniaParams(param_dict=pd)
+    auto = REF.MaCELeniaXChan((64, 64), params=params, state_init=crop.clone())
+    if "alpha" in pd:
+        auto.alpha = float(pd["alpha"])
+    aff = auto._compute_affinity()
+    auto.step()
+    raw = {k: pd[k] for k in PARAM_KEYS}
+    save("xchan_realstate.npz", state_in=crop, state_out=auto.state, aff=aff, K=auto.k, mu_s=auto.mu,
+         sigma_s=auto.sigma, weights_s=auto.weights, b=np.array(float(auto.b)),
+         alpha_used=np.array(float(auto.alpha)), k_size=np.array(pd["k_size"]), **raw)
+
+
+# ------------------------------------------------------------------ NCA
+def gen_nca():
+    folder = os.path.join(DEMO, "NCA_models")
+    for mi, f in enumerate(sorted(os.listdir(folder))):
+        name = f[:-3]
+        sd = torch.load(os.path.join(folder, f), map_location="cpu")["state_dict"]
+        model = REF.NCAModule(n_states=16, n_hidden=128)
+        model.load_model(os.path.join(folder, f))
+        model.eval()
+        B, H, W = 2, 24, 40
+        # world 0: dense random; world 1: grown from the all-ones seed pixel (sparse, exercises life masks)
+        g = torch.Generator().manual_seed(50 + mi)
+        dense = torch.rand(1, 16, H, W, generator=g)
+        grown = torch.zeros(1, 16, H, W)
+        grown[0, :, H // 2, W // 2] = 1.0
+        torch.manual_seed(77 + mi)
+        for _ in range(12):
+            grown = model(grown)
+        s0 = torch.cat([dense, grown], dim=0)
+        seed = 900 + mi
+        torch.manual_seed(seed)
+        out = model(s0.clone())
+        gm = torch.Generator().manual_seed(seed)
+        mask = torch.rand(B, 1, H, W, generator=gm) <= 0.5
+        save(f"nca_{name}.npz", W1=sd["computer.0.weight"], b1=sd["computer.0.bias"], W2=sd["computer.2.weight"],
+             b2=sd["computer.2.bias"], sobelkern=sd["sobel.sobelkern"], state_in=s0, mask=mask.to(torch.uint8),
+             state_out=out, seed=np.array(seed))
+
+
+if __name__ == "__main__":
+    gen_gol()
+    gen_lenia_family()
+    gen_nca()
