@@ -1,0 +1,165 @@
+/*
+ * b200ca.h -- C ABI of the B200-native (sm_100a) cellular-automaton step kernels.
+ *
+ * The reference (frotaur/PyCA) is pure Python + PyTorch and has NO foreign-function
+ * interface: its hot path is `Automaton.step()` of the model classes in
+ * `pyca/automata/models/`.  The entry points below are therefore what a binding
+ * for that path replaces, one per reference method (file:line relative to the PyCA
+ * tree).  The reference-side binding (a ctypes stub inside each `step()`) is shown
+ * in INTEGRATION.md; `pyca_b200/_lib.py` is that stub for this repository.
+ *
+ * Conventions
+ *   - `extern "C"`, plain pointers and sizes; no torch types.
+ *   - Pointers without the `h_` prefix are DEVICE pointers owned by the caller, valid on
+ *     the current CUDA device; `h_` pointers are HOST buffers (the `*_host` entry points
+ *     do their own H2D/D2H copies and are what `e2e` in bench.py times).
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).
+ *     Every call only enqueues work on that stream unless documented otherwise.
+ *   - Return value: 0 on success; >0 a `cudaError_t`; <0 a B200CA_E_* code.  The text
+ *     of the last error on the calling thread is `b200ca_last_error()`.
+ *   - No allocation per call: the library keeps small per-device caches (TMA tensor maps,
+ *     scratch) released by `b200ca_shutdown()`.
+ *   - There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef B200CA_H
+#define B200CA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200CA_VERSION 100
+
+#define B200CA_E_BADARG (-1)   /* inconsistent sizes / null pointers / unsupported shape */
+#define B200CA_E_NODEVICE (-2) /* no sm_100 CUDA device */
+#define B200CA_E_DRIVER (-3)   /* driver entry point (TMA descriptor encode) unavailable/failed */
+#define B200CA_E_UNSUPPORTED (-4)
+
+int b200ca_version(void);
+const char *b200ca_last_error(void);
+/* sm count / compute capability of the current device (error if none). */
+int b200ca_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* frees cached descriptors/scratch of all devices. */
+int b200ca_shutdown(void);
+
+/* ------------------------------------------------------------------------------------
+ * Game of Life / outer-totalistic CA2D.   Replaces CA2D.step  (models/ca2d.py:195-209,
+ * get_nth_bit :221-225).  The world lives bit-packed: 32 cells per uint32, cell x of row y
+ * is bit (x & 31) of word  y*stride_words + (x >> 5);  bits at x >= W are kept zero.
+ * ---------------------------------------------------------------------------------- */
+int b200ca_gol_words_per_row(int W); /* ceil(W/32) */
+
+/* elem_bytes in {1,2,4,8}: uint8/bool, int16 (world after reset(), ca2d.py:227-246), int32 (world
+ * after any step, ca2d.py:209), int64.  A cell is alive iff its value == 1 (ca2d.py:208). */
+int b200ca_gol_pack(const void *world, int elem_bytes, uint32_t *bits, int H, int W, int stride_words, void *stream);
+int b200ca_gol_unpack(const uint32_t *bits, void *world, int elem_bytes, int H, int W, int stride_words, void *stream);
+
+/* One step.  s_mask/b_mask: 9-bit survive/birth masks, bit n set = rule holds for n live
+ * neighbours (ca2d.py:80-88; Life = S 0b1100, B 0b1000).  vert_open = 0: torus (reference
+ * semantics);  1: rows outside [0,H) are dead (used on a row slab that carries ghost rows;
+ * columns always wrap).  bits_in != bits_out. */
+int b200ca_gol_step(const uint32_t *bits_in, uint32_t *bits_out, int H, int W, int stride_words, uint32_t s_mask,
+                    uint32_t b_mask, int vert_open, void *stream);
+/* nsteps steps ping-ponging a<->b; the result is in `a` if nsteps is even, else in `b`. */
+int b200ca_gol_run(uint32_t *a, uint32_t *b, int H, int W, int stride_words, uint32_t s_mask, uint32_t b_mask,
+                   int vert_open, int nsteps, void *stream);
+/* population count of the packed world into *count (device, uint64). */
+int b200ca_gol_population(const uint32_t *bits, int H, int W, int stride_words, unsigned long long *count, void *stream);
+/* fills the packed world with Bernoulli(1/2) bits from a counter-based generator (synthetic
+ * worlds too large to build as int32).  row0 offsets the row counter so
+ * slabs of one world can be generated independently. */
+int b200ca_gol_random_fill(uint32_t *bits, int H, int W, int stride_words, uint64_t seed, int64_t row0, void *stream);
+/* HOST world in, HOST world out (int32 0/1, H*W each), nsteps steps; copies inside. */
+int b200ca_gol_run_host(const int32_t *h_world_in, int32_t *h_world_out, int H, int W, uint32_t s_mask, uint32_t b_mask,
+                        int nsteps);
+
+/* ------------------------------------------------------------------------------------
+ * Lenia family.  State planes live in a FRAMED layout so the periodic wrap (and a row-slab
+ * neighbour's rows) are plain reads:  plane (b,c) has (H + 2*B200CA_FRAME) rows of `pitch`
+ * floats; cell (y,x) is at  ((b*C + c)*(H+2F) + y + F)*pitch + x + F.  The frame holds the
+ * wrapped copies of the opposite edges; the step kernels keep it current for their output.
+ * ---------------------------------------------------------------------------------- */
+#define B200CA_FRAME 16
+int b200ca_frame_pitch(int W);                 /* floats per framed row: roundup(W + 2F, 4) */
+int64_t b200ca_frame_elems(int B, int C, int H, int W); /* floats in a framed (B,C,H,W) tensor */
+/* dense (B,C,H,W) -> framed (interior + wrapped frame) and back.  `wrap_rows` = 0 leaves the top/bottom
+ * frame rows untouched (row slab: they are ghost rows owned by the neighbours). */
+int b200ca_frame_load(const float *dense, float *framed, int B, int C, int H, int W, int wrap_rows, void *stream);
+int b200ca_frame_store(const float *framed, float *dense, int B, int C, int H, int W, void *stream);
+/* re-derives the frame of `framed` from its interior (after in-place edits of the interior). */
+int b200ca_frame_refresh(float *framed, int B, int C, int H, int W, int wrap_rows, void *stream);
+
+/* Kernel preparation (cold; called from update_params, lenia.py:143-205).  K is the reference's
+ * `self.k` (B, C*k_mult, C, ks, ks) fp32 (lenia.py:202, :314-362), ks odd <= 31.  Kprep receives
+ * b200ca_lenia_kprep_elems() floats: the D4-symmetric kernel centred in 31x31 and folded to the
+ * rows dy >= 0.  Returns B200CA_E_UNSUPPORTED if K is not symmetric under row reversal. */
+int64_t b200ca_lenia_kprep_elems(int B, int C, int k_mult);
+int b200ca_lenia_prepare_kernel(const float *K, float *Kprep, int B, int C, int k_mult, int ks, void *stream);
+
+#define B200CA_MODE_LENIA 0 /* out = clamp(state + dt * dx, 0, 1)            lenia.py:430-451        */
+#define B200CA_MODE_AFF 1   /* out = dx (affinity, framed with pad>=2)        macelenia.py:122-159    */
+
+/* Direct (spatial) convolution + growth + weighted source sum (+ Euler/clamp).
+ *   U[b,i*km+m,j] = K[b,i*km+m,j] (*) state[b,i]   (periodic; lenia.py:453-469 computes it by FFT)
+ *   G = 2*exp(-((U-mu)^2/sigma^2)/2) - 1           (lenia.py:423-426)
+ *   dx[b,j] = sum_{i,m} weights[b,i*km+m,j] * G    (lenia.py:444-446)
+ * state_in/state_out: framed (B,C,H,W); mu/sigma/weights: (B, C*k_mult, C) fp32 device.
+ * row_wrap = 1: the kernel also maintains the top/bottom frame of `out` (torus);
+ *            0: top/bottom frame rows of `out` are left to the caller (row slab / halo exchange).
+ * tile_row_begin/end: restricts the launch to output tile-rows [begin,end) in units of
+ *            b200ca_lenia_tile_rows() rows (0,0 = all) so slab boundaries can be issued first. */
+int b200ca_lenia_tile_rows(int H, int W, int B, int C);
+int b200ca_lenia_step(const float *state_in, float *state_out, const float *Kprep, const float *mu, const float *sigma,
+                      const float *weights, int B, int C, int k_mult, int H, int W, float dt, int mode, int row_wrap,
+                      int tile_row_begin, int tile_row_end, void *stream);
+
+/* Mass-conserving redistribution (+ optional cross-channel mixing).  Replaces
+ * MaCELenia._mace_step (macelenia.py:89-120) after the affinity, and
+ * MaCELeniaXChan._cross_chan_step (mace_lenia_xchan.py:68-76) when alpha_on != 0:
+ *   E = exp(beta*Aff);  Z = sum3x3(E);  A' = E * sum3x3(A / Z);
+ *   P = softmax_c(beta*Aff);  A'' = A' - alpha * (A' - (sum_c A') * P).
+ * aff: framed (B,C,H,W) written by b200ca_lenia_step(mode=AFF) (frame valid to 2 cells). */
+int b200ca_mace_redistribute(const float *state_in, const float *aff, float *state_out, int B, int C, int H, int W,
+                             float beta, int alpha_on, float alpha, int row_wrap, void *stream);
+
+/* sum over H*W of every (b,c) plane of a framed tensor into mass[b*C+c] (double, device): total_mass()
+ * (macelenia.py:421-428). */
+int b200ca_frame_mass(const float *framed, double *mass, int B, int C, int H, int W, void *stream);
+
+/* HOST dense state in/out, device parameters prepared by the caller; nsteps Lenia (mode 0) or
+ * MaCE (mode 1) / MaCE-XChan (mode 2) steps with the copies inside the call. */
+int b200ca_lenia_run_host(const float *h_state_in, float *h_state_out, const float *Kprep, const float *mu,
+                          const float *sigma, const float *weights, int B, int C, int k_mult, int H, int W, float dt,
+                          int family, float beta, float alpha, int nsteps);
+
+/* ------------------------------------------------------------------------------------
+ * Neural CA inference.  Replaces NCAModule.forward for one step (models/nca.py:239-263):
+ * SobelConv perception (:328-344), Linear-ReLU-Linear (:205-208), sigmoid * update mask,
+ * life masks (:226-237), clamp.  state: dense (B,n,H,W) fp32 NCHW, n == 16, hidden == 128.
+ * ---------------------------------------------------------------------------------- */
+/* Weight preparation (cold; after load_model, nca.py:53-64).  W1 (hid, 3n), b1 (hid), W2 (n, hid), b2 (n)
+ * as in the checkpoint's state_dict.  Wprep gets b200ca_nca_wprep_bytes() bytes (folded W1 columns,
+ * split-precision copies for the tensor-core path). */
+int64_t b200ca_nca_wprep_bytes(int n, int hid);
+int b200ca_nca_prepare_weights(const float *W1, const float *b1, const float *W2, const float *b2, void *Wprep, int n,
+                               int hid, void *stream);
+/* scratch for the post-update alive bits: bytes needed for (B,H,W). */
+int64_t b200ca_nca_scratch_bytes(int B, int H, int W);
+
+#define B200CA_NCA_SIMT 0  /* fp32 FMA MLP (reference-grade arithmetic, slow)             */
+#define B200CA_NCA_TC 1    /* tcgen05 / TMEM MLP, split-tf32 (fp32-equivalent accuracy)    */
+
+/* update_mask: (B,H,W) uint8, non-zero = cell updates (the reference's `torch.rand(B,1,H,W) <= 0.5`,
+ * nca.py:256);  NULL = draw it in-kernel from Philox4x32-10(seed, step, cell).  */
+int b200ca_nca_step(const float *state_in, float *state_out, const void *Wprep, const uint8_t *update_mask,
+                    uint64_t seed, uint64_t step_index, void *scratch, int B, int n, int hid, int H, int W, int impl,
+                    void *stream);
+int b200ca_nca_run_host(const float *h_state_in, float *h_state_out, const void *Wprep, const uint8_t *h_update_mask,
+                        uint64_t seed, int B, int n, int hid, int H, int W, int impl, int nsteps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CA_H */

@@ -1,0 +1,409 @@
+// Bit-packed outer-totalistic 2-state CA (Game of Life family) for sm_100a.
+//
+// Replaces CA2D.step (pyca/automata/models/ca2d.py:195-209): the reference builds 8 rolled
+// copies of an int32 world, adds them and selects bit `count` of the survive / birth mask
+// (~22 elementwise passes, ~200 B/cell of traffic).  Here the world is 1 bit/cell:
+//   * one thread owns VEC consecutive 32-cell words of a row and walks RPT rows downwards,
+//     keeping a 3-row sliding window of bit-sliced horizontal sums in registers;
+//   * west/east neighbours come from funnel shifts of (left word, word, right word); the left/
+//     right words of a thread's group come from the adjacent lanes by warp shuffle, only the
+//     warp-edge lanes touch memory for them;
+//   * the 8-neighbour count is a bit-sliced adder tree (LOP3), the rule is evaluated on the
+//     4 count bit-planes (2 LOP3 for Life, a mux tree for arbitrary 9-bit S/B masks).
+// Algorithmic traffic: 1 bit read + 1 bit written per cell (0.25 B/cell/step).
+#include <algorithm>
+#include "common.cuh"
+
+namespace b200ca {
+
+// 32 cells of the periodic row starting at (possibly negative / >= W) cell index c0; generic slow path
+// used only at the row ends when W is not a multiple of 32.
+__device__ __noinline__ uint32_t gol_gather32(const uint32_t *__restrict__ row, int W, long long c0) {
+    int c = (int)(((c0 % W) + W) % W);
+    uint32_t out = 0;
+    int filled = 0;
+    while (filled < 32) {
+        int wi = c >> 5, off = c & 31;
+        int take = min(min(32 - off, W - c), 32 - filled);
+        uint32_t bits = row[wi] >> off;
+        if (take < 32) bits &= (1u << take) - 1u;
+        out |= bits << filled;
+        filled += take;
+        c += take;
+        if (c == W) c = 0;
+    }
+    return out;
+}
+
+struct GolGeom {
+    int H, W, stride, wpr;  // wpr = words per row
+    int aligned;            // W % 32 == 0
+    uint32_t last_mask;     // valid bits of the last word of a row
+    int vert_open;
+};
+
+// logical word j (j in [-1, wpr]) of row `row` of the x-periodic world
+__device__ __forceinline__ uint32_t gol_fetch(const uint32_t *__restrict__ row, const GolGeom &g, int j) {
+    if (g.aligned) {
+        int jj = j < 0 ? j + g.wpr : (j >= g.wpr ? j - g.wpr : j);
+        return __ldg(row + jj);
+    }
+    if (j >= 0 && j < g.wpr - 1) return __ldg(row + j);
+    if (j >= g.wpr) return 0u;  // only feeds bits beyond W, which are masked off
+    return gol_gather32(row, g.W, (long long)j * 32);
+}
+
+template <int VEC>
+struct RowSums {
+    uint32_t c[VEC];   // centre cells
+    uint32_t s0[VEC], s1[VEC];  // west+centre+east (2-bit)
+    uint32_t t0[VEC], t1[VEC];  // west+east (2-bit)
+};
+
+template <int VEC>
+__device__ __forceinline__ void gol_load_row(RowSums<VEC> &R, const uint32_t *__restrict__ in, const GolGeom &g, int r,
+                                             int j0, bool valid, int lane) {
+    uint32_t c[VEC];
+    bool live_row = true;
+    int rr = r;
+    if (g.vert_open) {
+        live_row = (r >= 0 && r < g.H);
+    } else {
+        rr = r < 0 ? r + g.H : (r >= g.H ? r - g.H : r);
+    }
+    const uint32_t *row = in + (size_t)rr * g.stride;
+    const bool ld = valid && live_row;
+    if (VEC == 4) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (ld) v = __ldg(reinterpret_cast<const uint4 *>(row + j0));
+        c[0] = v.x; c[1 % VEC] = v.y; c[2 % VEC] = v.z; c[3 % VEC] = v.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) c[k] = ld ? gol_fetch(row, g, j0 + k) : 0u;
+    }
+    uint32_t left = __shfl_up_sync(0xffffffffu, c[VEC - 1], 1);
+    uint32_t right = __shfl_down_sync(0xffffffffu, c[0], 1);
+    if (lane == 0 || j0 == 0) left = ld ? gol_fetch(row, g, j0 - 1) : 0u;
+    if (lane == 31 || j0 + VEC >= g.wpr) right = ld ? gol_fetch(row, g, j0 + VEC) : 0u;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        uint32_t L = k == 0 ? left : c[k - 1];
+        uint32_t Rw = k == VEC - 1 ? right : c[k + 1];
+        uint32_t w = __funnelshift_l(L, c[k], 1);   // bit i <- cell i-1
+        uint32_t e = __funnelshift_r(c[k], Rw, 1);  // bit i <- cell i+1
+        R.c[k] = c[k];
+        R.t0[k] = w ^ e;
+        R.t1[k] = w & e;
+        R.s0[k] = R.t0[k] ^ c[k];
+        R.s1[k] = R.t1[k] | (R.t0[k] & c[k]);
+    }
+}
+
+struct RuleMasks {
+    uint32_t s[9], b[9];  // 0 or ~0
+};
+
+template <bool LIFE>
+__device__ __forceinline__ uint32_t gol_rule(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, uint32_t m0, uint32_t m1,
+                                             uint32_t c, const RuleMasks &rm) {
+    // (a1a0) + (b1b0) -> x2x1x0 ; + (m1m0) -> y3y2y1y0
+    uint32_t x0 = a0 ^ b0, k0 = a0 & b0;
+    uint32_t x1 = a1 ^ b1 ^ k0;
+    uint32_t x2 = (a1 & b1) | (k0 & (a1 ^ b1));
+    uint32_t y0 = x0 ^ m0, d0 = x0 & m0;
+    uint32_t y1 = x1 ^ m1 ^ d0;
+    uint32_t d1 = (x1 & m1) | (d0 & (x1 ^ m1));
+    uint32_t y2 = x2 ^ d1;
+    if (LIFE) {
+        // count==3 | (alive & count==2); count==8 has y1==0 so y3 is not needed
+        return y1 & ~y2 & (y0 | c);
+    } else {
+        uint32_t y3 = x2 & d1;
+        uint32_t m[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) m[k] = (c & rm.s[k]) | (~c & rm.b[k]);
+        uint32_t q0 = (y0 & m[1]) | (~y0 & m[0]);
+        uint32_t q1 = (y0 & m[3]) | (~y0 & m[2]);
+        uint32_t q2 = (y0 & m[5]) | (~y0 & m[4]);
+        uint32_t q3 = (y0 & m[7]) | (~y0 & m[6]);
+        uint32_t h0 = (y1 & q1) | (~y1 & q0);
+        uint32_t h1 = (y1 & q3) | (~y1 & q2);
+        uint32_t f = (y2 & h1) | (~y2 & h0);
+        return (y3 & m[8]) | (~y3 & f);
+    }
+}
+
+template <int VEC, int RPT, bool LIFE>
+__global__ void __launch_bounds__(128) gol_step_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, GolGeom g,
+                                                        uint32_t s_mask, uint32_t b_mask) {
+    const int lane = threadIdx.x & 31;
+    const int unit = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j0 = unit * VEC;
+    const bool valid = j0 < g.wpr;
+    const int r0 = blockIdx.y * RPT;
+    RuleMasks rm;
+    if (!LIFE) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            rm.s[k] = ((s_mask >> k) & 1u) ? 0xffffffffu : 0u;
+            rm.b[k] = ((b_mask >> k) & 1u) ? 0xffffffffu : 0u;
+        }
+    }
+    RowSums<VEC> A, Bc, Cn;
+    gol_load_row<VEC>(A, in, g, r0 - 1, j0, valid, lane);
+    gol_load_row<VEC>(Bc, in, g, r0, j0, valid, lane);
+#pragma unroll 4
+    for (int i = 0; i < RPT; ++i) {
+        const int r = r0 + i;
+        if (r >= g.H) break;  // uniform across the block
+        gol_load_row<VEC>(Cn, in, g, r + 1, j0, valid, lane);
+        uint32_t o[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            o[k] = gol_rule<LIFE>(A.s0[k], A.s1[k], Cn.s0[k], Cn.s1[k], Bc.t0[k], Bc.t1[k], Bc.c[k], rm);
+            if (j0 + k == g.wpr - 1) o[k] &= g.last_mask;
+        }
+        if (valid) {
+            uint32_t *orow = out + (size_t)r * g.stride + j0;
+            if (VEC == 4) {
+                *reinterpret_cast<uint4 *>(orow) = make_uint4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k)
+                    if (j0 + k < g.wpr) orow[k] = o[k];
+            }
+        }
+        A = Bc;
+        Bc = Cn;
+    }
+}
+
+// ---- pack / unpack / population / random fill ---------------------------------------------------
+template <typename T>
+__global__ void gol_pack_kernel(const T *__restrict__ world, uint32_t *__restrict__ bits, int H, int W, int stride, int wpr) {
+    // one warp packs 32 consecutive words of a row (1024 cells): 32 coalesced reads + ballots
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int groups = ceil_div(wpr, 32);
+    const int y = warp / groups;
+    if (y >= H) return;
+    const int wg = (warp % groups) * 32;
+    const T *row = world + (size_t)y * W;
+    uint32_t mine = 0;
+    for (int k = 0; k < 32; ++k) {
+        int x = (wg + k) * 32 + lane;
+        bool alive = (x < W) && (row[x] == (T)1);
+        uint32_t b = __ballot_sync(0xffffffffu, alive);
+        if (k == lane) mine = b;
+    }
+    if (wg + lane < wpr) bits[(size_t)y * stride + wg + lane] = mine;
+}
+
+template <typename T>
+__global__ void gol_unpack_kernel(const uint32_t *__restrict__ bits, T *__restrict__ world, int H, int W, int stride) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W) return;
+    uint32_t wv = __ldg(bits + (size_t)y * stride + (x >> 5));
+    world[(size_t)y * W + x] = (T)((wv >> (x & 31)) & 1u);
+}
+
+__global__ void gol_population_kernel(const uint32_t *__restrict__ bits, int H, int wpr, int stride,
+                                      unsigned long long *__restrict__ count) {
+    unsigned long long local = 0;
+    const size_t total = (size_t)H * wpr;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t y = i / wpr, j = i % wpr;
+        local += __popc(bits[y * stride + j]);
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    __shared__ unsigned long long sm[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sm[wid] = local;
+    __syncthreads();
+    if (wid == 0) {
+        local = lane < (blockDim.x >> 5) ? sm[lane] : 0ull;
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if (lane == 0) atomicAdd(count, local);
+    }
+}
+
+__global__ void gol_random_fill_kernel(uint32_t *__restrict__ bits, int H, int wpr, int stride, uint32_t last_mask,
+                                       uint64_t seed, int64_t row0) {
+    // one Philox call -> 4 words
+    const int quads = ceil_div(wpr, 4);
+    const size_t total = (size_t)H * quads;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t y = i / quads;
+        int q = (int)(i % quads);
+        uint32_t r[4];
+        Philox::gen(seed, (uint64_t)q, (uint64_t)(row0 + (int64_t)y), r);
+        for (int k = 0; k < 4; ++k) {
+            int j = q * 4 + k;
+            if (j < wpr) {
+                uint32_t v = r[k];
+                if (j == wpr - 1) v &= last_mask;
+                bits[y * stride + j] = v;
+            }
+        }
+    }
+}
+
+static int make_geom(GolGeom &g, int H, int W, int stride, int vert_open) {
+    B200CA_REQUIRE(H >= 1 && W >= 1, "gol: bad world size %dx%d", H, W);
+    g.H = H;
+    g.W = W;
+    g.wpr = ceil_div(W, 32);
+    B200CA_REQUIRE(stride >= g.wpr, "gol: stride_words %d < words per row %d", stride, g.wpr);
+    g.stride = stride;
+    g.aligned = (W % 32 == 0);
+    int nb = W - 32 * (g.wpr - 1);
+    g.last_mask = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
+    g.vert_open = vert_open ? 1 : 0;
+    return 0;
+}
+
+template <int VEC, int RPT>
+static int launch_step(const uint32_t *in, uint32_t *out, const GolGeom &g, uint32_t s, uint32_t b, cudaStream_t st) {
+    const int units = ceil_div(g.wpr, VEC);
+    int bx = units >= 128 ? 128 : ceil_div(units, 32) * 32;
+    dim3 grid(ceil_div(units, bx), ceil_div(g.H, RPT));
+    if (s == 0b1100u && b == 0b1000u)
+        gol_step_kernel<VEC, RPT, true><<<grid, bx, 0, st>>>(in, out, g, s, b);
+    else
+        gol_step_kernel<VEC, RPT, false><<<grid, bx, 0, st>>>(in, out, g, s, b);
+    B200CA_LAUNCH_CHECK("gol_step_kernel");
+    return 0;
+}
+
+static int gol_step_impl(const uint32_t *in, uint32_t *out, int H, int W, int stride, uint32_t s, uint32_t b, int vert_open,
+                         cudaStream_t st) {
+    GolGeom g;
+    int rc = make_geom(g, H, W, stride, vert_open);
+    if (rc) return rc;
+    B200CA_REQUIRE(in && out && in != out, "gol_step: null or aliased buffers");
+    B200CA_REQUIRE(s < 512 && b < 512, "gol_step: rule masks are 9-bit");
+    const bool vec4 = g.aligned && (g.wpr % 4 == 0) && (stride % 4 == 0) && ((((uintptr_t)in) | ((uintptr_t)out)) % 16 == 0);
+    // enough row bands to fill the machine: 16 rows per thread for big worlds, 4 for small ones
+    const long long units = (long long)ceil_div(g.wpr, vec4 ? 4 : 1) * ceil_div(H, 16);
+    const bool big = units >= (long long)num_sms() * 128 * 8;
+    if (vec4) return big ? launch_step<4, 16>(in, out, g, s, b, st) : launch_step<4, 4>(in, out, g, s, b, st);
+    return big ? launch_step<1, 16>(in, out, g, s, b, st) : launch_step<1, 4>(in, out, g, s, b, st);
+}
+
+}  // namespace b200ca
+
+using namespace b200ca;
+
+extern "C" int b200ca_gol_words_per_row(int W) { return ceil_div(W, 32); }
+
+extern "C" int b200ca_gol_pack(const void *world, int elem_bytes, uint32_t *bits, int H, int W, int stride_words, void *stream) {
+    GolGeom g;
+    int rc = make_geom(g, H, W, stride_words, 0);
+    if (rc) return rc;
+    B200CA_REQUIRE(world && bits, "gol_pack: null pointer");
+    const int groups = ceil_div(g.wpr, 32);
+    const long long warps = (long long)H * groups;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)ceil_div64(warps * 32, threads);
+    cudaStream_t st = as_stream(stream);
+    switch (elem_bytes) {
+        case 1: gol_pack_kernel<uint8_t><<<blocks, threads, 0, st>>>((const uint8_t *)world, bits, H, W, stride_words, g.wpr); break;
+        case 2: gol_pack_kernel<int16_t><<<blocks, threads, 0, st>>>((const int16_t *)world, bits, H, W, stride_words, g.wpr); break;
+        case 4: gol_pack_kernel<int32_t><<<blocks, threads, 0, st>>>((const int32_t *)world, bits, H, W, stride_words, g.wpr); break;
+        case 8: gol_pack_kernel<long long><<<blocks, threads, 0, st>>>((const long long *)world, bits, H, W, stride_words, g.wpr); break;
+        default: B200CA_REQUIRE(false, "gol_pack: elem_bytes %d not in {1,2,4,8}", elem_bytes);
+    }
+    B200CA_LAUNCH_CHECK("gol_pack_kernel");
+    return 0;
+}
+
+extern "C" int b200ca_gol_unpack(const uint32_t *bits, void *world, int elem_bytes, int H, int W, int stride_words, void *stream) {
+    GolGeom g;
+    int rc = make_geom(g, H, W, stride_words, 0);
+    if (rc) return rc;
+    B200CA_REQUIRE(world && bits, "gol_unpack: null pointer");
+    dim3 grid(ceil_div(W, 256), H);
+    cudaStream_t st = as_stream(stream);
+    switch (elem_bytes) {
+        case 1: gol_unpack_kernel<uint8_t><<<grid, 256, 0, st>>>(bits, (uint8_t *)world, H, W, stride_words); break;
+        case 2: gol_unpack_kernel<int16_t><<<grid, 256, 0, st>>>(bits, (int16_t *)world, H, W, stride_words); break;
+        case 4: gol_unpack_kernel<int32_t><<<grid, 256, 0, st>>>(bits, (int32_t *)world, H, W, stride_words); break;
+        case 8: gol_unpack_kernel<long long><<<grid, 256, 0, st>>>(bits, (long long *)world, H, W, stride_words); break;
+        default: B200CA_REQUIRE(false, "gol_unpack: elem_bytes %d not in {1,2,4,8}", elem_bytes);
+    }
+    B200CA_LAUNCH_CHECK("gol_unpack_kernel");
+    return 0;
+}
+
+extern "C" int b200ca_gol_step(const uint32_t *bits_in, uint32_t *bits_out, int H, int W, int stride_words, uint32_t s_mask,
+                               uint32_t b_mask, int vert_open, void *stream) {
+    return gol_step_impl(bits_in, bits_out, H, W, stride_words, s_mask, b_mask, vert_open, as_stream(stream));
+}
+
+extern "C" int b200ca_gol_run(uint32_t *a, uint32_t *b, int H, int W, int stride_words, uint32_t s_mask, uint32_t b_mask,
+                              int vert_open, int nsteps, void *stream) {
+    B200CA_REQUIRE(nsteps >= 0, "gol_run: nsteps < 0");
+    uint32_t *src = a, *dst = b;
+    for (int i = 0; i < nsteps; ++i) {
+        int rc = gol_step_impl(src, dst, H, W, stride_words, s_mask, b_mask, vert_open, as_stream(stream));
+        if (rc) return rc;
+        uint32_t *t = src;
+        src = dst;
+        dst = t;
+    }
+    return 0;
+}
+
+extern "C" int b200ca_gol_population(const uint32_t *bits, int H, int W, int stride_words, unsigned long long *count, void *stream) {
+    GolGeom g;
+    int rc = make_geom(g, H, W, stride_words, 0);
+    if (rc) return rc;
+    B200CA_REQUIRE(bits && count, "gol_population: null pointer");
+    cudaStream_t st = as_stream(stream);
+    B200CA_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned long long), st));
+    const long long total = (long long)H * g.wpr;
+    int blocks = (int)std::min<long long>(ceil_div64(total, 256), (long long)num_sms() * 8);
+    gol_population_kernel<<<blocks, 256, 0, st>>>(bits, H, g.wpr, stride_words, count);
+    B200CA_LAUNCH_CHECK("gol_population_kernel");
+    return 0;
+}
+
+extern "C" int b200ca_gol_random_fill(uint32_t *bits, int H, int W, int stride_words, uint64_t seed, int64_t row0, void *stream) {
+    GolGeom g;
+    int rc = make_geom(g, H, W, stride_words, 0);
+    if (rc) return rc;
+    B200CA_REQUIRE(bits, "gol_random_fill: null pointer");
+    const long long total = (long long)H * ceil_div(g.wpr, 4);
+    int blocks = (int)std::min<long long>(ceil_div64(total, 256), (long long)num_sms() * 16);
+    gol_random_fill_kernel<<<blocks, 256, 0, as_stream(stream)>>>(bits, H, g.wpr, stride_words, g.last_mask, seed, row0);
+    B200CA_LAUNCH_CHECK("gol_random_fill_kernel");
+    return 0;
+}
+
+extern "C" int b200ca_gol_run_host(const int32_t *h_world_in, int32_t *h_world_out, int H, int W, uint32_t s_mask,
+                                   uint32_t b_mask, int nsteps) {
+    B200CA_REQUIRE(h_world_in && h_world_out && H >= 1 && W >= 1 && nsteps >= 0, "gol_run_host: bad arguments");
+    const int wpr = ceil_div(W, 32);
+    const int stride = ceil_div(wpr, 4) * 4;
+    int32_t *d_world = nullptr;
+    uint32_t *d_a = nullptr, *d_b = nullptr;
+    const size_t wbytes = (size_t)H * W * sizeof(int32_t), bbytes = (size_t)H * stride * sizeof(uint32_t);
+    int rc = 0;
+    cudaStream_t st = 0;
+    do {
+        if ((rc = check_cuda(cudaMalloc(&d_world, wbytes), "cudaMalloc world"))) break;
+        if ((rc = check_cuda(cudaMalloc(&d_a, bbytes), "cudaMalloc bits"))) break;
+        if ((rc = check_cuda(cudaMalloc(&d_b, bbytes), "cudaMalloc bits"))) break;
+        if ((rc = check_cuda(cudaMemcpyAsync(d_world, h_world_in, wbytes, cudaMemcpyHostToDevice, st), "H2D"))) break;
+        if ((rc = b200ca_gol_pack(d_world, 4, d_a, H, W, stride, st))) break;
+        if ((rc = b200ca_gol_run(d_a, d_b, H, W, stride, s_mask, b_mask, 0, nsteps, st))) break;
+        if ((rc = b200ca_gol_unpack((nsteps & 1) ? d_b : d_a, d_world, 4, H, W, stride, st))) break;
+        if ((rc = check_cuda(cudaMemcpyAsync(h_world_out, d_world, wbytes, cudaMemcpyDeviceToHost, st), "D2H"))) break;
+        rc = check_cuda(cudaStreamSynchronize(st), "sync");
+    } while (0);
+    cudaFree(d_world);
+    cudaFree(d_a);
+    cudaFree(d_b);
+    return rc;
+}

@@ -1,0 +1,322 @@
+"""B200 drop-ins for PyCA's Lenia family: ``Lenia`` (pyca/automata/models/lenia/lenia.py),
+``MaCELenia`` (lenia/macelenia.py) and ``MaCELeniaXChan`` (lenia/mace_lenia_xchan.py).
+
+Same constructor signatures, attributes (``state``, ``mu``, ``sigma``, ``weights``, ``k``, ``dt``,
+``b``, ``alpha``, ``frames``) and methods (``step``, ``draw``, ``update_params``, ``mass``,
+``total_mass``).  Cold code -- parameter loading, sanitising, kernel construction -- stays torch on
+the host side (``lenia_params.py``); ``step()`` is CUDA through the C ABI:
+
+* Lenia.step (lenia.py:430-451)                  -> b200ca_lenia_step(mode=LENIA)
+* MaCELenia.step (macelenia.py:72-120)           -> b200ca_lenia_step(mode=AFF) + b200ca_mace_redistribute
+* MaCELeniaXChan.step (mace_lenia_xchan.py:59-76)-> same with alpha_on
+
+State ownership: the reference exposes ``self.state`` (B,C,H,W) as a public tensor that event handlers
+mutate in place between steps (lenia.py:681-690).  Here the state lives in two FRAMED device buffers
+(interior + 16-cell periodic frame, see include/b200ca.h); ``self.state`` is a strided view of the
+current buffer's interior.  In-place edits are detected through the view's version counter (the frame
+is refreshed before the next step); assigning a new tensor makes the next step load it.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+
+import torch
+
+from . import _lib
+from .automaton import Automaton
+from .lenia_params import LeniaParams, compute_kernel
+
+F = _lib.FRAME
+
+
+class FramedState:
+    """Two framed (B,C,H,W) fp32 device buffers with ping-pong and an interior view."""
+
+    def __init__(self, B, C, H, W, device, wrap_rows=True):
+        self.B, self.C, self.H, self.W = int(B), int(C), int(H), int(W)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.B200CAError(f"Lenia-family automata need a CUDA device (got {device}); there is no CPU path")
+        L = _lib.lib()
+        self.pitch = L.b200ca_frame_pitch(self.W)
+        self.rows = self.H + 2 * F
+        self.wrap_rows = wrap_rows
+        self.bufs = [torch.zeros((self.B, self.C, self.rows, self.pitch), dtype=torch.float32, device=self.device)
+                     for _ in range(2)]
+        self.cur = 0
+        self._view = None
+        self._view_version = -1
+
+    def _stream(self):
+        return _lib.current_stream(self.device)
+
+    @property
+    def buf(self):
+        return self.bufs[self.cur]
+
+    @property
+    def other(self):
+        return self.bufs[self.cur ^ 1]
+
+    def swap(self):
+        self.cur ^= 1
+        self._view = None
+
+    def view(self) -> torch.Tensor:
+        if self._view is None:
+            self._view = self.buf[:, :, F:F + self.H, F:F + self.W]
+            self._view_version = self._view._version
+        return self._view
+
+    def load_dense(self, dense: torch.Tensor):
+        d = dense.to(device=self.device, dtype=torch.float32).contiguous()
+        if tuple(d.shape) != (self.B, self.C, self.H, self.W):
+            raise _lib.B200CAError(f"state shape {tuple(d.shape)} != {(self.B, self.C, self.H, self.W)}")
+        with torch.cuda.device(self.device):
+            _lib.call("b200ca_frame_load", _lib.ptr(d), _lib.ptr(self.buf), self.B, self.C, self.H, self.W,
+                      1 if self.wrap_rows else 0, self._stream())
+        self._view = None
+
+    def refresh_if_edited(self):
+        """Re-derives the frame when the interior view was mutated in place since the last step."""
+        if self._view is not None and self._view._version != self._view_version:
+            with torch.cuda.device(self.device):
+                _lib.call("b200ca_frame_refresh", _lib.ptr(self.buf), self.B, self.C, self.H, self.W,
+                          1 if self.wrap_rows else 0, self._stream())
+            self._view_version = self._view._version
+
+    def dense(self) -> torch.Tensor:
+        return self.view().contiguous()
+
+    def mass(self) -> torch.Tensor:
+        out = torch.zeros((self.B, self.C), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.call("b200ca_frame_mass", _lib.ptr(self.buf), _lib.ptr(out), self.B, self.C, self.H, self.W, self._stream())
+        return out
+
+
+class Lenia(Automaton):
+    """
+    Multi-channel lenia automaton. A multi-colored GoL-inspired continuous automaton. Introduced by Bert Chan.
+    (B200 step: direct TMA-tiled convolution fused with growth, channel sum, Euler step and clamp.)
+    """
+
+    def __init__(self, size, dt=0.1, num_channels=3, params=None, state_init=None, device="cuda",
+                 interest_files=None, save_dir="."):
+        if len(size) == 2:
+            size = (1,) + tuple(size)
+        Automaton.__init__(self, size[1:], device)
+        self.batch = size[0]
+        self.h, self.w = size[1:]
+        self.C = num_channels
+        self.dt = dt
+        if params is None:
+            raise _lib.B200CAError("random parameter generation is not part of the step path: pass params= (LeniaParams, "
+                                   "dict or a demo_data .pt path)")
+        self.g_arbi = False
+        self.k_arbi = False
+        self._fs = FramedState(self.batch, self.C, self.h, self.w, device)
+        self._pending_state = None
+        self._init_family_buffers()
+        self.update_params(params)
+        if state_init is None:
+            state_init = torch.rand((self.batch, self.C, self.h, self.w))
+        self.state = state_init
+        self.display_kernel = False
+        self.save_dir = save_dir
+        if interest_files is not None:
+            self.interest_files = sorted(p.as_posix() for p in Path(interest_files).rglob("*.pt"))
+        else:
+            self.interest_files = None
+        self.chosen_interesting = 0
+        self.frames = 0
+        self._worldmap = self._worldmap.to(device)
+
+    def _init_family_buffers(self):
+        pass
+
+    # ---- public state tensor ------------------------------------------------------------------
+    @property
+    def state(self) -> torch.Tensor:
+        if self._pending_state is not None:
+            return self._pending_state
+        return self._fs.view()
+
+    @state.setter
+    def state(self, value: torch.Tensor):
+        self._pending_state = value
+
+    def _sync_state(self):
+        if self._pending_state is not None:
+            self._fs.load_dense(self._pending_state)
+            self._pending_state = None
+        else:
+            self._fs.refresh_if_edited()
+
+    # ---- parameters (cold path, lenia.py:143-205) ----------------------------------------------
+    def update_params(self, params, k_size_override=None):
+        self.frames = 0
+        if isinstance(params, (str, Path)):
+            params = LeniaParams(from_file=params, channels=self.C)
+        elif isinstance(params, dict):
+            d = dict(params)
+            st = d.pop("state", None)
+            params = LeniaParams(param_dict=d, channels=self.C)
+            if st is not None:
+                self.state = st
+        elif not isinstance(params, LeniaParams) and hasattr(params, "param_dict"):
+            params = LeniaParams(param_dict=params.param_dict, channels=self.C)  # e.g. the reference's own LeniaParams
+        self.params = params.to(self.device)
+        p = self.params.param_dict
+        if p["weights"].shape[0] != self.batch:
+            raise _lib.B200CAError(f"params batch {p['weights'].shape[0]} != automaton batch {self.batch}")
+        if k_size_override is not None:
+            p["k_size"] = k_size_override
+        if p["k_size"] % 2 == 0:
+            p["k_size"] += 1
+        self.k_size = p["k_size"]
+        self.k_mult = p.get("k_mult", 1)
+        self.g_arbi = bool(p.get("g_arbi", False))
+        self.k_arbi = bool(p.get("k_arbi", False))
+        if self.g_arbi:
+            raise _lib.B200CAError("g_arbi (Fourier growth functions) is not built yet (SURVEY.md 8f-3)")
+        self.mu = p["mu"].float().contiguous()
+        self.sigma = p["sigma"].float().contiguous()
+        self.weights = p["weights"].float().contiguous()
+        for key in ("beta", "mu_k", "sigma_k"):
+            if key in p:
+                setattr(self, key, p[key])
+        exp_shape = (self.batch, self.C * self.k_mult, self.C)
+        if tuple(self.mu.shape) != exp_shape:
+            raise _lib.B200CAError(f"mu shape {tuple(self.mu.shape)} != {exp_shape}")
+        self.k = compute_kernel(self.params, self.C).float().contiguous()  # (B, C*k_mult, C, ks, ks)
+        L = _lib.lib()
+        n = L.b200ca_lenia_kprep_elems(self.batch, self.C, self.k_mult)
+        self._kprep = torch.empty(n, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.call("b200ca_lenia_prepare_kernel", _lib.ptr(self.k), _lib.ptr(self._kprep), self.batch, self.C, self.k_mult,
+                      int(self.k_size), _lib.current_stream(self.device))
+
+    # ---- hot path ---------------------------------------------------------------------------------
+    def _conv(self, dst: torch.Tensor, mode: int):
+        fs = self._fs
+        with torch.cuda.device(fs.device):
+            _lib.call("b200ca_lenia_step", _lib.ptr(fs.buf), _lib.ptr(dst), _lib.ptr(self._kprep), _lib.ptr(self.mu),
+                      _lib.ptr(self.sigma), _lib.ptr(self.weights), fs.B, fs.C, self.k_mult, fs.H, fs.W, float(self.dt), mode,
+                      1, 0, 0, _lib.current_stream(fs.device))
+
+    @torch.no_grad()
+    def step(self):
+        """lenia.py:430-451."""
+        self._sync_state()
+        self._conv(self._fs.other, _lib.MODE_LENIA)
+        self._fs.swap()
+        self.frames += 1
+
+    def mass(self):
+        """(B,C) mean mass (lenia.py:471-479)."""
+        self._sync_state()
+        return (self._fs.mass() / (self.h * self.w)).float()
+
+    @torch.no_grad()
+    def draw(self):
+        """lenia.py:481-500."""
+        assert self.state.shape[0] == 1, "Batch size must be 1 to draw"
+        toshow = self.state[0].clone()
+        if self.C == 1:
+            toshow = toshow.expand(3, -1, -1)
+        elif self.C == 2:
+            toshow = torch.cat([toshow, torch.zeros_like(toshow[:1])], dim=0)
+        else:
+            toshow = toshow[:3, :, :]
+        self._worldmap = torch.clamp(toshow, 0.0, 1.0)
+
+
+class MaCELenia(Lenia):
+    """
+    Mass conserving Lenia-like Alife model (B200 step).
+    """
+
+    def __init__(self, size, num_channels=3, params=None, state_init=None, device="cuda", has_food=False, sense_food=False,
+                 interest_files=None, save_dir="."):
+        if has_food or sense_food:
+            raise _lib.B200CAError("the MaCE food subsystem is not built yet (SURVEY.md 8f-3)")
+        self.has_food = False
+        self.sense_food = False
+        self._beta = 8
+        super().__init__(size, dt=0.1, num_channels=num_channels, params=params, state_init=state_init, device=device,
+                         interest_files=interest_files, save_dir=save_dir)
+        self.show_batch = 0
+
+    def _init_family_buffers(self):
+        fs = self._fs
+        self._aff = torch.zeros((fs.B, fs.C, fs.rows, fs.pitch), dtype=torch.float32, device=fs.device)
+
+    @property
+    def b(self):
+        return self._beta
+
+    @b.setter
+    def b(self, value):
+        self._beta = value
+
+    @property
+    def Aff(self) -> torch.Tensor:
+        """Affinity of the last step, (B,C,H,W) view (macelenia.py:52)."""
+        return self._aff[:, :, F:F + self.h, F:F + self.w]
+
+    def _compute_affinity(self) -> torch.Tensor:
+        """macelenia.py:122-159 (food off)."""
+        self._sync_state()
+        self._conv(self._aff, _lib.MODE_AFF)
+        return self.Aff
+
+    def _mace_step(self, alpha_on=False, alpha=0.0):
+        fs = self._fs
+        self._compute_affinity()
+        with torch.cuda.device(fs.device):
+            _lib.call("b200ca_mace_redistribute", _lib.ptr(fs.buf), _lib.ptr(self._aff), _lib.ptr(fs.other), fs.B, fs.C, fs.H,
+                      fs.W, float(self.b), 1 if alpha_on else 0, float(alpha), 1, _lib.current_stream(fs.device))
+        fs.swap()
+        return self.Aff
+
+    @torch.no_grad()
+    def step(self):
+        """macelenia.py:72-87."""
+        self._mace_step()
+        self.frames += 1
+
+    def total_mass(self):
+        """(B,) total mass (macelenia.py:421-428)."""
+        self._sync_state()
+        return self._fs.mass().sum(dim=1)
+
+    def draw(self):
+        st = self.state[self.show_batch]
+        toshow = st[:3] if self.C >= 3 else torch.cat([st, torch.zeros((3 - self.C,) + tuple(st.shape[1:]), device=st.device)], 0)
+        self._worldmap = torch.clamp(toshow, 0.0, 1.0)
+
+
+class MaCELeniaXChan(MaCELenia):
+    """
+    MaCELenia with cross channel step (B200 step).
+    """
+
+    def __init__(self, size, num_channels=3, params=None, state_init=None, device="cuda", has_food=False, sense_food=False,
+                 interest_files=None, save_dir="."):
+        super().__init__(size, num_channels, params, state_init, device=device, has_food=has_food, sense_food=sense_food,
+                         interest_files=interest_files, save_dir=save_dir)
+        # the reference constructor resets these after update_params ran (mace_lenia_xchan.py:47-49)
+        self._beta = 6
+        self.alpha = 0.03
+        self.params["alpha"] = self.alpha
+
+    def update_params(self, params, k_size_override=None):
+        super().update_params(params, k_size_override=k_size_override)
+        if "alpha" in self.params:
+            self.alpha = float(self.params["alpha"])
+
+    @torch.no_grad()
+    def step(self):
+        """mace_lenia_xchan.py:59-66 (note: the reference does not advance `frames` here)."""
+        self._mace_step(alpha_on=True, alpha=self.alpha)

@@ -1,0 +1,252 @@
+"""GPU parity of the Lenia-family kernels (through the C ABI / Automaton drop-ins) against the golden
+vectors produced by the unmodified reference and against the oracle.
+
+Tolerance (BASELINE.json north_star): single step max-abs 1e-5 in fp32 on states in [0,1]; states with
+values >> 1 (real saved MaCE states reach 247) use the same bound relative to the state maximum.
+Multi-step runs compare mass / statistics only (chaotic dynamics).  MaCE must conserve mass to fp32 round-off.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pyca_oracle as orc
+from tests.util import family_case, golden_names, load_npz, t
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def params_dict(p, C=3):
+    d = {k: t(p[k]) for k in ["mu", "sigma", "beta", "mu_k", "sigma_k", "weights"]}
+    d["k_size"] = int(p["k_size"])
+    return d
+
+
+def sliced(d, c):
+    return {k: (v[:, :c, :c].clone() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+
+
+@pytest.mark.parametrize("name", golden_names("lenia"))
+def test_lenia_golden(name):
+    import pyca_b200
+
+    fx, p = family_case("lenia", name)
+    s0 = t(fx["state_in"])
+    a = pyca_b200.Lenia(tuple(s0.shape[2:]), dt=float(fx["dt"]), params=params_dict(p), state_init=s0, device="cuda")
+    assert torch.allclose(a.k.cpu(), t(p["K"]), atol=1e-8), "host kernel construction differs from the reference's"
+    a.step()
+    err = (a.state.cpu() - t(fx["state_out"])).abs().max().item()
+    assert err <= TOL, f"{name}: max-abs {err:.2e}"
+    assert a.frames == 1
+    # single-channel slice of the same file (BASELINE configs[1])
+    a1 = pyca_b200.Lenia(tuple(s0.shape[2:]), dt=float(fx["dt"]), num_channels=1, params=sliced(params_dict(p), 1),
+                         state_init=s0[:, :1], device="cuda")
+    assert torch.allclose(a1.k.cpu(), t(fx["c1_K"]), atol=1e-8)
+    a1.step()
+    err1 = (a1.state.cpu() - t(fx["c1_out"])).abs().max().item()
+    assert err1 <= TOL, f"{name} C=1: max-abs {err1:.2e}"
+
+
+@pytest.mark.parametrize("name", golden_names("mace"))
+def test_mace_golden(name):
+    import pyca_b200
+
+    fx, p = family_case("mace", name)
+    s0 = t(fx["state_in"])
+    a = pyca_b200.MaCELenia(tuple(s0.shape[2:]), params=params_dict(p), state_init=s0, device="cuda")
+    assert a.b == float(fx["b"])
+    m0 = a.total_mass().cpu()
+    a.step()
+    aff_err = (a.Aff.cpu() - t(fx["aff"])).abs().max().item()
+    err = (a.state.cpu() - t(fx["state_out"])).abs().max().item()
+    scale = max(1.0, float(t(fx["state_out"]).max()))
+    assert err <= TOL * scale, f"{name}: state max-abs {err:.2e} (aff {aff_err:.2e})"
+    m1 = a.total_mass().cpu()
+    assert torch.allclose(m0, m1, rtol=1e-6), "mass not conserved"
+
+
+@pytest.mark.parametrize("name", golden_names("xchan"))
+def test_xchan_golden(name):
+    import pyca_b200
+
+    fx, p = family_case("xchan", name)
+    s0 = t(fx["state_in"])
+    a = pyca_b200.MaCELeniaXChan(tuple(s0.shape[2:]), params=params_dict(p), state_init=s0, device="cuda")
+    a.alpha = float(fx["alpha_used"])
+    assert a.b == float(fx["b"])
+    m0 = a.total_mass().cpu()
+    a.step()
+    ref = t(fx["state_out"])
+    scale = max(1.0, float(ref.max()))
+    err = (a.state.cpu() - ref).abs().max().item()
+    assert err <= TOL * scale, f"{name}: max-abs {err:.2e} (scale {scale:.1f})"
+    assert torch.allclose(m0, a.total_mass().cpu(), rtol=1e-6)
+
+
+def _oracle_params(name="abominable_mongolic", tag="lenia"):
+    p = load_npz(f"params_{tag}_{name}.npz")
+    return params_dict(p), t(p["K"]), t(p["mu_s"]), t(p["sigma_s"]), t(p["weights_s"])
+
+
+@pytest.mark.parametrize("shape", [(32, 32), (50, 70), (64, 64), (65, 129), (100, 47), (31 + 1, 200), (256, 256)])
+def test_lenia_odd_shapes_vs_oracle(shape):
+    """Tile overhang, partial strips and worlds narrower than a tile."""
+    import pyca_b200
+
+    d, K, mu, sg, w = _oracle_params()
+    g = torch.Generator().manual_seed(shape[0] * 1000 + shape[1])
+    s0 = torch.rand(1, 3, *shape, generator=g)
+    a = pyca_b200.Lenia(shape, params=d, state_init=s0, device="cuda")
+    a.step()
+    ref = orc.lenia_step(s0, K, mu, sg, w, 0.1)
+    err = (a.state.cpu() - ref).abs().max().item()
+    assert err <= TOL, f"{shape}: {err:.2e}"
+
+
+def test_lenia_batched_params_and_state_contract():
+    import pyca_b200
+
+    d0, K0, mu0, sg0, w0 = _oracle_params("abominable_mongolic")
+    d1, K1, mu1, sg1, w1 = _oracle_params("bedfast_laplace")
+    d = {k: (torch.cat([d0[k], d1[k]], 0) if isinstance(d0[k], torch.Tensor) else d0[k]) for k in d0}
+    g = torch.Generator().manual_seed(5)
+    s0 = torch.rand(2, 3, 64, 96, generator=g)
+    a = pyca_b200.Lenia((2, 64, 96), params=d, state_init=s0, device="cuda")
+    a.step()
+    ref = torch.cat([orc.lenia_step(s0[:1], K0, mu0, sg0, w0), orc.lenia_step(s0[1:], K1, mu1, sg1, w1)], 0)
+    assert (a.state.cpu() - ref).abs().max().item() <= TOL
+    # in-place edit of the public state between steps (brush, lenia.py:681-690), including frame cells
+    st = a.state
+    st[:, :, :5, :] = 0.25
+    st[:, 1, 20:30, 90:] += 0.1
+    ref[:, :, :5, :] = 0.25
+    ref[:, 1, 20:30, 90:] += 0.1
+    a.step()
+    ref2 = torch.cat([orc.lenia_step(ref[:1], K0, mu0, sg0, w0), orc.lenia_step(ref[1:], K1, mu1, sg1, w1)], 0)
+    assert (a.state.cpu() - ref2).abs().max().item() <= TOL
+    # re-assignment
+    a.state = s0.cuda()
+    a.step()
+    assert (a.state.cpu() - ref).abs().max().item() <= TOL
+    a.draw() if a.batch == 1 else None
+
+
+def test_small_kernel_size_embedding():
+    import pyca_b200
+
+    d, *_ = _oracle_params()
+    d = dict(d)
+    d["k_size"] = 13
+    q = orc.sanitize_params({k: v for k, v in d.items() if isinstance(v, torch.Tensor)})
+    K = orc.lenia_kernel(q["beta"], q["mu_k"], q["sigma_k"], 13)
+    g = torch.Generator().manual_seed(9)
+    s0 = torch.rand(1, 3, 40, 72, generator=g)
+    a = pyca_b200.Lenia((40, 72), params=d, state_init=s0, device="cuda")
+    a.step()
+    ref = orc.lenia_step(s0, K, q["mu"], q["sigma"], q["weights"])
+    assert (a.state.cpu() - ref).abs().max().item() <= TOL
+
+
+def test_lenia_multistep_statistics():
+    """Chaotic dynamics: compare mass and moments after 20 steps, not cells."""
+    import pyca_b200
+
+    d, K, mu, sg, w = _oracle_params()
+    g = torch.Generator().manual_seed(21)
+    s0 = torch.rand(1, 3, 128, 128, generator=g)
+    a = pyca_b200.Lenia((128, 128), params=d, state_init=s0, device="cuda")
+    ref = s0.clone()
+    Kf = orc.kernel_fft(K, 128, 128)
+    for _ in range(20):
+        a.step()
+        ref = orc.lenia_step(ref, K, mu, sg, w, 0.1, Kf)
+    got = a.state.cpu()
+    assert got.min() >= 0 and got.max() <= 1
+    assert torch.allclose(a.mass().cpu(), ref.mean(dim=(-1, -2)), atol=2e-3)
+    assert abs(got.std().item() - ref.std().item()) < 5e-3
+
+
+def test_vs_float64_noise_floor():
+    """|cuda - ref64| must not exceed the reference's own fp32 rounding error |ref32 - ref64| by much
+    (BASELINE.md section 6)."""
+    import pyca_b200
+
+    d, K, mu, sg, w = _oracle_params("arborical_asbestosis", "xchan")
+    g = torch.Generator().manual_seed(33)
+    s0 = torch.rand(1, 3, 128, 128, generator=g)
+    a = pyca_b200.MaCELenia((128, 128), params=d, state_init=s0, device="cuda")
+    aff = a._compute_affinity().cpu()
+    aff32 = orc.lenia_affinity(s0, K, mu, sg, w)
+    aff64 = orc.lenia_affinity_f64(s0, K, mu, sg, w)
+    e_cuda = (aff.double() - aff64).abs().max().item()
+    e_ref = (aff32.double() - aff64).abs().max().item()
+    print(f"affinity error vs fp64: cuda {e_cuda:.2e}, reference fp32 {e_ref:.2e}")
+    assert e_cuda <= max(4 * e_ref, 2e-6)
+
+
+def test_xchan_realstate_relative():
+    """Crop of a real saved MaCE-XChan state (values up to ~20): relative tolerance."""
+    import pyca_b200
+
+    fx = load_npz("xchan_realstate.npz")
+    s0 = t(fx["state_in"])
+    a = pyca_b200.MaCELeniaXChan((64, 64), params=params_dict(fx), state_init=s0, device="cuda")
+    a.alpha = float(fx["alpha_used"])
+    a.step()
+    ref = t(fx["state_out"])
+    err = (a.state.cpu() - ref).abs().max().item()
+    assert err <= TOL * max(1.0, float(ref.max())), f"{err:.2e} vs max {float(ref.max()):.1f}"
+
+
+def test_mace_mass_conservation_long_run():
+    import pyca_b200
+
+    d, *_ = _oracle_params("arborical_asbestosis", "xchan")
+    g = torch.Generator().manual_seed(44)
+    s0 = torch.rand(1, 3, 512, 512, generator=g)
+    for cls in (pyca_b200.MaCELenia, pyca_b200.MaCELeniaXChan):
+        a = cls((512, 512), params=d, state_init=s0, device="cuda")
+        m0 = a.total_mass().item()
+        for _ in range(25):
+            a.step()
+        m1 = a.total_mass().item()
+        assert abs(m1 - m0) <= 2e-5 * m0, f"{cls.__name__}: mass {m0} -> {m1}"
+        assert torch.isfinite(a.state).all() and a.state.min() >= 0
+
+
+def test_periodic_tiling_identity():
+    """A 2x2 tiling of a small torus must evolve as 4 copies of the small torus (exercises frame + tile seams)."""
+    import pyca_b200
+
+    d, *_ = _oracle_params("arborical_asbestosis", "xchan")
+    g = torch.Generator().manual_seed(55)
+    s0 = torch.rand(1, 3, 96, 160, generator=g)
+    small = pyca_b200.MaCELeniaXChan((96, 160), params=d, state_init=s0, device="cuda")
+    big = pyca_b200.MaCELeniaXChan((192, 320), params=d, state_init=s0.repeat(1, 1, 2, 2), device="cuda")
+    for _ in range(3):
+        small.step()
+        big.step()
+    sm = small.state
+    bg = big.state
+    for ty in range(2):
+        for tx in range(2):
+            tile = bg[:, :, ty * 96:(ty + 1) * 96, tx * 160:(tx + 1) * 160]
+            assert (tile - sm).abs().max().item() <= 2e-6
+
+
+def test_host_entry_point():
+    import ctypes
+
+    import pyca_b200
+    from pyca_b200 import _lib
+
+    d, K, mu, sg, w = _oracle_params()
+    g = torch.Generator().manual_seed(66)
+    s0 = torch.rand(1, 3, 64, 80, generator=g)
+    a = pyca_b200.Lenia((64, 80), params=d, state_init=s0, device="cuda")  # prepares device params
+    h_in = s0.numpy()
+    h_out = np.empty_like(h_in)
+    _lib.call("b200ca_lenia_run_host", h_in.ctypes.data_as(ctypes.c_void_p), h_out.ctypes.data_as(ctypes.c_void_p),
+              _lib.ptr(a._kprep), _lib.ptr(a.mu), _lib.ptr(a.sigma), _lib.ptr(a.weights), 1, 3, 1, 64, 80, 0.1, 0, 0.0, 0.0, 2)
+    ref = orc.lenia_step(orc.lenia_step(s0, K, mu, sg, w), K, mu, sg, w)
+    assert (torch.from_numpy(h_out) - ref).abs().max().item() <= 2 * TOL
