@@ -26,7 +26,10 @@ constexpr int KW = 2 * R + 1;    // 31
 constexpr int TW = 64;           // output tile width
 constexpr int STRIP = 16;        // outputs per thread (one row)
 constexpr int SROW = 100;        // smem row pitch in floats: >= TW + 2R, multiple of 4, == 4 (mod 32)
-constexpr int NLD = 12;          // LDS.128 per input row segment (48 >= STRIP + 2R floats)
+constexpr int NLD = 12;          // LDS.128 per input row segment (48 >= STRIP + 2R + 1 floats)
+constexpr int XH = 16;           // left halo of the staged tile: the TMA box must start on a 16-byte boundary
+                                 // (inner coordinate multiple of 4 floats; probed in tools/tma_probe.cu), so 16 not R
+constexpr int XOFF = XH - R;     // column of the first tap inside a thread's 48-float row segment
 constexpr int KROWS = R + 1;     // folded kernel rows dy = 0..15
 constexpr int KPITCH = 32;       // floats per folded kernel row (31 taps + pad)
 constexpr int KPREP = KROWS * KPITCH;
@@ -64,10 +67,11 @@ __device__ __forceinline__ void store_mirrors(float *__restrict__ plane, int H, 
 }
 
 template <int NW>
-__global__ void __launch_bounds__(32 * NW) lenia_conv_kernel(const __grid_constant__ CUtensorMap tmap, const LeniaArgs a) {
+__global__ void __launch_bounds__(32 * NW) lenia_conv_kernel(const CUtensorMap *__restrict__ tmap, const LeniaArgs a) {
     constexpr int TH = 8 * NW;
     constexpr int TROWS = TH + 2 * R;
-    constexpr int STAGE = TROWS * SROW;  // floats
+    constexpr int STAGE = (TROWS * SROW + 31) / 32 * 32;  // floats; stage buffers stay 128-byte aligned (TMA destination)
+    constexpr int TX_BYTES = TROWS * SROW * 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *tile = reinterpret_cast<float *>(smem_raw);                 // [2][STAGE]
     float *taps = tile + 2 * STAGE;                                    // [2][KPREP]
@@ -81,16 +85,15 @@ __global__ void __launch_bounds__(32 * NW) lenia_conv_kernel(const __grid_consta
     const int yl = warp * 8 + ty;
 
     if (tid == 0) {
-        tma_prefetch_desc(&tmap);
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         mbar_fence_init();
     }
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(&bars[0], STAGE * sizeof(float));
-        // framed coords of the tile origin: (x0 - R + F, y0 - R + F); source plane of kernel 0 is channel 0
-        tma_load_3d(tile, &tmap, &bars[0], x0 + F - R, y0 + F - R, b * a.C + 0);
+        mbar_expect_tx(&bars[0], TX_BYTES);
+        // framed coords of the tile origin: (x0 - XH + F, y0 - R + F); source plane of kernel 0 is channel 0
+        tma_load_3d(tile, tmap, &bars[0], x0 + F - XH, y0 + F - R, b * a.C + 0);
     }
 
     float dxs[STRIP];
@@ -100,8 +103,8 @@ __global__ void __launch_bounds__(32 * NW) lenia_conv_kernel(const __grid_consta
     for (int i = 0; i < a.NS; ++i) {
         const int s = i & 1;
         if (tid == 0 && i + 1 < a.NS) {
-            mbar_expect_tx(&bars[s ^ 1], STAGE * sizeof(float));
-            tma_load_3d(tile + (s ^ 1) * STAGE, &tmap, &bars[s ^ 1], x0 + F - R, y0 + F - R, b * a.C + (i + 1) / a.k_mult);
+            mbar_expect_tx(&bars[s ^ 1], TX_BYTES);
+            tma_load_3d(tile + (s ^ 1) * STAGE, tmap, &bars[s ^ 1], x0 + F - XH, y0 + F - R, b * a.C + (i + 1) / a.k_mult);
         }
         // stage the folded taps of kernel (i -> j)
         {
@@ -149,11 +152,11 @@ __global__ void __launch_bounds__(32 * NW) lenia_conv_kernel(const __grid_consta
             }
             float p[STRIP];
 #pragma unroll
-            for (int k = 0; k < STRIP; ++k) p[k] = tv[0] * sv[k];
+            for (int k = 0; k < STRIP; ++k) p[k] = tv[0] * sv[k + XOFF];
 #pragma unroll
             for (int dx = 1; dx < KW; ++dx) {
 #pragma unroll
-                for (int k = 0; k < STRIP; ++k) p[k] = fmaf(tv[dx], sv[k + dx], p[k]);
+                for (int k = 0; k < STRIP; ++k) p[k] = fmaf(tv[dx], sv[k + dx + XOFF], p[k]);
             }
 #pragma unroll
             for (int k = 0; k < STRIP; ++k) acc[k] += p[k];
@@ -237,9 +240,9 @@ __global__ void lenia_prepare_kernel_kernel(const float *__restrict__ K, float *
 }
 
 template <int NW>
-static int launch_conv(const CUtensorMap &tm, const LeniaArgs &a, int tiles_y, cudaStream_t st) {
+static int launch_conv(const CUtensorMap *tm, const LeniaArgs &a, int tiles_y, cudaStream_t st) {
     constexpr int TH = 8 * NW;
-    constexpr size_t smem = (size_t)2 * (TH + 2 * R) * SROW * 4 + 2 * KPREP * 4 + 64;
+    constexpr size_t smem = (size_t)2 * (((TH + 2 * R) * SROW + 31) / 32 * 32) * 4 + 2 * KPREP * 4 + 64;
     static bool attr_set[64] = {false};
     int dev = 0;
     B200CA_CUDA(cudaGetDevice(&dev));
@@ -343,7 +346,7 @@ extern "C" int b200ca_lenia_step(const float *state_in, float *state_out, const 
     a.mode = mode;
     a.row_wrap = row_wrap;
     a.tile_row0 = tile_row_begin;
-    CUtensorMap tm;
+    const CUtensorMap *tm = nullptr;
     const uint64_t rows = (uint64_t)H + 2 * F;
     int rc = get_tensor_map_3d(&tm, state_in, (uint64_t)a.pitch, rows, (uint64_t)B * C, (uint64_t)a.pitch, (uint64_t)a.pitch * rows,
                                SROW, (uint32_t)(TH + 2 * R));

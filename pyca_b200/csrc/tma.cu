@@ -3,6 +3,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <vector>
 
 #include "tma.cuh"
 
@@ -27,16 +28,53 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// Descriptors live in GLOBAL memory (one 128-byte slot each, carved from per-device slabs): on this
+// driver (580.x) a `__grid_constant__` CUtensorMap kernel parameter makes UTMALDG fault with "illegal
+// instruction", a descriptor read through a global pointer works (tools/tma_probe.cu variants 4 / 12).
 typedef std::tuple<int, const void *, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t> MapKey;
-static std::map<MapKey, CUtensorMap> g_maps;
+static std::map<MapKey, const CUtensorMap *> g_maps;
 static std::mutex g_maps_mu;
+struct Slab {
+    CUtensorMap *base;
+    int used;
+    int dev;
+};
+static std::vector<Slab> g_slabs;
+constexpr int SLAB_SLOTS = 512;
 
 void clear_tensor_map_cache() {
     std::lock_guard<std::mutex> lk(g_maps_mu);
     g_maps.clear();
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto &s : g_slabs) {
+        cudaSetDevice(s.dev);
+        cudaDeviceSynchronize();
+        cudaFree(s.base);
+    }
+    cudaSetDevice(cur);
+    g_slabs.clear();
+    (void)cudaGetLastError();
 }
 
-int get_tensor_map_3d(CUtensorMap *out, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
+// caller holds g_maps_mu
+static int alloc_slot(int dev, CUtensorMap **out) {
+    for (auto &s : g_slabs)
+        if (s.dev == dev && s.used < SLAB_SLOTS) {
+            *out = s.base + s.used++;
+            return 0;
+        }
+    Slab s;
+    s.dev = dev;
+    s.used = 0;
+    s.base = nullptr;
+    B200CA_CUDA(cudaMalloc(&s.base, sizeof(CUtensorMap) * SLAB_SLOTS));
+    g_slabs.push_back(s);
+    *out = g_slabs.back().base + g_slabs.back().used++;
+    return 0;
+}
+
+int get_tensor_map_3d(const CUtensorMap **out, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
                       uint32_t b0, uint32_t b1) {
     int dev = 0;
     B200CA_CUDA(cudaGetDevice(&dev));
@@ -73,10 +111,14 @@ int get_tensor_map_3d(CUtensorMap *out, const void *base, uint64_t d0, uint64_t 
     }
     {
         std::lock_guard<std::mutex> lk(g_maps_mu);
-        if (g_maps.size() > 4096) g_maps.clear();
-        g_maps[key] = m;
+        CUtensorMap *slot = nullptr;
+        int rc = alloc_slot(dev, &slot);
+        if (rc) return rc;
+        // blocking copy (cold path): the descriptor is visible to every later launch on any stream
+        B200CA_CUDA(cudaMemcpy(slot, &m, sizeof(m), cudaMemcpyHostToDevice));
+        g_maps[key] = slot;
+        *out = slot;
     }
-    *out = m;
     return 0;
 }
 

@@ -6,9 +6,10 @@
 
 namespace b200ca {
 
-// Encodes (and caches per device/pointer/shape) a rank-3 fp32 tiled tensor map:
+// Encodes (and caches per device/pointer/shape) a rank-3 fp32 tiled tensor map and returns a pointer to
+// its copy in device global memory:
 //   dims  {d0 (inner, elements), d1, d2},  strides in elements {s1, s2},  box {b0, b1, 1}.
-int get_tensor_map_3d(CUtensorMap *out, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
+int get_tensor_map_3d(const CUtensorMap **out, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
                       uint32_t b0, uint32_t b1);
 void clear_tensor_map_cache();
 

@@ -119,10 +119,11 @@ def test_lenia_batched_params_and_state_contract():
     st = a.state
     st[:, :, :5, :] = 0.25
     st[:, 1, 20:30, 90:] += 0.1
-    ref[:, :, :5, :] = 0.25
-    ref[:, 1, 20:30, 90:] += 0.1
+    edited = ref.clone()
+    edited[:, :, :5, :] = 0.25
+    edited[:, 1, 20:30, 90:] += 0.1
     a.step()
-    ref2 = torch.cat([orc.lenia_step(ref[:1], K0, mu0, sg0, w0), orc.lenia_step(ref[1:], K1, mu1, sg1, w1)], 0)
+    ref2 = torch.cat([orc.lenia_step(edited[:1], K0, mu0, sg0, w0), orc.lenia_step(edited[1:], K1, mu1, sg1, w1)], 0)
     assert (a.state.cpu() - ref2).abs().max().item() <= TOL
     # re-assignment
     a.state = s0.cuda()
