@@ -12,6 +12,9 @@ namespace b200ca {
 void set_error(const char *fmt, ...);
 int check_cuda(cudaError_t e, const char *what);
 int num_sms();
+// grow-only per-device scratch buffers for the *_host entry points (slot 0..7); freed by b200ca_shutdown()
+int scratch_get(int slot, size_t bytes, void **out);
+void scratch_free_all();
 
 #define B200CA_CUDA(call)                                  \
     do {                                                   \

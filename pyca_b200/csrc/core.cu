@@ -34,6 +34,50 @@ int num_sms() {
     return cached[dev];
 }
 
+struct ScratchSlot {
+    void *p;
+    size_t bytes;
+};
+static ScratchSlot g_scratch[64][8] = {};
+
+int scratch_get(int slot, size_t bytes, void **out) {
+    int dev = 0;
+    B200CA_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || slot < 0 || slot >= 8) {
+        set_error("scratch_get: bad device/slot");
+        return B200CA_E_BADARG;
+    }
+    ScratchSlot &s = g_scratch[dev][slot];
+    if (s.bytes < bytes) {
+        if (s.p) {
+            B200CA_CUDA(cudaDeviceSynchronize());
+            cudaFree(s.p);
+            s.p = nullptr;
+            s.bytes = 0;
+        }
+        B200CA_CUDA(cudaMalloc(&s.p, bytes));
+        s.bytes = bytes;
+    }
+    *out = s.p;
+    return 0;
+}
+
+void scratch_free_all() {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < 64; ++d)
+        for (int k = 0; k < 8; ++k)
+            if (g_scratch[d][k].p) {
+                cudaSetDevice(d);
+                cudaDeviceSynchronize();
+                cudaFree(g_scratch[d][k].p);
+                g_scratch[d][k].p = nullptr;
+                g_scratch[d][k].bytes = 0;
+            }
+    cudaSetDevice(cur);
+    (void)cudaGetLastError();
+}
+
 // ---- framed layout ---------------------------------------------------------------------------
 // frame cell (fy, fx) in [0, H+2F) x [0, W+2F) holds interior cell ((fy-F) mod H, (fx-F) mod W)
 __global__ void frame_load_kernel(const float *__restrict__ dense, float *__restrict__ framed, int planes, int H, int W,

@@ -392,9 +392,9 @@ extern "C" int b200ca_gol_run_host(const int32_t *h_world_in, int32_t *h_world_o
     int rc = 0;
     cudaStream_t st = 0;
     do {
-        if ((rc = check_cuda(cudaMalloc(&d_world, wbytes), "cudaMalloc world"))) break;
-        if ((rc = check_cuda(cudaMalloc(&d_a, bbytes), "cudaMalloc bits"))) break;
-        if ((rc = check_cuda(cudaMalloc(&d_b, bbytes), "cudaMalloc bits"))) break;
+        if ((rc = scratch_get(0, wbytes, (void **)&d_world))) break;
+        if ((rc = scratch_get(1, bbytes, (void **)&d_a))) break;
+        if ((rc = scratch_get(2, bbytes, (void **)&d_b))) break;
         if ((rc = check_cuda(cudaMemcpyAsync(d_world, h_world_in, wbytes, cudaMemcpyHostToDevice, st), "H2D"))) break;
         if ((rc = b200ca_gol_pack(d_world, 4, d_a, H, W, stride, st))) break;
         if ((rc = b200ca_gol_run(d_a, d_b, H, W, stride, s_mask, b_mask, 0, nsteps, st))) break;
@@ -402,8 +402,5 @@ extern "C" int b200ca_gol_run_host(const int32_t *h_world_in, int32_t *h_world_o
         if ((rc = check_cuda(cudaMemcpyAsync(h_world_out, d_world, wbytes, cudaMemcpyDeviceToHost, st), "D2H"))) break;
         rc = check_cuda(cudaStreamSynchronize(st), "sync");
     } while (0);
-    cudaFree(d_world);
-    cudaFree(d_a);
-    cudaFree(d_b);
     return rc;
 }

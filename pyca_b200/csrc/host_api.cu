@@ -15,10 +15,10 @@ extern "C" int b200ca_lenia_run_host(const float *h_state_in, float *h_state_out
     cudaStream_t st = 0;
     int rc = 0;
     do {
-        if ((rc = check_cuda(cudaMalloc(&d_dense, dbytes), "cudaMalloc"))) break;
-        if ((rc = check_cuda(cudaMalloc(&d_a, fbytes), "cudaMalloc"))) break;
-        if ((rc = check_cuda(cudaMalloc(&d_b, fbytes), "cudaMalloc"))) break;
-        if (family > 0 && (rc = check_cuda(cudaMalloc(&d_aff, fbytes), "cudaMalloc"))) break;
+        if ((rc = scratch_get(0, dbytes, (void **)&d_dense))) break;
+        if ((rc = scratch_get(1, fbytes, (void **)&d_a))) break;
+        if ((rc = scratch_get(2, fbytes, (void **)&d_b))) break;
+        if (family > 0 && (rc = scratch_get(3, fbytes, (void **)&d_aff))) break;
         if ((rc = check_cuda(cudaMemcpyAsync(d_dense, h_state_in, dbytes, cudaMemcpyHostToDevice, st), "H2D"))) break;
         if ((rc = b200ca_frame_load(d_dense, d_a, B, C, H, W, 1, st))) break;
         float *src = d_a, *dst = d_b;
@@ -38,9 +38,5 @@ extern "C" int b200ca_lenia_run_host(const float *h_state_in, float *h_state_out
         if ((rc = check_cuda(cudaMemcpyAsync(h_state_out, d_dense, dbytes, cudaMemcpyDeviceToHost, st), "D2H"))) break;
         rc = check_cuda(cudaStreamSynchronize(st), "sync");
     } while (0);
-    cudaFree(d_dense);
-    cudaFree(d_a);
-    cudaFree(d_b);
-    cudaFree(d_aff);
     return rc;
 }

@@ -253,11 +253,11 @@ extern "C" int b200ca_nca_run_host(const float *h_state_in, float *h_state_out, 
     void *d_s = nullptr;
     cudaStream_t st = 0;
     do {
-        if ((rc = check_cuda(cudaMalloc(&d_a, sbytes), "cudaMalloc"))) break;
-        if ((rc = check_cuda(cudaMalloc(&d_b, sbytes), "cudaMalloc"))) break;
-        if ((rc = check_cuda(cudaMalloc(&d_s, (size_t)b200ca_nca_scratch_bytes(B, H, W)), "cudaMalloc"))) break;
+        if ((rc = scratch_get(0, sbytes, (void **)&d_a))) break;
+        if ((rc = scratch_get(1, sbytes, (void **)&d_b))) break;
+        if ((rc = scratch_get(2, (size_t)b200ca_nca_scratch_bytes(B, H, W), &d_s))) break;
         if (h_update_mask) {
-            if ((rc = check_cuda(cudaMalloc(&d_m, mbytes * (nsteps > 0 ? nsteps : 1)), "cudaMalloc"))) break;
+            if ((rc = scratch_get(3, mbytes * (nsteps > 0 ? nsteps : 1), (void **)&d_m))) break;
             if ((rc = check_cuda(cudaMemcpyAsync(d_m, h_update_mask, mbytes * nsteps, cudaMemcpyHostToDevice, st), "H2D mask"))) break;
         }
         if ((rc = check_cuda(cudaMemcpyAsync(d_a, h_state_in, sbytes, cudaMemcpyHostToDevice, st), "H2D"))) break;
@@ -273,9 +273,5 @@ extern "C" int b200ca_nca_run_host(const float *h_state_in, float *h_state_out, 
         if ((rc = check_cuda(cudaMemcpyAsync(h_state_out, src, sbytes, cudaMemcpyDeviceToHost, st), "D2H"))) break;
         rc = check_cuda(cudaStreamSynchronize(st), "sync");
     } while (0);
-    cudaFree(d_a);
-    cudaFree(d_b);
-    cudaFree(d_m);
-    cudaFree(d_s);
     return rc;
 }

@@ -126,5 +126,6 @@ int get_tensor_map_3d(const CUtensorMap **out, const void *base, uint64_t d0, ui
 
 extern "C" int b200ca_shutdown(void) {
     b200ca::clear_tensor_map_cache();
+    b200ca::scratch_free_all();
     return 0;
 }

@@ -1,0 +1,280 @@
+"""Row-slab sharding of one large torus world across the GPUs of a box (one process per GPU).
+
+The reference has no distributed code at all: it scales only by allocating a
+bigger tensor on one device, and Lenia's global FFT (lenia.py:460-467) cannot be partitioned.  The
+CUDA kernels here are local operators, so the world splits into row slabs:
+
+    rank r owns global rows [r*H/N, (r+1)*H/N);  rank r-1 is "above", rank r+1 "below" (ring = torus).
+
+* Game of Life: the slab carries `g` ghost rows on each side.  `g` generations are computed locally
+  with rows outside the buffer treated as dead (`vert_open`); the error creeps one row per generation
+  from the buffer edge, so after `g` generations the owned rows are still exact.  Then ONE exchange
+  refreshes the ghost rows.  (Per-step latency of a send/recv pair would dominate a ~25 us step;
+  trading 2g redundant rows for 1/g as many exchanges hides it.)
+* Lenia: the framed layout already has 16 ghost rows; each step computes the slab-boundary tile rows
+  first, then exchanges the fresh boundary rows on a side stream while the interior tiles run.
+
+The exchange itself is `torch.distributed` point-to-point (NCCL over NVLink on GPUs, gloo in the CPU
+tests) on contiguous row blocks; the functions below are device-agnostic so the N>1 logic is covered
+on CPU with world_size 2.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def slab_rows(H: int, world: int, rank: int) -> Tuple[int, int]:
+    """Global row range [r0, r1) owned by `rank` (H must divide evenly: slabs are equal so ranks stay in step)."""
+    if H % world != 0:
+        raise ValueError(f"world height {H} is not divisible by the number of ranks {world}")
+    hl = H // world
+    return rank * hl, (rank + 1) * hl
+
+
+def ring_neighbours(rank: int, world: int) -> Tuple[int, int]:
+    """(rank above, rank below) on the periodic ring."""
+    return (rank - 1) % world, (rank + 1) % world
+
+
+def exchange_ghost_rows(blocks_up_send: List[torch.Tensor], blocks_up_recv: List[torch.Tensor],
+                        blocks_down_send: List[torch.Tensor], blocks_down_recv: List[torch.Tensor],
+                        rank: int, world: int, group=None) -> None:
+    """One halo exchange.
+
+    blocks_up_send:   my first owned rows   -> become the BOTTOM ghost rows of the rank above
+    blocks_down_send: my last owned rows    -> become the TOP ghost rows of the rank below
+    blocks_up_recv:   my TOP ghost rows     <- last owned rows of the rank above
+    blocks_down_recv: my BOTTOM ghost rows  <- first owned rows of the rank below
+    Every block must be a contiguous tensor (a row block of one plane).  world == 1: local copies.
+    """
+    if world == 1:
+        for s, r in zip(blocks_down_send, blocks_up_recv):
+            r.copy_(s)
+        for s, r in zip(blocks_up_send, blocks_down_recv):
+            r.copy_(s)
+        return
+    up, down = ring_neighbours(rank, world)
+    # Post order matters when up == down (world == 2): messages between one pair of ranks match in posting
+    # order, so send [last rows, first rows] against the peer's receives [top ghost, bottom ghost].
+    ops = []
+    for s in blocks_down_send:
+        assert s.is_contiguous()
+        ops.append(dist.P2POp(dist.isend, s, down, group))
+    for s in blocks_up_send:
+        assert s.is_contiguous()
+        ops.append(dist.P2POp(dist.isend, s, up, group))
+    for r in blocks_up_recv:
+        assert r.is_contiguous()
+        ops.append(dist.P2POp(dist.irecv, r, up, group))
+    for r in blocks_down_recv:
+        assert r.is_contiguous()
+        ops.append(dist.P2POp(dist.irecv, r, down, group))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+
+
+class GolSlab:
+    """Bit-packed Game-of-Life row slab with `ghost` ghost rows per side (device-agnostic bookkeeping).
+
+    `step_fn(src, dst, rows, nsteps)` advances the whole local buffer (owned + ghost rows, rows outside
+    dead) by nsteps generations ping-ponging src->dst and returns the tensor holding the result.
+    """
+
+    def __init__(self, H: int, W: int, rank: int, world: int, ghost: int, device, stride_words: Optional[int] = None):
+        self.H, self.W, self.rank, self.world = H, W, rank, world
+        self.r0, self.r1 = slab_rows(H, world, rank)
+        self.hl = self.r1 - self.r0
+        if ghost < 1 or ghost > self.hl:
+            raise ValueError(f"ghost rows {ghost} must be in [1, {self.hl}]")
+        self.g = ghost
+        self.rows = self.hl + 2 * ghost
+        wpr = (W + 31) // 32
+        self.stride = stride_words or (wpr + 3) // 4 * 4
+        self.bufs = [torch.zeros((self.rows, self.stride), dtype=torch.int32, device=device) for _ in range(2)]
+        self.cur = 0
+        self.fresh = 0  # generations the ghost rows are still good for
+
+    @property
+    def buf(self):
+        return self.bufs[self.cur]
+
+    def owned(self) -> torch.Tensor:
+        return self.buf[self.g:self.g + self.hl]
+
+    def exchange(self, group=None):
+        b, g, hl = self.buf, self.g, self.hl
+        exchange_ghost_rows([b[g:2 * g]], [b[0:g]], [b[hl:hl + g]], [b[hl + g:hl + 2 * g]], self.rank, self.world, group)
+        self.fresh = g
+
+    def advance(self, step_fn, nsteps: int, group=None):
+        """nsteps generations, exchanging ghost rows whenever they run out."""
+        done = 0
+        while done < nsteps:
+            if self.fresh == 0:
+                self.exchange(group)
+            n = min(self.fresh, nsteps - done)
+            out = step_fn(self.bufs[self.cur], self.bufs[self.cur ^ 1], self.rows, n)
+            self.cur = 0 if out is self.bufs[0] else 1
+            self.fresh -= n
+            done += n
+
+
+class LeniaSlab:
+    """Framed Lenia row slab: (B,C,hl+2F,pitch) fp32 ping-pong buffers whose top/bottom frame rows are
+    ghost rows owned by the ring neighbours."""
+
+    def __init__(self, B: int, C: int, H: int, W: int, rank: int, world: int, frame: int, pitch: int, device):
+        self.B, self.C, self.H, self.W, self.rank, self.world, self.F = B, C, H, W, rank, world, frame
+        self.r0, self.r1 = slab_rows(H, world, rank)
+        self.hl = self.r1 - self.r0
+        if self.hl < frame:
+            raise ValueError(f"slab height {self.hl} < frame {frame}")
+        self.pitch = pitch
+        self.rows = self.hl + 2 * frame
+        self.bufs = [torch.zeros((B, C, self.rows, pitch), dtype=torch.float32, device=device) for _ in range(2)]
+        self.cur = 0
+
+    @property
+    def buf(self):
+        return self.bufs[self.cur]
+
+    @property
+    def other(self):
+        return self.bufs[self.cur ^ 1]
+
+    def interior(self, t=None) -> torch.Tensor:
+        t = self.buf if t is None else t
+        return t[:, :, self.F:self.F + self.hl, self.F:self.F + self.W]
+
+    def ghost_blocks(self, t: torch.Tensor):
+        """(up_send, up_recv, down_send, down_recv) lists of contiguous row blocks (full framed rows, so the
+        x-frame travels with them)."""
+        F, hl = self.F, self.hl
+        us, ur, ds, dr = [], [], [], []
+        for b in range(self.B):
+            for c in range(self.C):
+                p = t[b, c]
+                us.append(p[F:2 * F])
+                ur.append(p[0:F])
+                ds.append(p[hl:hl + F])
+                dr.append(p[hl + F:hl + 2 * F])
+        return us, ur, ds, dr
+
+    def exchange(self, t=None, group=None):
+        t = self.buf if t is None else t
+        us, ur, ds, dr = self.ghost_blocks(t)
+        exchange_ghost_rows(us, ur, ds, dr, self.rank, self.world, group)
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA drivers of the slabs (one process per GPU; torch.distributed NCCL for the halo exchange)
+# ------------------------------------------------------------------------------------------------
+class GolSlabCUDA(GolSlab):
+    """GolSlab whose local generations run through b200ca_gol_run(vert_open=1)."""
+
+    def __init__(self, H, W, rank, world, ghost=16, device="cuda", s_mask=0b1100, b_mask=0b1000):
+        super().__init__(H, W, rank, world, ghost, device)
+        self.s_mask, self.b_mask = s_mask, b_mask
+        self.device = torch.device(device)
+
+    def _step_fn(self, src, dst, rows, n):
+        from . import _lib
+
+        with torch.cuda.device(self.device):
+            _lib.call("b200ca_gol_run", _lib.ptr(src), _lib.ptr(dst), rows, self.W, self.stride, self.s_mask, self.b_mask, 1, n,
+                      _lib.current_stream(self.device))
+        return dst if (n & 1) else src
+
+    def random_fill(self, seed: int):
+        """Fills the OWNED rows with the rows [r0, r1) of the synthetic world `seed` (same bits for any N)."""
+        from . import _lib
+
+        own = self.owned()
+        with torch.cuda.device(self.device):
+            _lib.call("b200ca_gol_random_fill", _lib.ptr(own), self.hl, self.W, self.stride, seed, self.r0,
+                      _lib.current_stream(self.device))
+        self.fresh = 0
+
+    def run(self, nsteps: int, group=None):
+        self.advance(self._step_fn, nsteps, group)
+
+    def population(self) -> int:
+        from . import _lib
+
+        cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
+        own = self.owned()
+        with torch.cuda.device(self.device):
+            _lib.call("b200ca_gol_population", _lib.ptr(own), self.hl, self.W, self.stride, _lib.ptr(cnt),
+                      _lib.current_stream(self.device))
+        return int(cnt.item())
+
+
+class LeniaSlabCUDA(LeniaSlab):
+    """Lenia row slab on one GPU: boundary tile rows first, halo exchange on a side stream overlapped with
+    the interior tiles (Lenia.step semantics, lenia.py:430-451, on rows [r0, r1) of the global torus)."""
+
+    def __init__(self, lenia_params, C, H, W, rank, world, device="cuda", dt=0.1, overlap=True):
+        from . import _lib
+        from .lenia_params import compute_kernel
+
+        L = _lib.lib()
+        B = lenia_params["weights"].shape[0]
+        super().__init__(B, C, H, W, rank, world, _lib.FRAME, L.b200ca_frame_pitch(W), device)
+        self.device = torch.device(device)
+        self.dt = dt
+        p = lenia_params.to(device).param_dict
+        self.k_mult = p.get("k_mult", 1)
+        self.mu = p["mu"].float().contiguous()
+        self.sigma = p["sigma"].float().contiguous()
+        self.weights = p["weights"].float().contiguous()
+        self.k = compute_kernel(lenia_params, C).float().contiguous()
+        self._kprep = torch.empty(L.b200ca_lenia_kprep_elems(B, C, self.k_mult), dtype=torch.float32, device=device)
+        with torch.cuda.device(self.device):
+            _lib.call("b200ca_lenia_prepare_kernel", _lib.ptr(self.k), _lib.ptr(self._kprep), B, C, self.k_mult, int(p["k_size"]),
+                      _lib.current_stream(self.device))
+        self.tile_rows = L.b200ca_lenia_tile_rows(self.hl, W, B, C)
+        self.n_tile_rows = (self.hl + self.tile_rows - 1) // self.tile_rows
+        self.n_boundary = (self.F + self.tile_rows - 1) // self.tile_rows  # tile rows covering F owned rows
+        self.overlap = overlap and world > 1 and self.n_tile_rows > 2 * self.n_boundary
+        self.comm_stream = torch.cuda.Stream(device=self.device) if world > 1 else None
+        self.launches_per_step = 3 if self.overlap else 1
+
+    def set_interior(self, dense: torch.Tensor, group=None):
+        """dense: (B,C,hl,W) rows [r0,r1) of the global state."""
+        from . import _lib
+
+        self.interior().copy_(dense)
+        with torch.cuda.device(self.device):
+            _lib.call("b200ca_frame_refresh", _lib.ptr(self.buf), self.B, self.C, self.hl, self.W, 1 if self.world == 1 else 0,
+                      _lib.current_stream(self.device))
+        if self.world > 1:
+            self.exchange(self.buf, group)
+
+    def _launch(self, t0, t1):
+        from . import _lib
+
+        _lib.call("b200ca_lenia_step", _lib.ptr(self.buf), _lib.ptr(self.other), _lib.ptr(self._kprep), _lib.ptr(self.mu),
+                  _lib.ptr(self.sigma), _lib.ptr(self.weights), self.B, self.C, self.k_mult, self.hl, self.W, float(self.dt), 0,
+                  1 if self.world == 1 else 0, t0, t1, _lib.current_stream(self.device))
+
+    def step(self, group=None):
+        with torch.cuda.device(self.device):
+            if self.world == 1:
+                self._launch(0, 0)
+            elif not self.overlap:
+                self._launch(0, 0)
+                self.exchange(self.other, group)
+            else:
+                nb, T = self.n_boundary, self.n_tile_rows
+                main = torch.cuda.current_stream(self.device)
+                self._launch(0, nb)
+                self._launch(T - nb, T)
+                self.comm_stream.wait_stream(main)
+                with torch.cuda.stream(self.comm_stream):
+                    self.exchange(self.other, group)
+                self._launch(nb, T - nb)
+                main.wait_stream(self.comm_stream)
+        self.cur ^= 1
