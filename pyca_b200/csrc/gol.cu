@@ -178,6 +178,129 @@ __global__ void __launch_bounds__(128) gol_step_kernel(const uint32_t *__restric
     }
 }
 
+// ---- fast path: W % 128 == 0 (uint4 per thread), H % RPT == 0, no per-word fix-ups ---------------------
+// Works on the 9-cell sums (centre included): per row and word only the 2-bit horizontal sum west+centre+east
+// is kept (2 SHF + 2 LOP3, computed once per row, used by three output rows); an output word adds the three
+// row sums bit-sliced (6 LOP3) and applies the rule on count9 (Life: count9==3 | alive & count9==4, 2 LOP3).
+// Per row and thread additionally: 1 LDG.128, 1 predicated edge LDG.32 (warp-edge lanes), 2 SHFL, 1 STG.128.
+// No branches in the row loop: threads past the row end load a clamped column and skip the store.
+struct Row4 {
+    uint32_t c[4], s0[4], s1[4];
+};
+
+__device__ __forceinline__ void gol_fast_load(Row4 &R, const uint32_t *__restrict__ base, uint32_t off_main, uint32_t off_edge,
+                                              bool edge_l, bool edge_r, uint32_t live_mask) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base + off_main));
+    uint32_t ev = 0u;
+    if (edge_l || edge_r) ev = __ldg(base + off_edge);
+    uint32_t left = __shfl_up_sync(0xffffffffu, v.w, 1);
+    uint32_t right = __shfl_down_sync(0xffffffffu, v.x, 1);
+    left = edge_l ? ev : left;
+    right = edge_r ? ev : right;
+    const uint32_t c[4] = {v.x & live_mask, v.y & live_mask, v.z & live_mask, v.w & live_mask};
+    left &= live_mask;
+    right &= live_mask;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t L = k == 0 ? left : c[k - 1];
+        const uint32_t Rw = k == 3 ? right : c[k + 1];
+        const uint32_t w = __funnelshift_l(L, c[k], 1);
+        const uint32_t e = __funnelshift_r(c[k], Rw, 1);
+        R.c[k] = c[k];
+        R.s0[k] = w ^ e ^ c[k];
+        R.s1[k] = (w & e) | (c[k] & (w ^ e));
+    }
+}
+
+// rule on the 9-cell count: p, q, n = 2-bit row sums (above, own, below), c = centre cells
+template <bool LIFE>
+__device__ __forceinline__ uint32_t gol_rule9(uint32_t p0, uint32_t p1, uint32_t q0, uint32_t q1, uint32_t n0, uint32_t n1, uint32_t c,
+                                              const RuleMasks &rm) {
+    const uint32_t z0 = p0 ^ q0 ^ n0;
+    const uint32_t k0 = (p0 & q0) | (n0 & (p0 ^ q0));
+    const uint32_t z1 = p1 ^ q1 ^ n1;
+    const uint32_t k1 = (p1 & q1) | (n1 & (p1 ^ q1));
+    const uint32_t y1 = k0 ^ z1;
+    const uint32_t y2 = k1 ^ (k0 & z1);
+    if (LIFE) {
+        // count9 == 3 (z0=1,y1=1,y2=0)  |  alive & count9 == 4 (z0=0,y1=0,y2=1); count9 >= 8 has y1 == 0 and y2 == 0
+        const uint32_t x = (y2 & c & ~z0) | (~y2 & z0);
+        return x & ~(z0 ^ y1);
+    } else {
+        const uint32_t y3 = k1 & k0 & z1;
+        uint32_t m[10];  // value for count9 == k: alive cells look at S[k-1], dead cells at B[k]
+#pragma unroll
+        for (int k = 0; k < 10; ++k) m[k] = (k > 0 ? (c & rm.s[k - 1]) : 0u) | (k < 9 ? (~c & rm.b[k]) : 0u);
+        const uint32_t q_0 = (z0 & m[1]) | (~z0 & m[0]);
+        const uint32_t q_1 = (z0 & m[3]) | (~z0 & m[2]);
+        const uint32_t q_2 = (z0 & m[5]) | (~z0 & m[4]);
+        const uint32_t q_3 = (z0 & m[7]) | (~z0 & m[6]);
+        const uint32_t q_4 = (z0 & m[9]) | (~z0 & m[8]);
+        const uint32_t h0 = (y1 & q_1) | (~y1 & q_0);
+        const uint32_t h1 = (y1 & q_3) | (~y1 & q_2);
+        const uint32_t f = (y2 & h1) | (~y2 & h0);
+        return (y3 & q_4) | (~y3 & f);
+    }
+}
+
+template <bool LIFE, bool OPEN, int RPT>
+__global__ void __launch_bounds__(128, 6) gol_fast_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int H, int wpr,
+                                                           int stride, uint32_t s_mask, uint32_t b_mask) {
+    const int lane = threadIdx.x & 31;
+    const int units = wpr >> 2;
+    const int unit_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = unit_raw < units;
+    const int unit = valid ? unit_raw : units - 1;
+    const uint32_t j0 = unit * 4;
+    // warp-edge lanes fetch the neighbouring word from memory; (units % 32 != 1 is guaranteed by the launcher, so
+    // no lane needs both)
+    const bool edge_l = (lane == 0), edge_r = !edge_l && ((lane == 31) || (unit == units - 1));
+    const uint32_t je = edge_l ? (unit == 0 ? wpr : j0) - 1 : ((unit == units - 1) ? 0 : j0 + 4);
+    const int r0 = blockIdx.y * RPT;  // H % RPT == 0: every block owns RPT full rows
+    RuleMasks rm;
+    if (!LIFE) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            rm.s[k] = ((s_mask >> k) & 1u) ? 0xffffffffu : 0u;
+            rm.b[k] = ((b_mask >> k) & 1u) ? 0xffffffffu : 0u;
+        }
+    }
+    // rows r0 .. r0+RPT-1 are contiguous; only the row above the first and below the last may wrap / be dead
+    const int ra = r0 == 0 ? (OPEN ? 0 : H - 1) : r0 - 1;
+    const int rb = r0 + RPT == H ? (OPEN ? H - 1 : 0) : r0 + RPT;
+    const uint32_t ma = (OPEN && r0 == 0) ? 0u : 0xffffffffu;
+    const uint32_t mb = (OPEN && r0 + RPT == H) ? 0u : 0xffffffffu;
+    const uint32_t ustride = (uint32_t)stride;
+    uint32_t row_off = (uint32_t)r0 * ustride;  // H * stride < 2^32 words is guaranteed by the launcher
+    Row4 Q, N;
+    uint32_t a0[4], a1[4];
+    gol_fast_load(N, in, (uint32_t)ra * ustride + j0, (uint32_t)ra * ustride + je, edge_l, edge_r, ma);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        a0[k] = N.s0[k];
+        a1[k] = N.s1[k];
+    }
+    gol_fast_load(Q, in, row_off + j0, row_off + je, edge_l, edge_r, 0xffffffffu);
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const uint32_t next_off = row_off + ustride;
+        if (i == RPT - 1)
+            gol_fast_load(N, in, (uint32_t)rb * ustride + j0, (uint32_t)rb * ustride + je, edge_l, edge_r, mb);
+        else
+            gol_fast_load(N, in, next_off + j0, next_off + je, edge_l, edge_r, 0xffffffffu);
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            o[k] = gol_rule9<LIFE>(a0[k], a1[k], Q.s0[k], Q.s1[k], N.s0[k], N.s1[k], Q.c[k], rm);
+            a0[k] = Q.s0[k];
+            a1[k] = Q.s1[k];
+        }
+        if (valid) *reinterpret_cast<uint4 *>(out + (row_off + j0)) = make_uint4(o[0], o[1], o[2], o[3]);
+        row_off = next_off;
+        Q = N;
+    }
+}
+
 // ---- pack / unpack / population / random fill ---------------------------------------------------
 template <typename T>
 __global__ void gol_pack_kernel(const T *__restrict__ world, uint32_t *__restrict__ bits, int H, int W, int stride, int wpr) {
@@ -276,6 +399,29 @@ static int launch_step(const uint32_t *in, uint32_t *out, const GolGeom &g, uint
     return 0;
 }
 
+template <bool LIFE, bool OPEN, int RPT>
+static int launch_fast_t(const uint32_t *in, uint32_t *out, const GolGeom &g, uint32_t s, uint32_t b, cudaStream_t st) {
+    const int units = g.wpr / 4;
+    const int bx = units >= 128 ? 128 : ceil_div(units, 32) * 32;
+    dim3 grid(ceil_div(units, bx), ceil_div(g.H, RPT));
+    gol_fast_kernel<LIFE, OPEN, RPT><<<grid, bx, 0, st>>>(in, out, g.H, g.wpr, g.stride, s, b);
+    B200CA_LAUNCH_CHECK("gol_fast_kernel");
+    return 0;
+}
+
+static int launch_fast(const uint32_t *in, uint32_t *out, const GolGeom &g, uint32_t s, uint32_t b, cudaStream_t st) {
+    const bool life = (s == 0b1100u && b == 0b1000u);
+    // 16 rows per thread when that still gives every SM several blocks, else 4
+    const long long blocks16 = (long long)ceil_div(g.wpr / 4, 128) * ceil_div(g.H, 16);
+    const bool big = (g.H % 16 == 0) && blocks16 >= (long long)num_sms() * 12;
+    if (life) {
+        if (g.vert_open) return big ? launch_fast_t<true, true, 16>(in, out, g, s, b, st) : launch_fast_t<true, true, 4>(in, out, g, s, b, st);
+        return big ? launch_fast_t<true, false, 16>(in, out, g, s, b, st) : launch_fast_t<true, false, 4>(in, out, g, s, b, st);
+    }
+    if (g.vert_open) return big ? launch_fast_t<false, true, 16>(in, out, g, s, b, st) : launch_fast_t<false, true, 4>(in, out, g, s, b, st);
+    return big ? launch_fast_t<false, false, 16>(in, out, g, s, b, st) : launch_fast_t<false, false, 4>(in, out, g, s, b, st);
+}
+
 static int gol_step_impl(const uint32_t *in, uint32_t *out, int H, int W, int stride, uint32_t s, uint32_t b, int vert_open,
                          cudaStream_t st) {
     GolGeom g;
@@ -284,6 +430,8 @@ static int gol_step_impl(const uint32_t *in, uint32_t *out, int H, int W, int st
     B200CA_REQUIRE(in && out && in != out, "gol_step: null or aliased buffers");
     B200CA_REQUIRE(s < 512 && b < 512, "gol_step: rule masks are 9-bit");
     const bool vec4 = g.aligned && (g.wpr % 4 == 0) && (stride % 4 == 0) && ((((uintptr_t)in) | ((uintptr_t)out)) % 16 == 0);
+    if (vec4 && (g.H % 4 == 0) && ((g.wpr / 4) % 32 != 1 || g.wpr == 4) && (long long)g.H * g.stride < (1ll << 32) && g.wpr > 4)
+        return launch_fast(in, out, g, s, b, st);
     // enough row bands to fill the machine: 16 rows per thread for big worlds, 4 for small ones
     const long long units = (long long)ceil_div(g.wpr, vec4 ? 4 : 1) * ceil_div(H, 16);
     const bool big = units >= (long long)num_sms() * 128 * 8;
