@@ -170,7 +170,7 @@ class LeniaWL(Workload):
             g = torch.Generator().manual_seed(0)
             self.h_state = torch.rand(1, self.C, self.H, self.W, generator=g).pin_memory()
             self.auto = pyca_b200.Lenia((self.H, self.W), num_channels=self.C, params=self.params, state_init=self.h_state,
-                                        device=self.device)
+                                        device=self.device, conv_path=os.environ.get("B200CA_LENIA_PATH", "auto"))
             self.slab = None
         else:
             self.slab = LeniaSlabCUDA(self.params, self.C, self.H, self.W, self.rank, self.world, device=self.device)
@@ -483,6 +483,8 @@ def make_workload(name, rank, world, device):
         return LeniaWL(rank, world, device, 1024, 1024, 3, name)
     if name == "lenia_4k":
         return LeniaWL(rank, world, device, 4096, 4096, 1, name)
+    if name == "lenia_seg":
+        return LeniaWL(rank, world, device, 4096, 3976, 1, name)
     if name == "lenia_16k":
         return LeniaWL(rank, world, device, 16384, 16384, 1, name)
     if name == "gol_64k":

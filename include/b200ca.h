@@ -115,6 +115,21 @@ int b200ca_lenia_step(const float *state_in, float *state_out, const float *Kpre
                       const float *weights, int B, int C, int k_mult, int H, int W, float dt, int mode, int row_wrap,
                       int tile_row_begin, int tile_row_end, void *stream);
 
+/* FFT path of the same operator (row FFT x column-direct hybrid, see pyca_b200/csrc/lenia_fft.cu): identical
+ * arguments and semantics to b200ca_lenia_step; supported when H is even (>= 32) and W >= 64.  The x direction is an
+ * exact periodic transform when W is 256, 1024 or 4096, overlap-save segments otherwise.
+ *   b200ca_lenia_fft_length        transform length N the path would use for an HxW world (0 = unsupported)
+ *   b200ca_lenia_fft_kernel_elems  floats of the prepared kernel spectra  (B, C*k_mult, C, 16, N)
+ *   b200ca_lenia_fft_workspace_elems floats of the row-spectra workspace the step needs
+ *   b200ca_lenia_fft_prepare_kernel  K (B, C*k_mult, C, ks, ks) -> Kfft (cold path, update_params) */
+int b200ca_lenia_fft_length(int H, int W);
+int64_t b200ca_lenia_fft_kernel_elems(int B, int C, int k_mult, int H, int W);
+int64_t b200ca_lenia_fft_workspace_elems(int B, int C, int k_mult, int H, int W);
+int b200ca_lenia_fft_prepare_kernel(const float *K, float *Kfft, int B, int C, int k_mult, int ks, int H, int W, void *stream);
+int b200ca_lenia_step_fft(const float *state_in, float *state_out, const float *Kfft, const float *mu, const float *sigma,
+                          const float *weights, float *workspace, int B, int C, int k_mult, int H, int W, float dt, int mode,
+                          int row_wrap, void *stream);
+
 /* Mass-conserving redistribution (+ optional cross-channel mixing).  Replaces
  * MaCELenia._mace_step (macelenia.py:89-120) after the affinity, and
  * MaCELeniaXChan._cross_chan_step (mace_lenia_xchan.py:68-76) when alpha_on != 0:

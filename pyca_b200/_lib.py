@@ -36,6 +36,12 @@ SIGNATURES = {
     "b200ca_lenia_tile_rows": (c_int, [c_int, c_int, c_int, c_int]),
     "b200ca_lenia_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                   c_int, c_float, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200ca_lenia_fft_length": (c_int, [c_int, c_int]),
+    "b200ca_lenia_fft_kernel_elems": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
+    "b200ca_lenia_fft_workspace_elems": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
+    "b200ca_lenia_fft_prepare_kernel": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200ca_lenia_step_fft": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                      c_int, c_int, c_float, c_int, c_int, c_void_p]),
     "b200ca_mace_redistribute": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_float,
                                          c_int, c_void_p]),
     "b200ca_frame_mass": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -102,7 +102,10 @@ class Lenia(Automaton):
     """
 
     def __init__(self, size, dt=0.1, num_channels=3, params=None, state_init=None, device="cuda",
-                 interest_files=None, save_dir="."):
+                 interest_files=None, save_dir=".", conv_path="auto"):
+        """conv_path: 'direct' (TMA-tiled folded spatial convolution), 'fft' (row-FFT x column-direct hybrid) or
+        'auto' (fft when the world shape supports it, else direct)."""
+        self.conv_path = conv_path
         if len(size) == 2:
             size = (1,) + tuple(size)
         Automaton.__init__(self, size[1:], device)
@@ -196,14 +199,33 @@ class Lenia(Automaton):
         with torch.cuda.device(self.device):
             _lib.call("b200ca_lenia_prepare_kernel", _lib.ptr(self.k), _lib.ptr(self._kprep), self.batch, self.C, self.k_mult,
                       int(self.k_size), _lib.current_stream(self.device))
+        # FFT path (optional): prepared kernel spectra + row-spectra workspace
+        self._kfft = self._fft_ws = None
+        fft_ok = L.b200ca_lenia_fft_length(self.h, self.w) > 0
+        if self.conv_path == "fft" and not fft_ok:
+            raise _lib.B200CAError(f"conv_path='fft' is not supported for a {self.h}x{self.w} world (H even >= 32, W >= 64)")
+        self.use_fft = fft_ok and self.conv_path in ("fft", "auto")
+        if self.use_fft:
+            self._kfft = torch.empty(L.b200ca_lenia_fft_kernel_elems(self.batch, self.C, self.k_mult, self.h, self.w),
+                                     dtype=torch.float32, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.call("b200ca_lenia_fft_prepare_kernel", _lib.ptr(self.k), _lib.ptr(self._kfft), self.batch, self.C, self.k_mult,
+                          int(self.k_size), self.h, self.w, _lib.current_stream(self.device))
+            self._fft_ws = torch.empty(L.b200ca_lenia_fft_workspace_elems(self.batch, self.C, self.k_mult, self.h, self.w),
+                                       dtype=torch.float32, device=self.device)
 
     # ---- hot path ---------------------------------------------------------------------------------
     def _conv(self, dst: torch.Tensor, mode: int):
         fs = self._fs
         with torch.cuda.device(fs.device):
-            _lib.call("b200ca_lenia_step", _lib.ptr(fs.buf), _lib.ptr(dst), _lib.ptr(self._kprep), _lib.ptr(self.mu),
-                      _lib.ptr(self.sigma), _lib.ptr(self.weights), fs.B, fs.C, self.k_mult, fs.H, fs.W, float(self.dt), mode,
-                      1, 0, 0, _lib.current_stream(fs.device))
+            if self.use_fft:
+                _lib.call("b200ca_lenia_step_fft", _lib.ptr(fs.buf), _lib.ptr(dst), _lib.ptr(self._kfft), _lib.ptr(self.mu),
+                          _lib.ptr(self.sigma), _lib.ptr(self.weights), _lib.ptr(self._fft_ws), fs.B, fs.C, self.k_mult, fs.H, fs.W,
+                          float(self.dt), mode, 1, _lib.current_stream(fs.device))
+            else:
+                _lib.call("b200ca_lenia_step", _lib.ptr(fs.buf), _lib.ptr(dst), _lib.ptr(self._kprep), _lib.ptr(self.mu),
+                          _lib.ptr(self.sigma), _lib.ptr(self.weights), fs.B, fs.C, self.k_mult, fs.H, fs.W, float(self.dt), mode,
+                          1, 0, 0, _lib.current_stream(fs.device))
 
     @torch.no_grad()
     def step(self):
@@ -238,14 +260,14 @@ class MaCELenia(Lenia):
     """
 
     def __init__(self, size, num_channels=3, params=None, state_init=None, device="cuda", has_food=False, sense_food=False,
-                 interest_files=None, save_dir="."):
+                 interest_files=None, save_dir=".", conv_path="auto"):
         if has_food or sense_food:
             raise _lib.B200CAError("the MaCE food subsystem is not built yet (SURVEY.md 8f-3)")
         self.has_food = False
         self.sense_food = False
         self._beta = 8
         super().__init__(size, dt=0.1, num_channels=num_channels, params=params, state_init=state_init, device=device,
-                         interest_files=interest_files, save_dir=save_dir)
+                         interest_files=interest_files, save_dir=save_dir, conv_path=conv_path)
         self.show_batch = 0
 
     def _init_family_buffers(self):
@@ -303,9 +325,9 @@ class MaCELeniaXChan(MaCELenia):
     """
 
     def __init__(self, size, num_channels=3, params=None, state_init=None, device="cuda", has_food=False, sense_food=False,
-                 interest_files=None, save_dir="."):
+                 interest_files=None, save_dir=".", conv_path="auto"):
         super().__init__(size, num_channels, params, state_init, device=device, has_food=has_food, sense_food=sense_food,
-                         interest_files=interest_files, save_dir=save_dir)
+                         interest_files=interest_files, save_dir=save_dir, conv_path=conv_path)
         # the reference constructor resets these after update_params ran (mace_lenia_xchan.py:47-49)
         self._beta = 6
         self.alpha = 0.03

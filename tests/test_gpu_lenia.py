@@ -26,13 +26,19 @@ def sliced(d, c):
     return {k: (v[:, :c, :c].clone() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
 
 
+PATHS = ["direct", "fft"]
+
+
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("name", golden_names("lenia"))
-def test_lenia_golden(name):
+def test_lenia_golden(name, path):
     import pyca_b200
 
     fx, p = family_case("lenia", name)
     s0 = t(fx["state_in"])
-    a = pyca_b200.Lenia(tuple(s0.shape[2:]), dt=float(fx["dt"]), params=params_dict(p), state_init=s0, device="cuda")
+    a = pyca_b200.Lenia(tuple(s0.shape[2:]), dt=float(fx["dt"]), params=params_dict(p), state_init=s0, device="cuda",
+                        conv_path=path)
+    assert a.use_fft == (path == "fft")
     assert torch.allclose(a.k.cpu(), t(p["K"]), atol=1e-8), "host kernel construction differs from the reference's"
     a.step()
     err = (a.state.cpu() - t(fx["state_out"])).abs().max().item()
@@ -40,20 +46,21 @@ def test_lenia_golden(name):
     assert a.frames == 1
     # single-channel slice of the same file (BASELINE configs[1])
     a1 = pyca_b200.Lenia(tuple(s0.shape[2:]), dt=float(fx["dt"]), num_channels=1, params=sliced(params_dict(p), 1),
-                         state_init=s0[:, :1], device="cuda")
+                         state_init=s0[:, :1], device="cuda", conv_path=path)
     assert torch.allclose(a1.k.cpu(), t(fx["c1_K"]), atol=1e-8)
     a1.step()
     err1 = (a1.state.cpu() - t(fx["c1_out"])).abs().max().item()
     assert err1 <= TOL, f"{name} C=1: max-abs {err1:.2e}"
 
 
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("name", golden_names("mace"))
-def test_mace_golden(name):
+def test_mace_golden(name, path):
     import pyca_b200
 
     fx, p = family_case("mace", name)
     s0 = t(fx["state_in"])
-    a = pyca_b200.MaCELenia(tuple(s0.shape[2:]), params=params_dict(p), state_init=s0, device="cuda")
+    a = pyca_b200.MaCELenia(tuple(s0.shape[2:]), params=params_dict(p), state_init=s0, device="cuda", conv_path=path)
     assert a.b == float(fx["b"])
     m0 = a.total_mass().cpu()
     a.step()
@@ -65,13 +72,14 @@ def test_mace_golden(name):
     assert torch.allclose(m0, m1, rtol=1e-6), "mass not conserved"
 
 
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("name", golden_names("xchan"))
-def test_xchan_golden(name):
+def test_xchan_golden(name, path):
     import pyca_b200
 
     fx, p = family_case("xchan", name)
     s0 = t(fx["state_in"])
-    a = pyca_b200.MaCELeniaXChan(tuple(s0.shape[2:]), params=params_dict(p), state_init=s0, device="cuda")
+    a = pyca_b200.MaCELeniaXChan(tuple(s0.shape[2:]), params=params_dict(p), state_init=s0, device="cuda", conv_path=path)
     a.alpha = float(fx["alpha_used"])
     assert a.b == float(fx["b"])
     m0 = a.total_mass().cpu()
@@ -88,15 +96,20 @@ def _oracle_params(name="abominable_mongolic", tag="lenia"):
     return params_dict(p), t(p["K"]), t(p["mu_s"]), t(p["sigma_s"]), t(p["weights_s"])
 
 
-@pytest.mark.parametrize("shape", [(32, 32), (50, 70), (64, 64), (65, 129), (100, 47), (31 + 1, 200), (256, 256)])
-def test_lenia_odd_shapes_vs_oracle(shape):
-    """Tile overhang, partial strips and worlds narrower than a tile."""
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("shape", [(32, 32), (50, 70), (64, 64), (65, 129), (100, 47), (31 + 1, 200), (256, 256), (34, 500),
+                                   (96, 1024), (40, 1100)])
+def test_lenia_odd_shapes_vs_oracle(shape, path):
+    """Tile overhang, partial strips, worlds narrower than a tile; FFT path: periodic (W = 256, 1024) and overlap-save
+    segments (one, several, partial last)."""
     import pyca_b200
 
+    if path == "fft" and pyca_b200.lib().b200ca_lenia_fft_length(*shape) == 0:
+        pytest.skip("shape not supported by the FFT path")
     d, K, mu, sg, w = _oracle_params()
     g = torch.Generator().manual_seed(shape[0] * 1000 + shape[1])
     s0 = torch.rand(1, 3, *shape, generator=g)
-    a = pyca_b200.Lenia(shape, params=d, state_init=s0, device="cuda")
+    a = pyca_b200.Lenia(shape, params=d, state_init=s0, device="cuda", conv_path=path)
     a.step()
     ref = orc.lenia_step(s0, K, mu, sg, w, 0.1)
     err = (a.state.cpu() - ref).abs().max().item()
@@ -167,7 +180,8 @@ def test_lenia_multistep_statistics():
     assert abs(got.std().item() - ref.std().item()) < 5e-3
 
 
-def test_vs_float64_noise_floor():
+@pytest.mark.parametrize("path", PATHS)
+def test_vs_float64_noise_floor(path):
     """|cuda - ref64| must not exceed the reference's own fp32 rounding error |ref32 - ref64| by much
     (BASELINE.md section 6)."""
     import pyca_b200
@@ -175,13 +189,13 @@ def test_vs_float64_noise_floor():
     d, K, mu, sg, w = _oracle_params("arborical_asbestosis", "xchan")
     g = torch.Generator().manual_seed(33)
     s0 = torch.rand(1, 3, 128, 128, generator=g)
-    a = pyca_b200.MaCELenia((128, 128), params=d, state_init=s0, device="cuda")
+    a = pyca_b200.MaCELenia((128, 128), params=d, state_init=s0, device="cuda", conv_path=path)
     aff = a._compute_affinity().cpu()
     aff32 = orc.lenia_affinity(s0, K, mu, sg, w)
     aff64 = orc.lenia_affinity_f64(s0, K, mu, sg, w)
     e_cuda = (aff.double() - aff64).abs().max().item()
     e_ref = (aff32.double() - aff64).abs().max().item()
-    print(f"affinity error vs fp64: cuda {e_cuda:.2e}, reference fp32 {e_ref:.2e}")
+    print(f"[{path}] affinity error vs fp64: cuda {e_cuda:.2e}, reference fp32 {e_ref:.2e}")
     assert e_cuda <= max(4 * e_ref, 2e-6)
 
 
@@ -232,7 +246,7 @@ def test_periodic_tiling_identity():
     for ty in range(2):
         for tx in range(2):
             tile = bg[:, :, ty * 96:(ty + 1) * 96, tx * 160:(tx + 1) * 160]
-            assert (tile - sm).abs().max().item() <= 2e-6
+            assert (tile - sm).abs().max().item() <= 1e-5  # different tilings/segmentations round differently
 
 
 def test_host_entry_point():

@@ -47,12 +47,13 @@ def main():
         d3 = pd("params_lenia_abominable_mongolic.npz")
         d1 = {k: (v[:, :1, :1].clone() if isinstance(v, torch.Tensor) else v) for k, v in d3.items()}
         for (C, d, H, W) in [(1, d1, 1024, 1024), (3, d3, 1024, 1024), (1, d1, 4096, 4096), (3, d3, 4096, 4096), (1, d1, 16384, 16384)]:
-            a = pyca_b200.Lenia((H, W), num_channels=C, params=d, state_init=torch.rand(1, C, H, W), device="cuda")
-            ms = timeit(a.step, 10 if H >= 4096 else 50)
-            fma = H * W * C * C * 496
-            print(f"Lenia C={C} {H}x{W}: {ms:.3f} ms/step -> {H*W/ms/1e6:.2f} GCUPS; {fma/ms/1e9:.2f} TFMA/s (folded);"
-                  f" alg bytes {H*W*C*8/ms/1e6:.1f} GB/s", flush=True)
-            del a
+            for path in ("direct", "fft"):
+                a = pyca_b200.Lenia((H, W), num_channels=C, params=d, state_init=torch.rand(1, C, H, W), device="cuda", conv_path=path)
+                ms = timeit(a.step, 10 if H >= 4096 else 50)
+                fma = H * W * C * C * 496
+                print(f"Lenia[{path}] C={C} {H}x{W}: {ms:.3f} ms/step -> {H*W/ms/1e6:.2f} GCUPS; {fma/ms/1e9:.2f} TFMA/s (folded-direct equiv);"
+                      f" alg bytes {H*W*C*8/ms/1e6:.1f} GB/s", flush=True)
+                del a
     if "mace" in which:
         d = pd("params_xchan_arborical_asbestosis.npz")
         for (H, W) in [(1024, 1024), (4096, 4096)]:
