@@ -12,15 +12,18 @@
 // of 496 FMA for the folded direct path; the column direction stays local (15 ghost rows), so row slabs and
 // the periodic frame work exactly as for the direct path.
 //
-//   kernel A  lenia_fft_rows_kernel   one CTA per row pair (r, r+D), r in [-15, D+15): in-place radix-4
-//             decimation-in-frequency FFT in shared memory (natural order in, base-4 digit-reversed out),
-//             spectrum written to a workspace in HBM.
-//   kernel B  lenia_fft_cols_kernel   one CTA per TH row pairs x segment: FIR along rows straight from the
-//             workspace (L2) into registers, spectra parked in shared memory, in-place radix-4
-//             decimation-in-time inverse FFT (digit-reversed in, natural out; 1/N folded into Khat), then
-//             growth + weighted source sum + Euler step/clamp (or affinity) with the periodic frame.
-// The x direction uses the exact periodic transform when W == N (N in {256, 1024, 4096}), otherwise overlap-save
-// segments of N = 1024 with N-30 valid outputs read from the framed layout.
+//   kernel A  lenia_fft_rows_kernel  one CTA per (two) row pairs (r, r+D), r in [-15, D+15): in-place radix-4
+//             decimation-in-frequency FFT in shared memory (natural order in, base-4 digit-reversed out; first
+//             and last stage fused with the global loads/stores), spectra Z written to a workspace.
+//   kernel B1 lenia_fft_fir_kernel   the column FIR: one frequency per thread, 32 output rows per thread, every
+//             spectrum value loaded once and fanned out with packed FFMA2; writes the filtered spectra O.
+//   kernel B2 lenia_fft_inv_kernel   one CTA per row pair: in-place radix-4 decimation-in-time inverse FFT
+//             (digit-reversed in, natural out; 1/N folded into Khat), then growth + weighted source sum +
+//             Euler step/clamp (or affinity) and the periodic frame of the output.
+// The x direction uses the exact periodic transform when W == N (N in {256, 1024}), otherwise overlap-save
+// segments (N = 1024, or 256 for narrow worlds) with N-30 valid outputs read from the framed layout.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200ca {
@@ -38,8 +41,9 @@ struct FftGeom {
 };
 
 // complex helpers on float2
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// (packed fp32x2 instructions of sm_100: one FADD2 / FFMA2 per complex add / real-times-complex FMA)
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
 __device__ __forceinline__ float2 cmulc(float2 a, float2 w) { return make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y); }  // a*conj(w)
 
@@ -71,54 +75,82 @@ __device__ __forceinline__ void dit4_inv(float2 &a, float2 &b, float2 &c, float2
 // passes) free of bank conflicts.  Only the low 4 bits change, so 16-element aligned blocks stay blocks.
 __device__ __forceinline__ int swz(int i) { return i ^ (5 * ((i >> 4) & 3)); }
 
+// Twiddles: one contiguous table per radix-4 stage so that consecutive butterflies read consecutive entries:
+//   tws[(span - 1) + r*span + k] = exp(-2 pi i (r+1) k / (4 span)),  r = 0..2, k < span   (N - 1 entries in total)
+// read with __ldg (8 KB, L1-resident) -- no shared-memory copy, no bank conflicts.
+__device__ __forceinline__ void load_tw(const float2 *__restrict__ tws, int span, int k, float2 &w1, float2 &w2, float2 &w3) {
+    const float2 *t = tws + (span - 1) + k;
+    w1 = __ldg(t);
+    w2 = __ldg(t + span);
+    w3 = __ldg(t + 2 * span);
+}
+
+
 // ---- kernel A: forward row FFTs -------------------------------------------------------------------
-// grid (zrows, nseg, B*C), block N/4 threads, smem 2N float2 (data + twiddles)
-__global__ void __launch_bounds__(1024) lenia_fft_rows_kernel(const float *__restrict__ state, float2 *__restrict__ Z,
-                                                               const float2 *__restrict__ twg, FftGeom g, int H, int W, int pitch) {
+// grid (ceil(zrows / FFT_RPC), nseg, B*C), block N/4 threads, smem FFT_RPC * N float2
+template <int FFT_RPC>
+__global__ void __launch_bounds__(256) lenia_fft_rows_kernel(const float *__restrict__ state, float2 *__restrict__ Z,
+                                                              const float2 *__restrict__ tws, FftGeom g, int H, int W, int pitch) {
     extern __shared__ __align__(16) float2 fsm[];
-    float2 *buf = fsm;           // [N]
-    float2 *tw = fsm + g.N;      // [N]
     const int N = g.N, T = N >> 2, tid = threadIdx.x;
-    const int zr = blockIdx.x, seg = blockIdx.y, plane = blockIdx.z;
-    for (int t = tid; t < N; t += T) tw[t] = __ldg(twg + t);
-    // image rows (framed): r = zr - R (may be negative: frame rows) and r + D
-    const float *rowA = state + ((size_t)plane * (H + 2 * F) + (zr - R + F)) * pitch;
-    const float *rowB = rowA + (size_t)g.D * pitch;
+    const int seg = blockIdx.y, plane = blockIdx.z;
     const int xoff = g.periodic ? F : seg * g.V - R + F;  // framed column of sample n = 0
-    // first stage straight from global memory (span = N/4)
+    int zr[FFT_RPC];
+#pragma unroll
+    for (int q = 0; q < FFT_RPC; ++q) zr[q] = min((int)blockIdx.x * FFT_RPC + q, g.zrows - 1);
+    // first stage straight from global memory (span = N/4, k = tid)
     {
-        float2 v[4];
+        float2 w1, w2, w3;
+        load_tw(tws, T, tid, w1, w2, w3);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int col = xoff + tid + r * T;
-            const bool ok = col < pitch;
-            v[r] = make_float2(ok ? __ldg(rowA + col) : 0.f, ok ? __ldg(rowB + col) : 0.f);
+        for (int q = 0; q < FFT_RPC; ++q) {
+            // image rows (framed): r = zr - R (may be negative: frame rows) and r + D
+            const float *rowA = state + ((size_t)plane * (H + 2 * F) + (zr[q] - R + F)) * pitch;
+            const float *rowB = rowA + (size_t)g.D * pitch;
+            float2 v[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int col = xoff + tid + r * T;
+                const bool ok = col < pitch;
+                v[r] = make_float2(ok ? __ldg(rowA + col) : 0.f, ok ? __ldg(rowB + col) : 0.f);
+            }
+            dif4(v[0], v[1], v[2], v[3], w1, w2, w3);
+            float2 *buf = fsm + q * N;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) buf[swz(tid + r * T)] = v[r];
         }
-        __syncthreads();  // twiddles visible
-        const int m = tid;  // k = tid, span = T: twiddle index k * N/(4*span) = k
-        dif4(v[0], v[1], v[2], v[3], tw[m], tw[2 * m], tw[3 * m]);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) buf[swz(tid + r * T)] = v[r];
     }
     // middle stages in shared memory
     for (int span = T >> 2; span > 1; span >>= 2) {
         __syncthreads();
         const int k = tid & (span - 1);
         const int i0 = ((tid - k) << 2) + k;
-        const int m = k * (T / span);
-        const int p0 = swz(i0), p1 = swz(i0 + span), p2 = swz(i0 + 2 * span), p3 = swz(i0 + 3 * span);
-        float2 a = buf[p0], b = buf[p1], c = buf[p2], d = buf[p3];
-        dif4(a, b, c, d, tw[m], tw[2 * m], tw[3 * m]);
-        buf[p0] = a; buf[p1] = b; buf[p2] = c; buf[p3] = d;
+        float2 w1, w2, w3;
+        load_tw(tws, span, k, w1, w2, w3);
+        // the swizzle only looks at index bits 4-5, which adding a multiple of 64 does not touch
+        const int p0 = swz(i0);
+        const int p1 = span >= 64 ? p0 + span : swz(i0 + span);
+        const int p2 = span >= 64 ? p0 + 2 * span : swz(i0 + 2 * span);
+        const int p3 = span >= 64 ? p0 + 3 * span : swz(i0 + 3 * span);
+#pragma unroll
+        for (int q = 0; q < FFT_RPC; ++q) {
+            float2 *buf = fsm + q * N;
+            float2 a = buf[p0], b = buf[p1], c = buf[p2], d = buf[p3];
+            dif4(a, b, c, d, w1, w2, w3);
+            buf[p0] = a; buf[p1] = b; buf[p2] = c; buf[p3] = d;
+        }
     }
     // last stage (span = 1, twiddles = 1) straight to global memory: 4 consecutive outputs per thread
     __syncthreads();
-    {
+#pragma unroll
+    for (int q = 0; q < FFT_RPC; ++q) {
+        if ((int)blockIdx.x * FFT_RPC + q >= g.zrows) break;
+        const float2 *buf = fsm + q * N;
         const int i0 = tid << 2;
         float2 a = buf[swz(i0)], b = buf[swz(i0 + 1)], c = buf[swz(i0 + 2)], d = buf[swz(i0 + 3)];
         const float2 one = make_float2(1.f, 0.f);
         dif4(a, b, c, d, one, one, one);
-        float4 *out = reinterpret_cast<float4 *>(Z + (((size_t)plane * g.zrows + zr) * g.nseg + seg) * N + i0);
+        float4 *out = reinterpret_cast<float4 *>(Z + (((size_t)plane * g.zrows + zr[q]) * g.nseg + seg) * N + i0);
         out[0] = make_float4(a.x, a.y, b.x, b.y);
         out[1] = make_float4(c.x, c.y, d.x, d.y);
     }
@@ -148,9 +180,12 @@ __global__ void __launch_bounds__(FIR_THREADS) lenia_fft_fir_kernel(const FftFir
     (void)j;
     const int src_plane = b * a.C + i / a.k_mult;
     const float *kf = a.kfft + (size_t)pair * KROWS * N + k;
-    float kt[KROWS];
+    float2 kt[KROWS];  // (w, w): real tap duplicated for the packed FMA
 #pragma unroll
-    for (int dy = 0; dy < KROWS; ++dy) kt[dy] = __ldg(kf + dy * N);
+    for (int dy = 0; dy < KROWS; ++dy) {
+        const float w = __ldg(kf + dy * N);
+        kt[dy] = make_float2(w, w);
+    }
     const size_t zstride = (size_t)a.g.nseg * N;
     const float2 *zp = a.Z + ((size_t)src_plane * a.g.zrows * a.g.nseg + seg) * N + k;
     float2 acc[FT];
@@ -163,11 +198,7 @@ __global__ void __launch_bounds__(FIR_THREADS) lenia_fft_fir_kernel(const FftFir
 #pragma unroll
         for (int y = 0; y < FT; ++y) {
             const int dy = rr - R - y;
-            if (dy >= -R && dy <= R) {
-                const float w = kt[dy < 0 ? -dy : dy];
-                acc[y].x = fmaf(w, z.x, acc[y].x);
-                acc[y].y = fmaf(w, z.y, acc[y].y);
-            }
+            if (dy >= -R && dy <= R) acc[y] = __ffma2_rn(kt[dy < 0 ? -dy : dy], z, acc[y]);
         }
     }
     float2 *op = a.O + ((size_t)pair * a.g.D * a.g.nseg + seg) * N + k;
@@ -181,7 +212,7 @@ struct FftInvArgs {
     const float *state_in;
     float *out;
     const float2 *O;
-    const float2 *twg;
+    const float2 *tws;
     const float *mu, *sigma, *weights;
     FftGeom g;
     int B, C, NS, H, W, pitch;
@@ -189,7 +220,8 @@ struct FftInvArgs {
     int mode, row_wrap;
 };
 
-__device__ __forceinline__ void fft_store_mirrors(float *__restrict__ plane, int H, int W, int pitch, int y, int x, float v, bool row_wrap) {
+// writes the periodic images (not the cell itself) of interior cell (y, x) into the frame; rare, kept out of line
+__device__ __noinline__ void fft_store_mirrors(float *__restrict__ plane, int H, int W, int pitch, int y, int x, float v, bool row_wrap) {
     const int fy = y + F, fx = x + F;
     int ys[3], xs[3], ny = 0, nx = 0;
     ys[ny++] = fy;
@@ -201,101 +233,137 @@ __device__ __forceinline__ void fft_store_mirrors(float *__restrict__ plane, int
     if (x < F) xs[nx++] = fx + W;
     if (x >= W - F) xs[nx++] = fx - W;
     for (int a = 0; a < ny; ++a)
-        for (int b = 0; b < nx; ++b) plane[(size_t)ys[a] * pitch + xs[b]] = v;
+        for (int b = 0; b < nx; ++b)
+            if (a | b) plane[(size_t)ys[a] * pitch + xs[b]] = v;
 }
 
-// grid (D, nseg, B*C), block N/4 threads
-__global__ void __launch_bounds__(1024) lenia_fft_inv_kernel(const FftInvArgs a) {
+// grid (ceil(D / FFT_RPC), nseg, B*C), block N/4 threads, smem FFT_RPC * N float2
+template <int FFT_RPC>
+__global__ void __launch_bounds__(256) lenia_fft_inv_kernel(const FftInvArgs a) {
     extern __shared__ __align__(16) float2 ism[];
     const int N = a.g.N, T = N >> 2, tid = threadIdx.x;
-    float2 *buf = ism;
-    float2 *tw = ism + N;
-    const int yy = blockIdx.x, seg = blockIdx.y;
+    const int seg = blockIdx.y;
     const int b = blockIdx.z / a.C, j = blockIdx.z % a.C;
-    for (int t = tid; t < N; t += T) tw[t] = __ldg(a.twg + t);
-    float2 dx[4];
+    int yy[FFT_RPC];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) dx[r] = make_float2(0.f, 0.f);
+    for (int q = 0; q < FFT_RPC; ++q) yy[q] = min((int)blockIdx.x * FFT_RPC + q, a.g.D - 1);
+    float2 dx[FFT_RPC][4], sv[FFT_RPC][4];
+#pragma unroll
+    for (int q = 0; q < FFT_RPC; ++q)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) dx[q][r] = sv[q][r] = make_float2(0.f, 0.f);
+    const size_t plane_off = (size_t)(b * a.C + j) * (a.H + 2 * F) * a.pitch;
     for (int i = 0; i < a.NS; ++i) {
         const int pidx = (b * a.NS + i) * a.C + j;
-        const float2 *op = a.O + (((size_t)pidx * a.g.D + yy) * a.g.nseg + seg) * N;
+        if (i > 0) __syncthreads();  // previous source done with the buffers
         // first DIT stage (span = 1, no twiddles) straight from global memory: 4 consecutive inputs per thread
-        {
+#pragma unroll
+        for (int q = 0; q < FFT_RPC; ++q) {
+            const float2 *op = a.O + (((size_t)pidx * a.g.D + yy[q]) * a.g.nseg + seg) * N;
             const float4 *in4 = reinterpret_cast<const float4 *>(op + (tid << 2));
             const float4 lo = __ldg(in4), hi = __ldg(in4 + 1);
-            float2 p = make_float2(lo.x, lo.y), q = make_float2(lo.z, lo.w), r = make_float2(hi.x, hi.y), s = make_float2(hi.z, hi.w);
+            float2 p = make_float2(lo.x, lo.y), qq = make_float2(lo.z, lo.w), r = make_float2(hi.x, hi.y), s = make_float2(hi.z, hi.w);
             const float2 one = make_float2(1.f, 0.f);
-            dit4_inv(p, q, r, s, one, one, one);
-            __syncthreads();  // twiddles visible (i == 0); previous source done with buf
+            dit4_inv(p, qq, r, s, one, one, one);
+            float2 *buf = ism + q * N;
             const int i0 = tid << 2;
-            buf[swz(i0)] = p; buf[swz(i0 + 1)] = q; buf[swz(i0 + 2)] = r; buf[swz(i0 + 3)] = s;
+            buf[swz(i0)] = p; buf[swz(i0 + 1)] = qq; buf[swz(i0 + 2)] = r; buf[swz(i0 + 3)] = s;
         }
         for (int span = 4; span < T; span <<= 2) {
             __syncthreads();
             const int k = tid & (span - 1);
             const int i0 = ((tid - k) << 2) + k;
-            const int m = k * (T / span);
-            const int p0 = swz(i0), p1 = swz(i0 + span), p2 = swz(i0 + 2 * span), p3 = swz(i0 + 3 * span);
-            float2 p = buf[p0], q = buf[p1], r = buf[p2], s = buf[p3];
-            dit4_inv(p, q, r, s, tw[m], tw[2 * m], tw[3 * m]);
-            buf[p0] = p; buf[p1] = q; buf[p2] = r; buf[p3] = s;
+            float2 w1, w2, w3;
+            load_tw(a.tws, span, k, w1, w2, w3);
+            const int p0 = swz(i0);
+            const int p1 = span >= 64 ? p0 + span : swz(i0 + span);
+            const int p2 = span >= 64 ? p0 + 2 * span : swz(i0 + 2 * span);
+            const int p3 = span >= 64 ? p0 + 3 * span : swz(i0 + 3 * span);
+#pragma unroll
+            for (int q = 0; q < FFT_RPC; ++q) {
+                float2 *buf = ism + q * N;
+                float2 p = buf[p0], qq = buf[p1], r = buf[p2], s = buf[p3];
+                dit4_inv(p, qq, r, s, w1, w2, w3);
+                buf[p0] = p; buf[p1] = qq; buf[p2] = r; buf[p3] = s;
+            }
         }
         __syncthreads();
-        // last stage (span = N/4): results stay in registers: sample n = tid + r*T of rows yy (real) and yy+D (imag)
-        float2 v[4];
-        {
-            v[0] = buf[swz(tid)]; v[1] = buf[swz(tid + T)]; v[2] = buf[swz(tid + 2 * T)]; v[3] = buf[swz(tid + 3 * T)];
-            const int m = tid;
-            dit4_inv(v[0], v[1], v[2], v[3], tw[m], tw[2 * m], tw[3 * m]);
+        if (i == a.NS - 1 && a.mode == B200CA_MODE_LENIA) {
+            // prefetch the state values of the Euler step; their latency hides behind the last stage + growth
+#pragma unroll
+            for (int q = 0; q < FFT_RPC; ++q)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int n = tid + r * T;
+                    const int x = a.g.periodic ? n : min(max(seg * a.g.V + n - R, 0), a.W - 1);
+                    const float *sp = a.state_in + plane_off + (size_t)(yy[q] + F) * a.pitch + x + F;
+                    sv[q][r] = make_float2(__ldg(sp), __ldg(sp + (size_t)a.g.D * a.pitch));
+                }
         }
-        // growth + weighted source sum (lenia.py:423-426, :444-446): 2*exp(-(u-mu)^2/(2 sigma^2)) - 1
+        // last stage (span = N/4): results stay in registers: sample n = tid + r*T of rows yy (real) and yy+D (imag)
         const float mu = __ldg(a.mu + pidx), sg = __ldg(a.sigma + pidx), wt = __ldg(a.weights + pidx);
         const float c2 = 1.4426950408889634f / (2.f * sg * sg);
+        float2 w1, w2, w3;
+        load_tw(a.tws, T, tid, w1, w2, w3);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const float d0 = v[r].x - mu, d1 = v[r].y - mu;
-            dx[r].x = fmaf(2.f * exp2f(-d0 * d0 * c2) - 1.f, wt, dx[r].x);
-            dx[r].y = fmaf(2.f * exp2f(-d1 * d1 * c2) - 1.f, wt, dx[r].y);
+        for (int q = 0; q < FFT_RPC; ++q) {
+            const float2 *buf = ism + q * N;
+            float2 v[4];
+            v[0] = buf[swz(tid)]; v[1] = buf[swz(tid + T)]; v[2] = buf[swz(tid + 2 * T)]; v[3] = buf[swz(tid + 3 * T)];
+            dit4_inv(v[0], v[1], v[2], v[3], w1, w2, w3);
+            // growth + weighted source sum (lenia.py:423-426, :444-446): 2*exp(-(u-mu)^2/(2 sigma^2)) - 1
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float d0 = v[r].x - mu, d1 = v[r].y - mu;
+                dx[q][r].x = fmaf(2.f * exp2f(-d0 * d0 * c2) - 1.f, wt, dx[q][r].x);
+                dx[q][r].y = fmaf(2.f * exp2f(-d1 * d1 * c2) - 1.f, wt, dx[q][r].y);
+            }
         }
     }
-    const size_t plane_off = (size_t)(b * a.C + j) * (a.H + 2 * F) * a.pitch;
     float *oplane = a.out + plane_off;
+    const bool lenia = a.mode == B200CA_MODE_LENIA;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int n = tid + r * T;
-        int x;
-        if (a.g.periodic) {
-            x = n;
-        } else {
-            if (n < R || n >= N - R) continue;
-            x = seg * a.g.V + n - R;
-            if (x >= a.W) continue;
-        }
+    for (int q = 0; q < FFT_RPC; ++q) {
+        if ((int)blockIdx.x * FFT_RPC + q >= a.g.D) break;
+        const int row0 = yy[q], row1 = yy[q] + a.g.D;
+        float *rp0 = oplane + (size_t)(row0 + F) * a.pitch + F;
+        float *rp1 = rp0 + (size_t)a.g.D * a.pitch;
+        const bool re0 = a.row_wrap && (row0 < F || row0 >= a.H - F);
+        const bool re1 = a.row_wrap && (row1 < F || row1 >= a.H - F);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int row = yy + h * a.g.D;
-            const float dv = h ? dx[r].y : dx[r].x;
-            float res = dv;
-            if (a.mode == B200CA_MODE_LENIA) {
-                const float sv = __ldg(a.state_in + plane_off + (size_t)(row + F) * a.pitch + x + F);
-                res = fminf(fmaxf(sv + a.dt * dv, 0.f), 1.f);
+        for (int r = 0; r < 4; ++r) {
+            const int n = tid + r * T;
+            int x = n;
+            if (!a.g.periodic) {
+                x = seg * a.g.V + n - R;
+                if (n < R || n >= N - R || x >= a.W) continue;
             }
-            const bool edge = (x < F) || (x >= a.W - F) || (a.row_wrap && (row < F || row >= a.H - F));
-            if (edge)
-                fft_store_mirrors(oplane, a.H, a.W, a.pitch, row, x, res, a.row_wrap != 0);
-            else
-                oplane[(size_t)(row + F) * a.pitch + x + F] = res;
+            float v0 = dx[q][r].x, v1 = dx[q][r].y;
+            if (lenia) {
+                v0 = fminf(fmaxf(sv[q][r].x + a.dt * v0, 0.f), 1.f);
+                v1 = fminf(fmaxf(sv[q][r].y + a.dt * v1, 0.f), 1.f);
+            }
+            rp0[x] = v0;
+            rp1[x] = v1;
+            const bool xe = (x < F) || (x >= a.W - F);
+            if (xe || re0) fft_store_mirrors(oplane, a.H, a.W, a.pitch, row0, x, v0, a.row_wrap != 0);
+            if (xe || re1) fft_store_mirrors(oplane, a.H, a.W, a.pitch, row1, x, v1, a.row_wrap != 0);
         }
     }
 }
 
 // ---- plan helpers ---------------------------------------------------------------------------------
-__global__ void lenia_fft_twiddle_kernel(float2 *tw, int N) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= N) return;
-    double s, c;
-    sincospi(-2.0 * (double)m / (double)N, &s, &c);
-    tw[m] = make_float2((float)c, (float)s);
+__global__ void lenia_fft_twiddle_kernel(float2 *tws, int N) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N - 1) return;
+    // entry e lies in the stage with span s where (s-1) <= e < (4s-1)
+    int span = 1;
+    while (e >= 4 * span - 1) span <<= 2;
+    const int off = e - (span - 1);
+    const int r = off / span, k = off % span;
+    double sn, cs;
+    sincospi(-2.0 * (double)((r + 1) * k) / (double)(4 * span), &sn, &cs);
+    tws[e] = make_float2((float)cs, (float)sn);
 }
 
 __device__ __forceinline__ int digit_reverse4(int p, int logN4) {
@@ -336,7 +404,7 @@ static int fft_geom(FftGeom &g, int H, int W) {
     if (H % 2 != 0 || H < 2 * F) return B200CA_E_UNSUPPORTED;
     g.D = H / 2;
     g.zrows = g.D + 2 * R;
-    if (W == 256 || W == 1024 || W == 4096) {
+    if (W == 256 || W == 1024) {
         g.N = W;
         g.periodic = 1;
         g.nseg = 1;
@@ -440,18 +508,20 @@ extern "C" int b200ca_lenia_step_fft(const float *state_in, float *state_out, co
     const int NS = C * k_mult;
     float2 *Z = reinterpret_cast<float2 *>(workspace);
     float2 *O = Z + (size_t)B * C * g.zrows * g.nseg * g.N;
-    const size_t smem = (size_t)2 * g.N * sizeof(float2);
-    static bool attr_done[64] = {false};
-    int dev = 0;
-    B200CA_CUDA(cudaGetDevice(&dev));
-    if (!attr_done[dev & 63]) {
-        B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr_done[dev & 63] = true;
+    static int rpc_rows = 0, rpc_inv = 0;
+    if (!rpc_rows) {
+        const char *e1 = getenv("B200CA_FFT_RPC_ROWS"), *e2 = getenv("B200CA_FFT_RPC_INV");
+        rpc_rows = e1 ? atoi(e1) : 2;
+        rpc_inv = e2 ? atoi(e2) : 1;
+        if (rpc_rows != 1 && rpc_rows != 4) rpc_rows = 2;
+        if (rpc_inv != 2 && rpc_inv != 4) rpc_inv = 1;
     }
     {
-        dim3 grid(g.zrows, g.nseg, B * C);
-        lenia_fft_rows_kernel<<<grid, g.N / 4, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
+        const size_t smem = (size_t)rpc_rows * g.N * sizeof(float2);
+        dim3 grid(ceil_div(g.zrows, rpc_rows), g.nseg, B * C);
+        if (rpc_rows == 1) lenia_fft_rows_kernel<1><<<grid, g.N / 4, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
+        else if (rpc_rows == 2) lenia_fft_rows_kernel<2><<<grid, g.N / 4, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
+        else lenia_fft_rows_kernel<4><<<grid, g.N / 4, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
         B200CA_LAUNCH_CHECK("lenia_fft_rows_kernel");
     }
     {
@@ -474,7 +544,7 @@ extern "C" int b200ca_lenia_step_fft(const float *state_in, float *state_out, co
         a.state_in = state_in;
         a.out = state_out;
         a.O = O;
-        a.twg = tw;
+        a.tws = tw;
         a.mu = mu;
         a.sigma = sigma;
         a.weights = weights;
@@ -488,8 +558,11 @@ extern "C" int b200ca_lenia_step_fft(const float *state_in, float *state_out, co
         a.dt = dt;
         a.mode = mode;
         a.row_wrap = row_wrap;
-        dim3 grid(g.D, g.nseg, B * C);
-        lenia_fft_inv_kernel<<<grid, g.N / 4, smem, st>>>(a);
+        const size_t smem = (size_t)rpc_inv * g.N * sizeof(float2);
+        dim3 grid(ceil_div(g.D, rpc_inv), g.nseg, B * C);
+        if (rpc_inv == 1) lenia_fft_inv_kernel<1><<<grid, g.N / 4, smem, st>>>(a);
+        else if (rpc_inv == 2) lenia_fft_inv_kernel<2><<<grid, g.N / 4, smem, st>>>(a);
+        else lenia_fft_inv_kernel<4><<<grid, g.N / 4, smem, st>>>(a);
         B200CA_LAUNCH_CHECK("lenia_fft_inv_kernel");
     }
     return 0;
