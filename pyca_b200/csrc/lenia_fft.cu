@@ -534,9 +534,15 @@ extern "C" int b200ca_lenia_step_fft(const float *state_in, float *state_out, co
         a.C = C;
         a.NS = NS;
         a.k_mult = k_mult;
-        constexpr int FT = 32;
-        dim3 grid((g.N / FIR_THREADS) * g.nseg, ceil_div(g.D, FT), B * NS * C);
-        lenia_fft_fir_kernel<FT><<<grid, FIR_THREADS, 0, st>>>(a);
+        // 32 output rows per thread (1.9x read amplification) when that still fills the machine, else 8 (4.75x, from L2)
+        const long long ctas32 = (long long)(g.N / FIR_THREADS) * g.nseg * ceil_div(g.D, 32) * B * NS * C;
+        if (ctas32 >= (long long)num_sms() * 16) {
+            dim3 grid((g.N / FIR_THREADS) * g.nseg, ceil_div(g.D, 32), B * NS * C);
+            lenia_fft_fir_kernel<32><<<grid, FIR_THREADS, 0, st>>>(a);
+        } else {
+            dim3 grid((g.N / FIR_THREADS) * g.nseg, ceil_div(g.D, 8), B * NS * C);
+            lenia_fft_fir_kernel<8><<<grid, FIR_THREADS, 0, st>>>(a);
+        }
         B200CA_LAUNCH_CHECK("lenia_fft_fir_kernel");
     }
     {

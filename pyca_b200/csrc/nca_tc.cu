@@ -1,13 +1,337 @@
-// tcgen05 / TMEM implementation of the NCA update pass (placeholder until the kernel lands).
+// Neural-CA update pass on the 5th-generation tensor cores (tcgen05 + TMEM) for sm_100a.
+//
+// Same arithmetic as nca_update_simt_kernel (nca.cu) -- perception (nca.py:328-344), Linear-ReLU-Linear
+// (nca.py:205-208), sigmoid * update mask, pre-update life mask (nca.py:226-237, :256-263) -- but the per-cell MLP,
+// a real dense contraction, runs as two tcgen05.mma GEMMs per 128-cell tile:
+//     D1[128 x 128] = P[128 x 32] * W1f^T          (folded first layer, K = 32)
+//     D2[128 x 16]  = relu(D1 + b1)[128 x 128] * W2^T   (K = 128)
+// with fp32 accumulators in tensor memory.  fp32-grade accuracy (the 1e-5 single-step parity bound rules out
+// plain tf32/bf16 operands) comes from a 2-way tf32 split of BOTH operands and three MMAs per
+// product, hi*hi + hi*lo + lo*hi (the dropped lo*lo term is 2^-22 relative).
+//
+// One CTA = 128 threads = 128 tile rows: thread t owns cell (warp row, lane column) of a 32x4 cell block, which is
+// also TMEM lane t of both accumulators, so every stage is "one thread, one cell":
+//   perception in registers -> hi/lo split -> A operand in shared memory (no-swizzle K-major core matrices:
+//   [k-chunk of 4][row][4 floats], conflict-free 16-byte stores) -> thread 0 issues the MMAs, tcgen05.commit ->
+//   mbarrier -> tcgen05.ld of the thread's own accumulator row -> bias/ReLU/split -> A operand of GEMM 2, fed in
+//   16-column chunks so the second GEMM's MMAs trail the epilogue of the first -> sigmoid, masks, coalesced NCHW
+//   stores + the two bit planes for the life-mask pass.
+// CTAs are persistent (grid = 2 x SMs, weights staged in shared memory once) and two CTAs share an SM so one
+// tile's CUDA-core phases overlap the other's tensor phases.  256 TMEM columns per CTA.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "nca.cuh"
+#include "tma.cuh"
 
 namespace b200ca {
 
-int nca_prepare_tc(const float *, const float *, const float *, const float *, void *, cudaStream_t) { return 0; }
+// ---- Wprep tensor-core section (byte offsets from WP_TC_OFF) -------------------------------------------------
+// B1hi/B1lo: W1f as [8 k-chunks][128 n][4 floats];  B2hi/B2lo: W2 as [32 k-chunks][16 n][4 floats]
+constexpr int TC_B1HI = 0;
+constexpr int TC_B1LO = TC_B1HI + NCA_HID * NCA_K1 * 4;   // 16 KB each
+constexpr int TC_B2HI = TC_B1LO + NCA_HID * NCA_K1 * 4;
+constexpr int TC_B2LO = TC_B2HI + NCA_N * NCA_HID * 4;    // 8 KB each
+constexpr int TC_BIAS1 = TC_B2LO + NCA_N * NCA_HID * 4;   // 128 floats
+constexpr int TC_BIAS2 = TC_BIAS1 + NCA_HID * 4;          // 16 floats
+constexpr int TC_WBYTES = TC_BIAS2 + NCA_N * 4;           // 49728
+static_assert(TC_WBYTES <= WP_TC_BYTES, "Wprep tensor-core section overflows");
 
-int nca_step_tc(const NcaArgs &, cudaStream_t) {
-    set_error("nca_step: tensor-core implementation not built yet");
-    return B200CA_E_UNSUPPORTED;
+// ---- shared memory plan ----------------------------------------------------------------------------------------
+constexpr int SM_W = 0;                                   // weight images + biases (TC_WBYTES, padded)
+constexpr int SM_A1HI = 50 * 1024;                        // [8][128][4] floats = 16 KB
+constexpr int SM_A1LO = SM_A1HI + 16 * 1024;
+constexpr int SM_A2HI = SM_A1LO + 16 * 1024;              // [4][128][4] floats = 8 KB (16 hidden columns)
+constexpr int SM_A2LO = SM_A2HI + 8 * 1024;
+constexpr int SM_BAR = SM_A2LO + 8 * 1024;                // mbarriers + tmem address
+constexpr int SM_TOTAL = SM_BAR + 64;                     // 98 KB + 64 -> two CTAs per SM
+
+constexpr int TMEM_COLS = 256;  // D1: columns [0,128), D2: [128,144)
+constexpr int D2_COL = 128;
+constexpr int H2CHUNK = 16;     // hidden columns per GEMM-2 chunk (two K=8 steps)
+
+// tf32 split: hi = x rounded to 10 explicit mantissa bits (low 13 bits zero, so the tensor core's truncation is exact);
+// lo = x - hi (exact in fp32; the tensor core keeps its top 11 bits: error <= 2^-22 |x|)
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    lo = x - hi;
+}
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE: 8x(16 B) core matrices; LBO = byte stride between the two
+// 16-byte K chunks of one MMA, SBO = byte stride between 8-row groups (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) | ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) |
+           (1ull << 46);
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32 K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float sigmoid_rn(float x) { return __fdiv_rn(1.f, 1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(128, 2) nca_update_tc_kernel(const NcaArgs a, int tiles_x, int tiles_y) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *sw = reinterpret_cast<float *>(smem + SM_W);
+    uint64_t *bar1 = reinterpret_cast<uint64_t *>(smem + SM_BAR);      // GEMM 1 done
+    uint64_t *bar2 = bar1 + 1;                                         // GEMM 2 chunk done
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar1 + 2);
+
+    // ---- one-time setup: weights -> smem, barriers, TMEM
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(a.wp) + WP_TC_OFF);
+        float4 *dst = reinterpret_cast<float4 *>(sw);
+        for (int t = tid; t < TC_WBYTES / 16; t += 128) dst[t] = __ldg(src + t);
+    }
+    if (tid == 0) {
+        mbar_init(bar1, 1);
+        mbar_init(bar2, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();  // weight images are read by the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
+
+    const uint32_t sA1hi = smem_u32(smem + SM_A1HI), sA1lo = smem_u32(smem + SM_A1LO);
+    const uint32_t sA2hi = smem_u32(smem + SM_A2HI), sA2lo = smem_u32(smem + SM_A2LO);
+    const uint32_t sB1hi = smem_u32(smem + SM_W + TC_B1HI), sB1lo = smem_u32(smem + SM_W + TC_B1LO);
+    const uint32_t sB2hi = smem_u32(smem + SM_W + TC_B2HI), sB2lo = smem_u32(smem + SM_W + TC_B2LO);
+    const float *bias1 = sw + TC_BIAS1 / 4, *bias2 = sw + TC_BIAS2 / 4;
+    // descriptor strides: A operands [chunk][128 rows][16 B], B1 [chunk][128 n][16 B], B2 [chunk][16 n][16 B]
+    constexpr uint32_t lboA = 128 * 16, lboB1 = 128 * 16, lboB2 = 16 * 16, sboA = 128, sboB1 = 128, sboB2 = 128;
+    constexpr uint32_t IDESC1 = make_idesc(128), IDESC2 = make_idesc(16);
+
+    const size_t plane = (size_t)a.H * a.W;
+    const int ntiles = tiles_x * tiles_y * a.B;
+    uint32_t ph1 = 0, ph2 = 0;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+        const int x = tx * 32 + lane, y = ty * 4 + warp;
+        const bool valid = x < a.W && y < a.H;
+        const int xc = min(x, a.W - 1), yc = min(y, a.H - 1);
+        const int xm = xc == 0 ? a.W - 1 : xc - 1, xp = xc == a.W - 1 ? 0 : xc + 1;
+        const int ym = yc == 0 ? a.H - 1 : yc - 1, yp = yc == a.H - 1 ? 0 : yc + 1;
+        const float *sb = a.in + (size_t)b * NCA_N * plane;
+
+        // ---- perception -> split -> A1 (hi, lo) in smem: chunk kc holds features 4kc..4kc+3
+        bool alive0 = false;
+        {
+            float p[NCA_K1];
+#pragma unroll
+            for (int c = 0; c < NCA_N; ++c) {
+                const float *pl = sb + (size_t)c * plane;
+                const float ctr = __ldg(pl + (size_t)yc * a.W + xc);
+                p[16 + c] = ctr;
+                if (c < 8) {
+                    const float l0 = __ldg(pl + (size_t)ym * a.W + xm), r0 = __ldg(pl + (size_t)ym * a.W + xp);
+                    const float l1 = __ldg(pl + (size_t)yc * a.W + xm), r1 = __ldg(pl + (size_t)yc * a.W + xp);
+                    const float l2 = __ldg(pl + (size_t)yp * a.W + xm), r2 = __ldg(pl + (size_t)yp * a.W + xp);
+                    p[c] = ((r0 - l0) + 2.f * (r1 - l1) + (r2 - l2)) * 0.125f;
+                    if (c == 3) {
+                        const float t1 = __ldg(pl + (size_t)ym * a.W + xc), b1 = __ldg(pl + (size_t)yp * a.W + xc);
+                        const float m = fmaxf(fmaxf(fmaxf(l0, r0), fmaxf(l1, r1)), fmaxf(fmaxf(l2, r2), fmaxf(t1, b1)));
+                        alive0 = fmaxf(m, ctr) > 0.1f;
+                    }
+                } else {
+                    const float t0 = __ldg(pl + (size_t)ym * a.W + xm), t1 = __ldg(pl + (size_t)ym * a.W + xc),
+                                t2 = __ldg(pl + (size_t)ym * a.W + xp);
+                    const float b0 = __ldg(pl + (size_t)yp * a.W + xm), b1 = __ldg(pl + (size_t)yp * a.W + xc),
+                                b2 = __ldg(pl + (size_t)yp * a.W + xp);
+                    p[c] = ((b0 - t0) + 2.f * (b1 - t1) + (b2 - t2)) * 0.125f;
+                }
+            }
+            float4 *ahi = reinterpret_cast<float4 *>(smem + SM_A1HI), *alo = reinterpret_cast<float4 *>(smem + SM_A1LO);
+#pragma unroll
+            for (int kc = 0; kc < NCA_K1 / 4; ++kc) {
+                float h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_tf32(p[4 * kc + e], h[e], l[e]);
+                ahi[kc * 128 + tid] = make_float4(h[0], h[1], h[2], h[3]);
+                alo[kc * 128 + tid] = make_float4(l[0], l[1], l[2], l[3]);
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+
+        // ---- GEMM 1: D1 = A1 * B1^T, K = 32 = 4 k-steps x (hi*hi + hi*lo + lo*hi)
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < NCA_K1 / 8; ++ks) {
+                const uint32_t offA = ks * 2 * 128 * 16, offB = ks * 2 * 128 * 16;
+                const uint64_t ah = make_desc(sA1hi + offA, lboA, sboA), al = make_desc(sA1lo + offA, lboA, sboA);
+                const uint64_t bh = make_desc(sB1hi + offB, lboB1, sboB1), bl = make_desc(sB1lo + offB, lboB1, sboB1);
+                mma_tf32(tmem, ah, bh, IDESC1, ks > 0);
+                mma_tf32(tmem, ah, bl, IDESC1, 1);
+                mma_tf32(tmem, al, bh, IDESC1, 1);
+            }
+            mma_commit(bar1);
+        }
+        mbar_wait(bar1, ph1);
+        ph1 ^= 1;
+        tc_fence_after();
+
+        // ---- epilogue 1 + GEMM 2 in chunks of 16 hidden units
+#pragma unroll 1
+        for (int c = 0; c < NCA_HID / H2CHUNK; ++c) {
+            float v[16];
+            tmem_ld16(my_tmem + c * H2CHUNK, v);
+            float hh[16], hl[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) split_tf32(fmaxf(v[e] + bias1[c * H2CHUNK + e], 0.f), hh[e], hl[e]);
+            if (c > 0) {  // the previous chunk's MMAs must have consumed the A2 buffer
+                mbar_wait(bar2, ph2);
+                ph2 ^= 1;
+            }
+            float4 *ahi = reinterpret_cast<float4 *>(smem + SM_A2HI), *alo = reinterpret_cast<float4 *>(smem + SM_A2LO);
+#pragma unroll
+            for (int kc = 0; kc < H2CHUNK / 4; ++kc) {
+                ahi[kc * 128 + tid] = make_float4(hh[4 * kc], hh[4 * kc + 1], hh[4 * kc + 2], hh[4 * kc + 3]);
+                alo[kc * 128 + tid] = make_float4(hl[4 * kc], hl[4 * kc + 1], hl[4 * kc + 2], hl[4 * kc + 3]);
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+#pragma unroll
+                for (int s = 0; s < H2CHUNK / 8; ++s) {
+                    const uint32_t offA = s * 2 * 128 * 16;
+                    const uint32_t offB = (c * (H2CHUNK / 4) + s * 2) * 16 * 16;
+                    const uint64_t ah = make_desc(sA2hi + offA, lboA, sboA), al = make_desc(sA2lo + offA, lboA, sboA);
+                    const uint64_t bh = make_desc(sB2hi + offB, lboB2, sboB2), bl = make_desc(sB2lo + offB, lboB2, sboB2);
+                    mma_tf32(tmem + D2_COL, ah, bh, IDESC2, (c | s) != 0);
+                    mma_tf32(tmem + D2_COL, ah, bl, IDESC2, 1);
+                    mma_tf32(tmem + D2_COL, al, bh, IDESC2, 1);
+                }
+                mma_commit(bar2);
+            }
+        }
+        mbar_wait(bar2, ph2);
+        ph2 ^= 1;
+        tc_fence_after();
+
+        // ---- epilogue 2: bias, sigmoid, update mask, pre-update life mask, stores
+        {
+            float o[16];
+            tmem_ld16(my_tmem + D2_COL, o);
+            const size_t cell = ((size_t)b * a.H + yc) * a.W + xc;
+            const bool upd = valid && nca_update_bit(a, cell);
+            const float alpha_new = upd ? sigmoid_rn(o[3] + bias2[3]) : 0.f;
+            const bool keep = upd && alive0;
+            const uint32_t abits = __ballot_sync(0xffffffffu, valid && alpha_new > 0.1f);
+            const uint32_t nbits = __ballot_sync(0xffffffffu, keep);
+            if (y < a.H && lane == 0) {
+                const size_t wi = ((size_t)b * a.H + y) * a.wpr + tx;
+                a.alive_bits[wi] = abits;
+                a.nz_bits[wi] = nbits;
+            }
+            if (valid) {
+                float *ob = a.out + (size_t)b * NCA_N * plane + (size_t)y * a.W + x;
+#pragma unroll
+                for (int ch = 0; ch < NCA_N; ++ch) ob[(size_t)ch * plane] = keep ? sigmoid_rn(o[ch] + bias2[ch]) : 0.f;
+            }
+        }
+        // all TMEM reads of this tile are done before the next tile's MMAs overwrite D1/D2
+        tc_fence_before();
+        __syncthreads();
+    }
+
+    if (warp == 0) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- weight preparation: split hi/lo images in the operand layouts ----------------------------------------------
+__global__ void nca_prepare_tc_kernel(const float *__restrict__ wp_simt, unsigned char *__restrict__ tc) {
+    // wp_simt holds W1f[128][32], b1, W2t[128][16], b2 (see nca.cuh)
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    float *b1hi = reinterpret_cast<float *>(tc + TC_B1HI), *b1lo = reinterpret_cast<float *>(tc + TC_B1LO);
+    float *b2hi = reinterpret_cast<float *>(tc + TC_B2HI), *b2lo = reinterpret_cast<float *>(tc + TC_B2LO);
+    if (t < NCA_HID * NCA_K1) {  // B1[n][k] = W1f[n][k] -> [k/4][n][k%4]
+        const int n = t / NCA_K1, k = t % NCA_K1;
+        const float w = wp_simt[WP_W1F + t];
+        const float hi = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xffffe000u);
+        const int idx = ((k >> 2) * NCA_HID + n) * 4 + (k & 3);
+        b1hi[idx] = hi;
+        b1lo[idx] = w - hi;
+    }
+    if (t < NCA_HID * NCA_N) {  // B2[n][k] = W2[n][k] = W2t[k][n] -> [k/4][n][k%4]
+        const int k = t / NCA_N, n = t % NCA_N;
+        const float w = wp_simt[WP_W2T + t];
+        const float hi = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xffffe000u);
+        const int idx = ((k >> 2) * NCA_N + n) * 4 + (k & 3);
+        b2hi[idx] = hi;
+        b2lo[idx] = w - hi;
+    }
+    if (t < NCA_HID) reinterpret_cast<float *>(tc + TC_BIAS1)[t] = wp_simt[WP_B1 + t];
+    if (t < NCA_N) reinterpret_cast<float *>(tc + TC_BIAS2)[t] = wp_simt[WP_B2 + t];
+}
+
+int nca_prepare_tc(const float *, const float *, const float *, const float *, void *Wprep, cudaStream_t st) {
+    // runs after nca_prepare_simt_kernel on the same stream: reads the folded/transposed fp32 copies it produced
+    unsigned char *base = reinterpret_cast<unsigned char *>(Wprep);
+    nca_prepare_tc_kernel<<<ceil_div(NCA_HID * NCA_K1, 256), 256, 0, st>>>(reinterpret_cast<const float *>(base), base + WP_TC_OFF);
+    B200CA_LAUNCH_CHECK("nca_prepare_tc_kernel");
+    return 0;
+}
+
+int nca_step_tc(const NcaArgs &a, cudaStream_t st) {
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    B200CA_CUDA(cudaGetDevice(&dev));
+    if (!attr_done[dev & 63]) {
+        B200CA_CUDA(cudaFuncSetAttribute(nca_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        attr_done[dev & 63] = true;
+    }
+    const int tiles_x = ceil_div(a.W, 32), tiles_y = ceil_div(a.H, 4);
+    const long long ntiles = (long long)tiles_x * tiles_y * a.B;
+    const int grid = (int)std::min<long long>(ntiles, 2LL * num_sms());
+    nca_update_tc_kernel<<<grid, 128, SM_TOTAL, st>>>(a, tiles_x, tiles_y);
+    B200CA_LAUNCH_CHECK("nca_update_tc_kernel");
+    return 0;
 }
 
 }  // namespace b200ca
