@@ -28,24 +28,31 @@
 namespace b200ca {
 
 // ---- Wprep tensor-core section (byte offsets from WP_TC_OFF) -------------------------------------------------
-// B1hi/B1lo: W1f as [8 k-chunks][128 n][4 floats];  B2hi/B2lo: W2 as [32 k-chunks][16 n][4 floats]
+// B1hi/B1lo: [W1f | b1 | 0] as [10 k-chunks][128 n][4 floats] (K = 40: column 32 is the bias, fed by a constant-1
+// feature, columns 33..39 are zero);  B2hi/B2lo: W2 as [32 k-chunks][16 n][4 floats]
+constexpr int K1P = 40;
 constexpr int TC_B1HI = 0;
-constexpr int TC_B1LO = TC_B1HI + NCA_HID * NCA_K1 * 4;   // 16 KB each
-constexpr int TC_B2HI = TC_B1LO + NCA_HID * NCA_K1 * 4;
+constexpr int TC_B1LO = TC_B1HI + NCA_HID * K1P * 4;      // 20 KB each
+constexpr int TC_B2HI = TC_B1LO + NCA_HID * K1P * 4;
 constexpr int TC_B2LO = TC_B2HI + NCA_N * NCA_HID * 4;    // 8 KB each
 constexpr int TC_BIAS1 = TC_B2LO + NCA_N * NCA_HID * 4;   // 128 floats
 constexpr int TC_BIAS2 = TC_BIAS1 + NCA_HID * 4;          // 16 floats
-constexpr int TC_WBYTES = TC_BIAS2 + NCA_N * 4;           // 49728
+constexpr int TC_WBYTES = TC_BIAS2 + NCA_N * 4;           // 57920
 static_assert(TC_WBYTES <= WP_TC_BYTES, "Wprep tensor-core section overflows");
 
 // ---- shared memory plan ----------------------------------------------------------------------------------------
 constexpr int SM_W = 0;                                   // weight images + biases (TC_WBYTES, padded)
-constexpr int SM_A1HI = 50 * 1024;                        // [8][128][4] floats = 16 KB
-constexpr int SM_A1LO = SM_A1HI + 16 * 1024;
-constexpr int SM_A2HI = SM_A1LO + 16 * 1024;              // [4][128][4] floats = 8 KB (16 hidden columns)
-constexpr int SM_A2LO = SM_A2HI + 8 * 1024;
-constexpr int SM_BAR = SM_A2LO + 8 * 1024;                // mbarriers + tmem address
-constexpr int SM_TOTAL = SM_BAR + 64;                     // 98 KB + 64 -> two CTAs per SM
+constexpr int SM_A1HI = 57 * 1024;                        // [10][128][4] floats = 20 KB
+constexpr int SM_A1LO = SM_A1HI + 20 * 1024;
+// A2 chunk buffers ([4][128][4] floats = 8 KB hi + 8 KB lo per 16 hidden columns, double-buffered = 32 KB) alias the
+// start of A1: GEMM 1 has consumed A1 (bar1) before the first chunk is written, and the next tile rewrites A1 only
+// after the last GEMM-2 commits (bar2)
+constexpr int SM_A2 = SM_A1HI;            // buffer b at SM_A2 + b * 16 KB: hi then lo
+constexpr int A2_BUF = 16 * 1024;
+constexpr int SM_BAR = SM_A1LO + 20 * 1024;               // mbarriers + tmem address
+constexpr int SM_TOTAL = SM_BAR + 64;                     // 97 KB + 64 -> two CTAs per SM (<= 113 KB each)
+static_assert(2 * (SM_TOTAL + 1024) <= 227 * 1024, "two CTAs must fit in one SM");
+static_assert(TC_WBYTES <= SM_A1HI, "weights overflow their smem region");
 
 constexpr int TMEM_COLS = 256;  // D1: columns [0,128), D2: [128,144)
 constexpr int D2_COL = 128;
@@ -54,7 +61,9 @@ constexpr int H2CHUNK = 16;     // hidden columns per GEMM-2 chunk (two K=8 step
 // tf32 split: hi = x rounded to 10 explicit mantissa bits (low 13 bits zero, so the tensor core's truncation is exact);
 // lo = x - hi (exact in fp32; the tensor core keeps its top 11 bits: error <= 2^-22 |x|)
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
     lo = x - hi;
 }
 
@@ -97,15 +106,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ float sigmoid_rn(float x) { return __fdiv_rn(1.f, 1.f + expf(-x)); }
+// sigmoid(x) = 1 / (1 + 2^(-x log2 e)) with the SFU ex2/rcp approximations (relative error < 4e-7, far inside the
+// 1e-5 parity bound; the reference's torch.sigmoid is itself only ~1 ulp accurate)
+__device__ __forceinline__ float sigmoid_rn(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return r;
+}
 
 __global__ void __launch_bounds__(128, 2) nca_update_tc_kernel(const NcaArgs a, int tiles_x, int tiles_y) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float *sw = reinterpret_cast<float *>(smem + SM_W);
     uint64_t *bar1 = reinterpret_cast<uint64_t *>(smem + SM_BAR);      // GEMM 1 done
-    uint64_t *bar2 = bar1 + 1;                                         // GEMM 2 chunk done
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar1 + 2);
+    uint64_t *bar2 = bar1 + 1;                                         // bar2[b]: GEMM 2 chunk using A2 buffer b done
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar1 + 3);
 
     // ---- one-time setup: weights -> smem, barriers, TMEM
     {
@@ -116,6 +132,7 @@ __global__ void __launch_bounds__(128, 2) nca_update_tc_kernel(const NcaArgs a, 
     if (tid == 0) {
         mbar_init(bar1, 1);
         mbar_init(bar2, 1);
+        mbar_init(bar2 + 1, 1);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -131,51 +148,53 @@ __global__ void __launch_bounds__(128, 2) nca_update_tc_kernel(const NcaArgs a, 
     const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
 
     const uint32_t sA1hi = smem_u32(smem + SM_A1HI), sA1lo = smem_u32(smem + SM_A1LO);
-    const uint32_t sA2hi = smem_u32(smem + SM_A2HI), sA2lo = smem_u32(smem + SM_A2LO);
+    const uint32_t sA2 = smem_u32(smem + SM_A2);
     const uint32_t sB1hi = smem_u32(smem + SM_W + TC_B1HI), sB1lo = smem_u32(smem + SM_W + TC_B1LO);
     const uint32_t sB2hi = smem_u32(smem + SM_W + TC_B2HI), sB2lo = smem_u32(smem + SM_W + TC_B2LO);
-    const float *bias1 = sw + TC_BIAS1 / 4, *bias2 = sw + TC_BIAS2 / 4;
+    const float *bias2 = sw + TC_BIAS2 / 4;
     // descriptor strides: A operands [chunk][128 rows][16 B], B1 [chunk][128 n][16 B], B2 [chunk][16 n][16 B]
     constexpr uint32_t lboA = 128 * 16, lboB1 = 128 * 16, lboB2 = 16 * 16, sboA = 128, sboB1 = 128, sboB2 = 128;
     constexpr uint32_t IDESC1 = make_idesc(128), IDESC2 = make_idesc(16);
 
     const size_t plane = (size_t)a.H * a.W;
     const int ntiles = tiles_x * tiles_y * a.B;
-    uint32_t ph1 = 0, ph2 = 0;
+    uint32_t ph1 = 0, ph2[2] = {0, 0};
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
         const int x = tx * 32 + lane, y = ty * 4 + warp;
         const bool valid = x < a.W && y < a.H;
         const int xc = min(x, a.W - 1), yc = min(y, a.H - 1);
-        const int xm = xc == 0 ? a.W - 1 : xc - 1, xp = xc == a.W - 1 ? 0 : xc + 1;
-        const int ym = yc == 0 ? a.H - 1 : yc - 1, yp = yc == a.H - 1 ? 0 : yc + 1;
         const float *sb = a.in + (size_t)b * NCA_N * plane;
 
-        // ---- perception -> split -> A1 (hi, lo) in smem: chunk kc holds features 4kc..4kc+3
+        // ---- perception straight from global memory (L1-cached; ~114 independent loads per thread keep the memory
+        //      system busy, which a staged shared-memory tile + barrier did not with only 8 warps per SM)
         bool alive0 = false;
         {
+            const int xm = xc == 0 ? a.W - 1 : xc - 1, xp = xc == a.W - 1 ? 0 : xc + 1;
+            const int ym = yc == 0 ? a.H - 1 : yc - 1, yp = yc == a.H - 1 ? 0 : yc + 1;
+            const int o00 = ym * a.W + xm, o01 = ym * a.W + xc, o02 = ym * a.W + xp;
+            const int o10 = yc * a.W + xm, o11 = yc * a.W + xc, o12 = yc * a.W + xp;
+            const int o20 = yp * a.W + xm, o21 = yp * a.W + xc, o22 = yp * a.W + xp;
             float p[NCA_K1];
 #pragma unroll
             for (int c = 0; c < NCA_N; ++c) {
                 const float *pl = sb + (size_t)c * plane;
-                const float ctr = __ldg(pl + (size_t)yc * a.W + xc);
+                const float ctr = __ldg(pl + o11);
                 p[16 + c] = ctr;
                 if (c < 8) {
-                    const float l0 = __ldg(pl + (size_t)ym * a.W + xm), r0 = __ldg(pl + (size_t)ym * a.W + xp);
-                    const float l1 = __ldg(pl + (size_t)yc * a.W + xm), r1 = __ldg(pl + (size_t)yc * a.W + xp);
-                    const float l2 = __ldg(pl + (size_t)yp * a.W + xm), r2 = __ldg(pl + (size_t)yp * a.W + xp);
+                    const float l0 = __ldg(pl + o00), r0 = __ldg(pl + o02);
+                    const float l1 = __ldg(pl + o10), r1 = __ldg(pl + o12);
+                    const float l2 = __ldg(pl + o20), r2 = __ldg(pl + o22);
                     p[c] = ((r0 - l0) + 2.f * (r1 - l1) + (r2 - l2)) * 0.125f;
                     if (c == 3) {
-                        const float t1 = __ldg(pl + (size_t)ym * a.W + xc), b1 = __ldg(pl + (size_t)yp * a.W + xc);
+                        const float t1 = __ldg(pl + o01), b1 = __ldg(pl + o21);
                         const float m = fmaxf(fmaxf(fmaxf(l0, r0), fmaxf(l1, r1)), fmaxf(fmaxf(l2, r2), fmaxf(t1, b1)));
                         alive0 = fmaxf(m, ctr) > 0.1f;
                     }
                 } else {
-                    const float t0 = __ldg(pl + (size_t)ym * a.W + xm), t1 = __ldg(pl + (size_t)ym * a.W + xc),
-                                t2 = __ldg(pl + (size_t)ym * a.W + xp);
-                    const float b0 = __ldg(pl + (size_t)yp * a.W + xm), b1 = __ldg(pl + (size_t)yp * a.W + xc),
-                                b2 = __ldg(pl + (size_t)yp * a.W + xp);
+                    const float t0 = __ldg(pl + o00), t1 = __ldg(pl + o01), t2 = __ldg(pl + o02);
+                    const float b0 = __ldg(pl + o20), b1 = __ldg(pl + o21), b2 = __ldg(pl + o22);
                     p[c] = ((b0 - t0) + 2.f * (b1 - t1) + (b2 - t2)) * 0.125f;
                 }
             }
@@ -188,16 +207,21 @@ __global__ void __launch_bounds__(128, 2) nca_update_tc_kernel(const NcaArgs a, 
                 ahi[kc * 128 + tid] = make_float4(h[0], h[1], h[2], h[3]);
                 alo[kc * 128 + tid] = make_float4(l[0], l[1], l[2], l[3]);
             }
+            // bias feature: constant 1 in column 32 (chunk 8), zeros up to column 39
+            ahi[8 * 128 + tid] = make_float4(1.f, 0.f, 0.f, 0.f);
+            ahi[9 * 128 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+            alo[8 * 128 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+            alo[9 * 128 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
 
-        // ---- GEMM 1: D1 = A1 * B1^T, K = 32 = 4 k-steps x (hi*hi + hi*lo + lo*hi)
+        // ---- GEMM 1: D1 = [P | 1 | 0] * [W1f | b1 | 0]^T, K = 40 = 5 k-steps x (hi*hi + hi*lo + lo*hi)
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
-            for (int ks = 0; ks < NCA_K1 / 8; ++ks) {
+            for (int ks = 0; ks < K1P / 8; ++ks) {
                 const uint32_t offA = ks * 2 * 128 * 16, offB = ks * 2 * 128 * 16;
                 const uint64_t ah = make_desc(sA1hi + offA, lboA, sboA), al = make_desc(sA1lo + offA, lboA, sboA);
                 const uint64_t bh = make_desc(sB1hi + offB, lboB1, sboB1), bl = make_desc(sB1lo + offB, lboB1, sboB1);
@@ -211,19 +235,21 @@ __global__ void __launch_bounds__(128, 2) nca_update_tc_kernel(const NcaArgs a, 
         ph1 ^= 1;
         tc_fence_after();
 
-        // ---- epilogue 1 + GEMM 2 in chunks of 16 hidden units
-#pragma unroll 1
+        // ---- epilogue 1 + GEMM 2 in chunks of 16 hidden units, A2 double-buffered so the MMA completion latency
+        //      of chunk c-1 is off the critical path of chunk c
+#pragma unroll 2
         for (int c = 0; c < NCA_HID / H2CHUNK; ++c) {
+            const int bsel = c & 1;
             float v[16];
             tmem_ld16(my_tmem + c * H2CHUNK, v);
             float hh[16], hl[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) split_tf32(fmaxf(v[e] + bias1[c * H2CHUNK + e], 0.f), hh[e], hl[e]);
-            if (c > 0) {  // the previous chunk's MMAs must have consumed the A2 buffer
-                mbar_wait(bar2, ph2);
-                ph2 ^= 1;
+            for (int e = 0; e < 16; ++e) split_tf32(fmaxf(v[e], 0.f), hh[e], hl[e]);
+            if (c >= 2) {  // the MMAs of chunk c-2 must have consumed this buffer
+                mbar_wait(bar2 + bsel, ph2[bsel]);
+                ph2[bsel] ^= 1;
             }
-            float4 *ahi = reinterpret_cast<float4 *>(smem + SM_A2HI), *alo = reinterpret_cast<float4 *>(smem + SM_A2LO);
+            float4 *ahi = reinterpret_cast<float4 *>(smem + SM_A2 + bsel * A2_BUF), *alo = ahi + (A2_BUF / 2) / 16;
 #pragma unroll
             for (int kc = 0; kc < H2CHUNK / 4; ++kc) {
                 ahi[kc * 128 + tid] = make_float4(hh[4 * kc], hh[4 * kc + 1], hh[4 * kc + 2], hh[4 * kc + 3]);
@@ -234,6 +260,7 @@ __global__ void __launch_bounds__(128, 2) nca_update_tc_kernel(const NcaArgs a, 
             __syncthreads();
             if (tid == 0) {
                 tc_fence_after();
+                const uint32_t sA2hi = sA2 + bsel * A2_BUF, sA2lo = sA2hi + A2_BUF / 2;
 #pragma unroll
                 for (int s = 0; s < H2CHUNK / 8; ++s) {
                     const uint32_t offA = s * 2 * 128 * 16;
@@ -244,11 +271,14 @@ __global__ void __launch_bounds__(128, 2) nca_update_tc_kernel(const NcaArgs a, 
                     mma_tf32(tmem + D2_COL, ah, bl, IDESC2, 1);
                     mma_tf32(tmem + D2_COL, al, bh, IDESC2, 1);
                 }
-                mma_commit(bar2);
+                mma_commit(bar2 + bsel);
             }
         }
-        mbar_wait(bar2, ph2);
-        ph2 ^= 1;
+        // chunks 6 and 7 are still outstanding
+        mbar_wait(bar2, ph2[0]);
+        ph2[0] ^= 1;
+        mbar_wait(bar2 + 1, ph2[1]);
+        ph2[1] ^= 1;
         tc_fence_after();
 
         // ---- epilogue 2: bias, sigmoid, update mask, pre-update life mask, stores
@@ -290,9 +320,9 @@ __global__ void nca_prepare_tc_kernel(const float *__restrict__ wp_simt, unsigne
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     float *b1hi = reinterpret_cast<float *>(tc + TC_B1HI), *b1lo = reinterpret_cast<float *>(tc + TC_B1LO);
     float *b2hi = reinterpret_cast<float *>(tc + TC_B2HI), *b2lo = reinterpret_cast<float *>(tc + TC_B2LO);
-    if (t < NCA_HID * NCA_K1) {  // B1[n][k] = W1f[n][k] -> [k/4][n][k%4]
-        const int n = t / NCA_K1, k = t % NCA_K1;
-        const float w = wp_simt[WP_W1F + t];
+    if (t < NCA_HID * K1P) {  // B1[n][k] = [W1f | b1 | 0][n][k] -> [k/4][n][k%4]
+        const int n = t / K1P, k = t % K1P;
+        const float w = k < NCA_K1 ? wp_simt[WP_W1F + n * NCA_K1 + k] : (k == NCA_K1 ? wp_simt[WP_B1 + n] : 0.f);
         const float hi = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xffffe000u);
         const int idx = ((k >> 2) * NCA_HID + n) * 4 + (k & 3);
         b1hi[idx] = hi;
@@ -313,7 +343,7 @@ __global__ void nca_prepare_tc_kernel(const float *__restrict__ wp_simt, unsigne
 int nca_prepare_tc(const float *, const float *, const float *, const float *, void *Wprep, cudaStream_t st) {
     // runs after nca_prepare_simt_kernel on the same stream: reads the folded/transposed fp32 copies it produced
     unsigned char *base = reinterpret_cast<unsigned char *>(Wprep);
-    nca_prepare_tc_kernel<<<ceil_div(NCA_HID * NCA_K1, 256), 256, 0, st>>>(reinterpret_cast<const float *>(base), base + WP_TC_OFF);
+    nca_prepare_tc_kernel<<<ceil_div(NCA_HID * K1P, 256), 256, 0, st>>>(reinterpret_cast<const float *>(base), base + WP_TC_OFF);
     B200CA_LAUNCH_CHECK("nca_prepare_tc_kernel");
     return 0;
 }
