@@ -61,9 +61,8 @@ constexpr int H2CHUNK = 16;     // hidden columns per GEMM-2 chunk (two K=8 step
 // tf32 split: hi = x rounded to 10 explicit mantissa bits (low 13 bits zero, so the tensor core's truncation is exact);
 // lo = x - hi (exact in fp32; the tensor core keeps its top 11 bits: error <= 2^-22 |x|)
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
+    // (cvt.rna.tf32.f32 expands to ~6 SASS instructions on sm_100; the add-and-mask form is 2)
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
     lo = x - hi;
 }
 
@@ -173,13 +172,19 @@ __global__ void __launch_bounds__(128, 2) nca_update_tc_kernel(const NcaArgs a, 
         {
             const int xm = xc == 0 ? a.W - 1 : xc - 1, xp = xc == a.W - 1 ? 0 : xc + 1;
             const int ym = yc == 0 ? a.H - 1 : yc - 1, yp = yc == a.H - 1 ? 0 : yc + 1;
-            const int o00 = ym * a.W + xm, o01 = ym * a.W + xc, o02 = ym * a.W + xp;
-            const int o10 = yc * a.W + xm, o11 = yc * a.W + xc, o12 = yc * a.W + xp;
-            const int o20 = yp * a.W + xm, o21 = yp * a.W + xc, o22 = yp * a.W + xp;
+            // 32-bit element offsets inside this world's (16,H,W) block: one IMAD.WIDE per load instead of 64-bit chains
+            const uint32_t uplane = (uint32_t)plane;
+            uint32_t o00 = ym * a.W + xm, o01 = ym * a.W + xc, o02 = ym * a.W + xp;
+            uint32_t o10 = yc * a.W + xm, o11 = yc * a.W + xc, o12 = yc * a.W + xp;
+            uint32_t o20 = yp * a.W + xm, o21 = yp * a.W + xc, o22 = yp * a.W + xp;
             float p[NCA_K1];
 #pragma unroll
             for (int c = 0; c < NCA_N; ++c) {
-                const float *pl = sb + (size_t)c * plane;
+                const float *pl = sb;
+                if (c > 0) {
+                    o00 += uplane; o01 += uplane; o02 += uplane; o10 += uplane; o11 += uplane; o12 += uplane;
+                    o20 += uplane; o21 += uplane; o22 += uplane;
+                }
                 const float ctr = __ldg(pl + o11);
                 p[16 + c] = ctr;
                 if (c < 8) {
