@@ -149,9 +149,13 @@ class Workload:
 class LeniaWL(Workload):
     """Lenia, single channel sliced from demo_lenia/abominable_mongolic (BASELINE configs[1]); slab-sharded for N>1."""
 
-    def __init__(self, rank, world, device, H, W, C=1, name="lenia_1k"):
+    def __init__(self, rank, world, device, H, W, C=1, name="lenia_1k", replicas=False):
         super().__init__(rank, world, device)
         self.H, self.W, self.C, self.name = H, W, C, name
+        # replicas: one independent world per GPU (no communication, weak scaling); else one world in row slabs
+        self.replicas = replicas and world > 1
+        if self.replicas:
+            self.scaling = "weak"
 
     def _params(self):
         import pyca_b200
@@ -166,8 +170,8 @@ class LeniaWL(Workload):
         from pyca_b200.slab import LeniaSlabCUDA
 
         self.params = self._params()
-        if self.world == 1:
-            g = torch.Generator().manual_seed(0)
+        if self.world == 1 or self.replicas:
+            g = torch.Generator().manual_seed(self.rank)
             self.h_state = torch.rand(1, self.C, self.H, self.W, generator=g).pin_memory()
             self.auto = pyca_b200.Lenia((self.H, self.W), num_channels=self.C, params=self.params, state_init=self.h_state,
                                         device=self.device, conv_path=os.environ.get("B200CA_LENIA_PATH", "auto"))
@@ -185,20 +189,32 @@ class LeniaWL(Workload):
             self.slab.step()
 
     def cells_per_step(self):
-        return self.H * self.W
+        return self.H * self.W * (self.world if self.replicas else 1)
+
+    def _fft(self):
+        return self.slab is None and getattr(self, "auto", None) is not None and self.auto.use_fft
 
     def launches_per_step(self):
-        return 1 if self.slab is None else self.slab.launches_per_step
+        if self.slab is not None:
+            return self.slab.launches_per_step
+        return 3 if self._fft() else 1
 
     def dominant(self):
-        cells = self.H * self.W // self.world
+        cells = self.H * self.W if self.replicas else self.H * self.W // self.world
+        if self._fft():
+            # all three kernels of the step are timed together (rows FFT, column FIR, inverse FFT + growth)
+            return {"kernel": "lenia_fft_rows + lenia_fft_fir + lenia_fft_inv (whole step)", "bytes": cells * self.C * 8, "fma": 0}
         return {"kernel": "lenia_conv_kernel", "bytes": cells * self.C * 8, "fma": cells * self.C * self.C * 496}
 
     def config(self):
+        path = "row-FFT x column-FIR hybrid + growth + clamp, 3 kernels/step" if self._fft() else \
+            "direct folded conv (TMA tiles) + growth + clamp, 1 kernel/step"
         return {"workload": self.name, "shape": [1, self.C, self.H, self.W], "k_size": 31,
                 "params": "demo_lenia/abominable_mongolic" + (f" sliced to C={self.C}" if self.C != 3 else ""),
-                "path": "direct folded conv (TMA tiles) + growth + clamp, 1 kernel/step",
-                "partition": "single GPU" if self.world == 1 else f"{self.world} row slabs, NCCL halo exchange overlapped with interior",
+                "path": path,
+                "partition": "single GPU" if self.world == 1 else (
+                    f"{self.world} independent worlds, one per GPU, no communication" if self.replicas else
+                    f"{self.world} row slabs, NCCL halo exchange" + (" overlapped with interior" if not (self.slab and self.slab.use_fft) else "")),
                 "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)"}
 
     def e2e_setup(self):
@@ -345,10 +361,12 @@ class MaceWL(Workload):
         return self.H * self.W * self.world  # independent worlds per rank
 
     def launches_per_step(self):
-        return 2
+        return 4 if self.auto.use_fft else 2
 
     def dominant(self):
         cells = self.H * self.W
+        if self.auto.use_fft:
+            return {"kernel": "affinity: lenia_fft_rows + lenia_fft_fir + lenia_fft_inv", "bytes": cells * 3 * 8, "fma": 0}
         return {"kernel": "lenia_conv_kernel", "bytes": cells * 3 * 8, "fma": cells * 9 * 496}
 
     def config(self):
@@ -435,7 +453,9 @@ class NcaWL(Workload):
 
     def dominant(self):
         cells = self.Bl * self.H * self.W
-        return {"kernel": "nca_update", "bytes": cells * 128, "fma": cells * 6144, "flops_tensor": cells * 12288}
+        return {"kernel": "nca_update_tc_kernel" if self.impl == 1 else "nca_update_simt_kernel", "bytes": cells * 128,
+                "fma": 0 if self.impl == 1 else cells * 6144, "flops_algorithmic": cells * 16384,
+                "flops_issued_tf32": cells * 2 * 3 * (128 * 40 + 16 * 128)}
 
     def config(self):
         return {"workload": self.name, "shape": [self.B, 16, self.H, self.W], "weights": "NCA_models/betta", "rng": "in-kernel Philox",
@@ -478,7 +498,7 @@ class NcaWL(Workload):
 
 def make_workload(name, rank, world, device):
     if name == "lenia_1k":
-        return LeniaWL(rank, world, device, 1024, 1024, 1, name)
+        return LeniaWL(rank, world, device, 1024, 1024, 1, name, replicas=True)
     if name == "lenia3_1k":
         return LeniaWL(rank, world, device, 1024, 1024, 3, name)
     if name == "lenia_4k":
@@ -563,7 +583,7 @@ def run_reference(args, rank, world):
     """--impl reference: the CPU implementation of the path (oracle port), all host threads, rank 0 only."""
     if rank != 0:
         return
-    name = args.workload or ("lenia_1k" if world == 1 else "lenia_16k")
+    name = args.workload or "lenia_1k"
     wl = make_workload(name, 0, 1, "cpu")
     if hasattr(wl, "_params"):
         wl.params = wl._params()
@@ -622,7 +642,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=torch.device(device))
-    name = args.workload or ("lenia_1k" if world == 1 else "lenia_16k")
+    name = args.workload or "lenia_1k"
     wl = make_workload(name, rank, world, device)
     wl.setup()
     dom = wl.dominant()
@@ -668,29 +688,36 @@ def main():
         roofline["fp32_fma"] = {"achieved_tfma_s": dom["fma"] / (kern_ms * 1e-3) / 1e12, "peak_tfma_s_at_sampled_clock": fma_peak,
                                 "frac": dom["fma"] / (kern_ms * 1e-3) / 1e12 / fma_peak,
                                 "note": "folded direct conv: 496 FMA per cell and channel pair; this pipe, not HBM, bounds the kernel"}
-    if dom.get("flops_tensor") and isinstance(wl, NcaWL) and wl.impl == 1:
-        tf = dom["flops_tensor"] / (kern_ms * 1e-3) / 1e12
-        roofline["tensor"] = {"achieved_tflops_algorithmic": tf, "issued_tflops_tf32x3": 3 * tf, "bf16_peak_tflops": peaks["bf16_tflops"],
-                              "frac_of_tf32_peak_issued": 3 * tf / (peaks["bf16_tflops"] / 2)}
+    if isinstance(wl, NcaWL) and wl.impl == 1:
+        alg = dom["flops_algorithmic"] / (kern_ms * 1e-3) / 1e12
+        iss = dom["flops_issued_tf32"] / (kern_ms * 1e-3) / 1e12
+        roofline["tensor"] = {"algorithmic_tflops": alg, "issued_tf32_tflops": iss, "tf32_peak_tflops": peaks["bf16_tflops"] / 2,
+                              "frac_issued_of_tf32_peak": iss / (peaks["bf16_tflops"] / 2),
+                              "note": "split-tf32: 3 tcgen05.mma per product for fp32-grade accuracy; tf32 peak taken as half the "
+                                      "measured bf16 peak"}
 
     e2e = None
-    if rank == 0 and world == 1:
+    if world == 1 or getattr(wl, "replicas", False):
+        # every rank drives its own world through the public API with pinned host buffers; max time over ranks
         wl.e2e_setup()
         for _ in range(3):
             wl.e2e_step()
-        torch.cuda.synchronize()
+        barrier(world)
         n_e2e = max(3, min(args.steps, 20))
         t0 = time.perf_counter()
         for _ in range(n_e2e):
             hb, db = wl.e2e_step()
         torch.cuda.synchronize()
-        el = time.perf_counter() - t0
+        el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        if world > 1:
+            torch.distributed.all_reduce(el, op=torch.distributed.ReduceOp.MAX)
+        el = float(el.item())
         cells = wl.e2e_cells() if hasattr(wl, "e2e_cells") else wl.cells_per_step()
         e2e = {"value": cells * n_e2e / el / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": hb, "d2h_bytes_per_step": db,
                "ms_per_step": el / n_e2e * 1e3, "api": "Automaton.state = <pinned host tensor>; step(); state -> pinned host tensor"}
     elif rank == 0:
         e2e = {"value": None, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "note": "end-to-end host-buffer path is measured at N=1 (a sharded world is generated per slab on device)"}
+               "note": "end-to-end host-buffer path is measured for single-GPU / replica workloads (a sharded world is generated per slab on device)"}
 
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
@@ -716,6 +743,36 @@ def main():
             except Exception as e:  # keep the headline line even if an extra fails
                 extras[other] = {"error": repr(e)[:200]}
 
+    sharded = None
+    if world > 1 and not args.no_extras:
+        # BASELINE configs[4]: one big torus in row slabs with NVLink halo exchange; raw values at N GPUs and, for
+        # reference, the same world on one GPU of this box (every rank runs it alone, rank 0's number is kept)
+        sharded = {}
+        for big in ["lenia_16k", "gol_64k"]:
+            try:
+                ent = {}
+                sw = make_workload(big, rank, world, device)
+                sw.setup()
+                k = 10
+                t = torch.tensor([time_block(sw, k, 3, world) / k], dtype=torch.float64, device=device)
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+                ent["ms_per_step"] = float(t.item())
+                ent["gcups"] = sw.cells_per_step() / (ent["ms_per_step"] * 1e-3) / 1e9
+                ent["config"] = sw.config()
+                del sw
+                torch.cuda.empty_cache()
+                s1 = make_workload(big, 0, 1, device)
+                s1.setup()
+                ms1 = time_block(s1, k, 3, 1) / k
+                ent["single_gpu_ms_per_step"] = ms1
+                ent["single_gpu_gcups"] = s1.cells_per_step() / (ms1 * 1e-3) / 1e9
+                del s1
+                torch.cuda.empty_cache()
+                torch.distributed.barrier()
+                sharded[big] = ent
+            except Exception as e:
+                sharded[big] = {"error": repr(e)[:300]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(wl)
@@ -725,7 +782,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": wl.scaling, "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.config(),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": wl.launches_per_step() * args.steps, "roofline": roofline,
-                "cpu_baseline": cpu, "per_model": extras}
+                "cpu_baseline": cpu, "per_model": extras, "sharded": sharded}
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.barrier()

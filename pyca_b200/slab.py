@@ -216,7 +216,7 @@ class LeniaSlabCUDA(LeniaSlab):
     """Lenia row slab on one GPU: boundary tile rows first, halo exchange on a side stream overlapped with
     the interior tiles (Lenia.step semantics, lenia.py:430-451, on rows [r0, r1) of the global torus)."""
 
-    def __init__(self, lenia_params, C, H, W, rank, world, device="cuda", dt=0.1, overlap=True):
+    def __init__(self, lenia_params, C, H, W, rank, world, device="cuda", dt=0.1, overlap=True, conv_path="auto"):
         from . import _lib
         from .lenia_params import compute_kernel
 
@@ -235,12 +235,24 @@ class LeniaSlabCUDA(LeniaSlab):
         with torch.cuda.device(self.device):
             _lib.call("b200ca_lenia_prepare_kernel", _lib.ptr(self.k), _lib.ptr(self._kprep), B, C, self.k_mult, int(p["k_size"]),
                       _lib.current_stream(self.device))
+        # FFT path (row-FFT x column-FIR hybrid): the column direction is local, so a slab only needs its 15 ghost rows
+        fft_ok = L.b200ca_lenia_fft_length(self.hl, W) > 0
+        if conv_path == "fft" and not fft_ok:
+            raise _lib.B200CAError(f"conv_path='fft' unsupported for a {self.hl}x{W} slab")
+        self.use_fft = fft_ok and conv_path in ("fft", "auto")
+        if self.use_fft:
+            self._kfft = torch.empty(L.b200ca_lenia_fft_kernel_elems(B, C, self.k_mult, self.hl, W), dtype=torch.float32, device=device)
+            with torch.cuda.device(self.device):
+                _lib.call("b200ca_lenia_fft_prepare_kernel", _lib.ptr(self.k), _lib.ptr(self._kfft), B, C, self.k_mult, int(p["k_size"]),
+                          self.hl, W, _lib.current_stream(self.device))
+            self._fft_ws = torch.empty(L.b200ca_lenia_fft_workspace_elems(B, C, self.k_mult, self.hl, W), dtype=torch.float32,
+                                       device=device)
         self.tile_rows = L.b200ca_lenia_tile_rows(self.hl, W, B, C)
         self.n_tile_rows = (self.hl + self.tile_rows - 1) // self.tile_rows
         self.n_boundary = (self.F + self.tile_rows - 1) // self.tile_rows  # tile rows covering F owned rows
-        self.overlap = overlap and world > 1 and self.n_tile_rows > 2 * self.n_boundary
+        self.overlap = overlap and world > 1 and self.n_tile_rows > 2 * self.n_boundary and not self.use_fft
         self.comm_stream = torch.cuda.Stream(device=self.device) if world > 1 else None
-        self.launches_per_step = 3 if self.overlap else 1
+        self.launches_per_step = 3 if (self.overlap or self.use_fft) else 1
 
     def set_interior(self, dense: torch.Tensor, group=None):
         """dense: (B,C,hl,W) rows [r0,r1) of the global state."""
@@ -256,6 +268,11 @@ class LeniaSlabCUDA(LeniaSlab):
     def _launch(self, t0, t1):
         from . import _lib
 
+        if self.use_fft:
+            _lib.call("b200ca_lenia_step_fft", _lib.ptr(self.buf), _lib.ptr(self.other), _lib.ptr(self._kfft), _lib.ptr(self.mu),
+                      _lib.ptr(self.sigma), _lib.ptr(self.weights), _lib.ptr(self._fft_ws), self.B, self.C, self.k_mult, self.hl,
+                      self.W, float(self.dt), 0, 1 if self.world == 1 else 0, _lib.current_stream(self.device))
+            return
         _lib.call("b200ca_lenia_step", _lib.ptr(self.buf), _lib.ptr(self.other), _lib.ptr(self._kprep), _lib.ptr(self.mu),
                   _lib.ptr(self.sigma), _lib.ptr(self.weights), self.B, self.C, self.k_mult, self.hl, self.W, float(self.dt), 0,
                   1 if self.world == 1 else 0, t0, t1, _lib.current_stream(self.device))
