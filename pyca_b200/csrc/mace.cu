@@ -121,6 +121,136 @@ __global__ void __launch_bounds__(MTHREADS) mace_kernel(const MaceArgs a) {
     }
 }
 
+
+// ---- fast path (C <= 4): register sliding windows + warp shuffles, no shared memory ---------------------------------
+// A warp owns 28 output columns (lanes 2..29; lanes 0,1,30,31 carry the 2-cell halo) and marches down MROWS rows.  Per
+// channel and input row r:  E(r) = exp(beta*Aff(r));  rE(r) = E(x-1)+E(x)+E(x+1) (2 shuffles);
+// Z(r-1) = rE(r-2)+rE(r-1)+rE(r);  G(r-1) = A(r-1)/Z(r-1);  rG(r-1) (2 shuffles);
+// out(r-2) = E(r-2) * (rG(r-3)+rG(r-2)+rG(r-1)).  ~40 instructions per cell and channel, every value loaded once.
+constexpr int MCOLS = 28;
+
+__device__ __noinline__ void mace_mirrors(float *__restrict__ plane, int H, int W, int pitch, int y, int x, float v, bool row_wrap) {
+    const int fy = y + F, fx = x + F;
+    int ys[3], xs[3], ny = 0, nx = 0;
+    ys[ny++] = fy;
+    if (row_wrap) {
+        if (y < F) ys[ny++] = fy + H;
+        if (y >= H - F) ys[ny++] = fy - H;
+    }
+    xs[nx++] = fx;
+    if (x < F) xs[nx++] = fx + W;
+    if (x >= W - F) xs[nx++] = fx - W;
+    for (int a = 0; a < ny; ++a)
+        for (int b = 0; b < nx; ++b)
+            if (a | b) plane[(size_t)ys[a] * pitch + xs[b]] = v;
+}
+
+template <int C, int MROWS>
+__global__ void __launch_bounds__(128) mace_fast_kernel(const MaceArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int xw = blockIdx.x * 4 + warp;
+    const int x = xw * MCOLS - 2 + lane;           // column this lane carries (may be halo / outside)
+    const int y0 = blockIdx.y * MROWS;
+    const int b = blockIdx.z;
+    const int frows = a.H + 2 * F;
+    const int fx = min(max(x + F, 0), a.pitch - 1);  // clamped framed column (out-of-range lanes feed nothing valid)
+    const bool out_lane = lane >= 2 && lane < 2 + MCOLS && x >= 0 && x < a.W;
+    const float bl2 = a.beta * 1.4426950408889634f;
+    const size_t pstride = (size_t)frows * a.pitch;
+    const float *affp = a.aff + (size_t)b * C * pstride + fx;
+    const float *stp = a.state_in + (size_t)b * C * pstride + fx;
+    float *outp = a.out + (size_t)b * C * pstride;
+
+    float E[C][3], rE[C][3], rG[C][3], AF[C][3];  // index 0: oldest row
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) E[c][k] = rE[c][k] = rG[c][k] = AF[c][k] = 0.f;
+
+    const int rend = min(y0 + MROWS, a.H) + 2;  // last input row + 1
+    // software pipeline: the loads of input row r+1 are issued before row r is processed
+    float afn[C], stn[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        afn[c] = __ldg(affp + (size_t)c * pstride + (size_t)(y0 - 2 + F) * a.pitch);
+        stn[c] = __ldg(stp + (size_t)c * pstride + (size_t)(y0 - 3 + F) * a.pitch);
+    }
+    for (int r = y0 - 2; r < rend; ++r) {
+        float afc[C], stc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            afc[c] = afn[c];
+            stc[c] = stn[c];
+        }
+        {
+            const int frn = min(r + 1 + F, frows - 1);  // next Aff row (clamped on the last iteration, value unused)
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                afn[c] = __ldg(affp + (size_t)c * pstride + (size_t)frn * a.pitch);
+                stn[c] = __ldg(stp + (size_t)c * pstride + (size_t)(frn - 1) * a.pitch);
+            }
+        }
+        float outv[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float af = afc[c];   // Aff row r
+            const float st = stc[c];   // state row r-1
+            const float e = exp2f(bl2 * af);
+            const float re = __shfl_up_sync(0xffffffffu, e, 1) + e + __shfl_down_sync(0xffffffffu, e, 1);
+            // shift windows
+            E[c][0] = E[c][1]; E[c][1] = E[c][2]; E[c][2] = e;
+            AF[c][0] = AF[c][1]; AF[c][1] = AF[c][2]; AF[c][2] = af;
+            rE[c][0] = rE[c][1]; rE[c][1] = rE[c][2]; rE[c][2] = re;
+            const float z = rE[c][0] + rE[c][1] + rE[c][2];           // Z(r-1)
+            const float gq = __fdividef(st, z);                        // G(r-1)
+            const float rg = __shfl_up_sync(0xffffffffu, gq, 1) + gq + __shfl_down_sync(0xffffffffu, gq, 1);
+            rG[c][0] = rG[c][1]; rG[c][1] = rG[c][2]; rG[c][2] = rg;
+            outv[c] = E[c][0] * (rG[c][0] + rG[c][1] + rG[c][2]);      // out(r-2)
+        }
+        const int yo = r - 2;
+        if (yo < y0 || !out_lane) continue;   // window still filling / halo lane
+        if (a.alpha_on) {
+            float mx = AF[0][0], tot = outv[0];
+#pragma unroll
+            for (int c = 1; c < C; ++c) {
+                mx = fmaxf(mx, AF[c][0]);
+                tot += outv[c];
+            }
+            float num[C], den = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                num[c] = exp2f(bl2 * (AF[c][0] - mx));
+                den += num[c];
+            }
+            const float inv = __fdividef(1.f, den);
+#pragma unroll
+            for (int c = 0; c < C; ++c) outv[c] = outv[c] - (outv[c] - tot * (num[c] * inv)) * a.alpha;
+        }
+        const bool edge = (x < F) || (x >= a.W - F) || (a.row_wrap && (yo < F || yo >= a.H - F));
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float *pl = outp + (size_t)c * pstride;
+            pl[(size_t)(yo + F) * a.pitch + x + F] = outv[c];
+            if (edge) mace_mirrors(pl, a.H, a.W, a.pitch, yo, x, outv[c], a.row_wrap != 0);
+        }
+    }
+}
+
+template <int C>
+static int launch_mace_fast(const MaceArgs &a, cudaStream_t st) {
+    // 32 rows per warp (12 % halo re-reads) when that still gives every SM several blocks, else 8 rows
+    const long long blocks32 = (long long)ceil_div(ceil_div(a.W, MCOLS), 4) * ceil_div(a.H, 32) * a.B;
+    if (blocks32 >= (long long)num_sms() * 8) {
+        dim3 grid(ceil_div(ceil_div(a.W, MCOLS), 4), ceil_div(a.H, 32), a.B);
+        mace_fast_kernel<C, 32><<<grid, 128, 0, st>>>(a);
+    } else {
+        dim3 grid(ceil_div(ceil_div(a.W, MCOLS), 4), ceil_div(a.H, 8), a.B);
+        mace_fast_kernel<C, 8><<<grid, 128, 0, st>>>(a);
+    }
+    B200CA_LAUNCH_CHECK("mace_fast_kernel");
+    return 0;
+}
+
 }  // namespace b200ca
 
 using namespace b200ca;
@@ -147,6 +277,13 @@ extern "C" int b200ca_mace_redistribute(const float *state_in, const float *aff,
     a.alpha = alpha;
     a.alpha_on = alpha_on ? 1 : 0;
     a.row_wrap = row_wrap;
+    switch (C) {  // register/shuffle fast path for the channel counts PyCA ships; shared-memory kernel otherwise
+        case 1: return launch_mace_fast<1>(a, as_stream(stream));
+        case 2: return launch_mace_fast<2>(a, as_stream(stream));
+        case 3: return launch_mace_fast<3>(a, as_stream(stream));
+        case 4: return launch_mace_fast<4>(a, as_stream(stream));
+        default: break;
+    }
     dim3 grid(ceil_div(W, MTX), ceil_div(H, MTY), B);
     mace_kernel<<<grid, MTHREADS, smem, as_stream(stream)>>>(a);
     B200CA_LAUNCH_CHECK("mace_kernel");
