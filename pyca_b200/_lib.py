@@ -91,9 +91,41 @@ def check(rc: int, what: str = "") -> None:
         raise B200CAError(f"{what or 'b200ca call'} failed (rc={rc}): {msg.decode() if msg else ''}")
 
 
+_fn_cache = {}
+
+
 def call(name: str, *args) -> None:
     """Calls an int-returning entry point and raises on a non-zero return."""
-    check(getattr(lib(), name)(*args), name)
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _fn_cache[name] = getattr(lib(), name)
+    rc = fn(*args)
+    if rc != 0:
+        check(rc, name)
+
+
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NOGUARD = _NoGuard()
+
+
+def device_guard(device):
+    """`torch.cuda.device(device)` only when `device` is not already current (the context manager costs microseconds,
+    a Lenia 1024^2 step takes ~25)."""
+    import torch
+
+    if not isinstance(device, torch.device):
+        device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx == torch.cuda.current_device():
+        return _NOGUARD
+    return torch.cuda.device(idx)
 
 
 def ptr(t) -> int:

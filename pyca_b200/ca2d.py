@@ -52,19 +52,19 @@ class PackedWorld:
         if w.dtype not in _ELEM:
             w = w.to(torch.int32)
         w = w.contiguous()
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.call("b200ca_gol_pack", _lib.ptr(w), _ELEM[w.dtype], _lib.ptr(self.bits), self.H, self.W, self.stride,
                       _lib.current_stream(self.device))
 
     def unpack(self, dtype=torch.int32) -> torch.Tensor:
         out = torch.empty((self.H, self.W), dtype=dtype, device=self.device)
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.call("b200ca_gol_unpack", _lib.ptr(self.bits), _lib.ptr(out), _ELEM[dtype], self.H, self.W, self.stride,
                       _lib.current_stream(self.device))
         return out
 
     def step(self, s_mask, b_mask, nsteps=1, vert_open=False):
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             a, b = self.bufs[self.cur], self.bufs[self.cur ^ 1]
             _lib.call("b200ca_gol_run", _lib.ptr(a), _lib.ptr(b), self.H, self.W, self.stride, s_mask, b_mask,
                       1 if vert_open else 0, nsteps, _lib.current_stream(self.device))
@@ -73,13 +73,13 @@ class PackedWorld:
 
     def population(self) -> int:
         cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.call("b200ca_gol_population", _lib.ptr(self.bits), self.H, self.W, self.stride, _lib.ptr(cnt),
                       _lib.current_stream(self.device))
         return int(cnt.item())
 
     def random_fill(self, seed: int, row0: int = 0):
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.call("b200ca_gol_random_fill", _lib.ptr(self.bits), self.H, self.W, self.stride, seed, row0,
                       _lib.current_stream(self.device))
 

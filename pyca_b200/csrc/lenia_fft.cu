@@ -88,20 +88,31 @@ __device__ __forceinline__ void load_tw(const float2 *__restrict__ tws, int span
 
 // ---- kernel A: forward row FFTs -------------------------------------------------------------------
 // grid (ceil(zrows / FFT_RPC), nseg, B*C), block N/4 threads, smem FFT_RPC * N float2
-template <int FFT_RPC>
-__global__ void __launch_bounds__(256) lenia_fft_rows_kernel(const float *__restrict__ state, float2 *__restrict__ Z,
+template <int FFT_RPC, int N>
+__global__ void __launch_bounds__(N / 4) lenia_fft_rows_kernel(const float *__restrict__ state, float2 *__restrict__ Z,
                                                               const float2 *__restrict__ tws, FftGeom g, int H, int W, int pitch) {
     extern __shared__ __align__(16) float2 fsm[];
-    const int N = g.N, T = N >> 2, tid = threadIdx.x;
+    constexpr int T = N >> 2;
+    const int tid = threadIdx.x;
     const int seg = blockIdx.y, plane = blockIdx.z;
     const int xoff = g.periodic ? F : seg * g.V - R + F;  // framed column of sample n = 0
     int zr[FFT_RPC];
 #pragma unroll
     for (int q = 0; q < FFT_RPC; ++q) zr[q] = min((int)blockIdx.x * FFT_RPC + q, g.zrows - 1);
+    // twiddles of every stage are fetched up front so their latency overlaps the first global loads instead of sitting
+    // on the critical path of each stage (stage s: span = T >> 2s; the last stage, span 1, needs none)
+    float2 tw1[5], tw2[5], tw3[5];
+    {
+        int sp = T;
+#pragma unroll
+        for (int st = 0; st < 5; ++st) {
+            if (sp > 1) load_tw(tws, sp, tid & (sp - 1), tw1[st], tw2[st], tw3[st]);
+            sp >>= 2;
+        }
+    }
     // first stage straight from global memory (span = N/4, k = tid)
     {
-        float2 w1, w2, w3;
-        load_tw(tws, T, tid, w1, w2, w3);
+        const float2 w1 = tw1[0], w2 = tw2[0], w3 = tw3[0];
 #pragma unroll
         for (int q = 0; q < FFT_RPC; ++q) {
             // image rows (framed): r = zr - R (may be negative: frame rows) and r + D
@@ -121,12 +132,13 @@ __global__ void __launch_bounds__(256) lenia_fft_rows_kernel(const float *__rest
         }
     }
     // middle stages in shared memory
-    for (int span = T >> 2; span > 1; span >>= 2) {
+    int stg = 1;
+#pragma unroll
+    for (int span = T >> 2; span > 1; span >>= 2, ++stg) {
         __syncthreads();
         const int k = tid & (span - 1);
         const int i0 = ((tid - k) << 2) + k;
-        float2 w1, w2, w3;
-        load_tw(tws, span, k, w1, w2, w3);
+        const float2 w1 = tw1[stg], w2 = tw2[stg], w3 = tw3[stg];
         // the swizzle only looks at index bits 4-5, which adding a multiple of 64 does not touch
         const int p0 = swz(i0);
         const int p1 = span >= 64 ? p0 + span : swz(i0 + span);
@@ -238,10 +250,11 @@ __device__ __noinline__ void fft_store_mirrors(float *__restrict__ plane, int H,
 }
 
 // grid (ceil(D / FFT_RPC), nseg, B*C), block N/4 threads, smem FFT_RPC * N float2
-template <int FFT_RPC>
-__global__ void __launch_bounds__(256) lenia_fft_inv_kernel(const FftInvArgs a) {
+template <int FFT_RPC, int N>
+__global__ void __launch_bounds__(N / 4, (FFT_RPC == 1 && N == 1024) ? 4 : 1) lenia_fft_inv_kernel(const FftInvArgs a) {
     extern __shared__ __align__(16) float2 ism[];
-    const int N = a.g.N, T = N >> 2, tid = threadIdx.x;
+    constexpr int T = N >> 2;
+    const int tid = threadIdx.x;
     const int seg = blockIdx.y;
     const int b = blockIdx.z / a.C, j = blockIdx.z % a.C;
     int yy[FFT_RPC];
@@ -269,11 +282,12 @@ __global__ void __launch_bounds__(256) lenia_fft_inv_kernel(const FftInvArgs a) 
             const int i0 = tid << 2;
             buf[swz(i0)] = p; buf[swz(i0 + 1)] = qq; buf[swz(i0 + 2)] = r; buf[swz(i0 + 3)] = s;
         }
+#pragma unroll
         for (int span = 4; span < T; span <<= 2) {
             __syncthreads();
             const int k = tid & (span - 1);
             const int i0 = ((tid - k) << 2) + k;
-            float2 w1, w2, w3;
+            float2 w1, w2, w3;  // (prefetching all stages' twiddles costs more in occupancy than it hides: measured)
             load_tw(a.tws, span, k, w1, w2, w3);
             const int p0 = swz(i0);
             const int p1 = span >= 64 ? p0 + span : swz(i0 + span);
@@ -508,23 +522,31 @@ extern "C" int b200ca_lenia_step_fft(const float *state_in, float *state_out, co
     const int NS = C * k_mult;
     float2 *Z = reinterpret_cast<float2 *>(workspace);
     float2 *O = Z + (size_t)B * C * g.zrows * g.nseg * g.N;
-    static int rpc_rows = 0, rpc_inv = 0;
+    static int rpc_rows = 0, rpc_inv = 0, only = 0;  // `only`: developer switch, run a single phase (timing)
     if (!rpc_rows) {
+        const char *e3 = getenv("B200CA_FFT_ONLY");
+        only = e3 ? atoi(e3) : 0;
         const char *e1 = getenv("B200CA_FFT_RPC_ROWS"), *e2 = getenv("B200CA_FFT_RPC_INV");
         rpc_rows = e1 ? atoi(e1) : 2;
         rpc_inv = e2 ? atoi(e2) : 1;
         if (rpc_rows != 1 && rpc_rows != 4) rpc_rows = 2;
         if (rpc_inv != 2 && rpc_inv != 4) rpc_inv = 1;
     }
-    {
+    if (only == 0 || only == 1) {
         const size_t smem = (size_t)rpc_rows * g.N * sizeof(float2);
         dim3 grid(ceil_div(g.zrows, rpc_rows), g.nseg, B * C);
-        if (rpc_rows == 1) lenia_fft_rows_kernel<1><<<grid, g.N / 4, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
-        else if (rpc_rows == 2) lenia_fft_rows_kernel<2><<<grid, g.N / 4, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
-        else lenia_fft_rows_kernel<4><<<grid, g.N / 4, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
+        if (g.N == 1024) {
+            if (rpc_rows == 1) lenia_fft_rows_kernel<1, 1024><<<grid, 256, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
+            else if (rpc_rows == 2) lenia_fft_rows_kernel<2, 1024><<<grid, 256, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
+            else lenia_fft_rows_kernel<4, 1024><<<grid, 256, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
+        } else {
+            if (rpc_rows == 1) lenia_fft_rows_kernel<1, 256><<<grid, 64, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
+            else if (rpc_rows == 2) lenia_fft_rows_kernel<2, 256><<<grid, 64, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
+            else lenia_fft_rows_kernel<4, 256><<<grid, 64, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
+        }
         B200CA_LAUNCH_CHECK("lenia_fft_rows_kernel");
     }
-    {
+    if (only == 0 || only == 2) {
         FftFirArgs a;
         a.Z = Z;
         a.O = O;
@@ -545,7 +567,7 @@ extern "C" int b200ca_lenia_step_fft(const float *state_in, float *state_out, co
         }
         B200CA_LAUNCH_CHECK("lenia_fft_fir_kernel");
     }
-    {
+    if (only == 0 || only == 3) {
         FftInvArgs a;
         a.state_in = state_in;
         a.out = state_out;
@@ -566,9 +588,15 @@ extern "C" int b200ca_lenia_step_fft(const float *state_in, float *state_out, co
         a.row_wrap = row_wrap;
         const size_t smem = (size_t)rpc_inv * g.N * sizeof(float2);
         dim3 grid(ceil_div(g.D, rpc_inv), g.nseg, B * C);
-        if (rpc_inv == 1) lenia_fft_inv_kernel<1><<<grid, g.N / 4, smem, st>>>(a);
-        else if (rpc_inv == 2) lenia_fft_inv_kernel<2><<<grid, g.N / 4, smem, st>>>(a);
-        else lenia_fft_inv_kernel<4><<<grid, g.N / 4, smem, st>>>(a);
+        if (g.N == 1024) {
+            if (rpc_inv == 1) lenia_fft_inv_kernel<1, 1024><<<grid, 256, smem, st>>>(a);
+            else if (rpc_inv == 2) lenia_fft_inv_kernel<2, 1024><<<grid, 256, smem, st>>>(a);
+            else lenia_fft_inv_kernel<4, 1024><<<grid, 256, smem, st>>>(a);
+        } else {
+            if (rpc_inv == 1) lenia_fft_inv_kernel<1, 256><<<grid, 64, smem, st>>>(a);
+            else if (rpc_inv == 2) lenia_fft_inv_kernel<2, 256><<<grid, 64, smem, st>>>(a);
+            else lenia_fft_inv_kernel<4, 256><<<grid, 64, smem, st>>>(a);
+        }
         B200CA_LAUNCH_CHECK("lenia_fft_inv_kernel");
     }
     return 0;

@@ -72,7 +72,7 @@ class FramedState:
         d = dense.to(device=self.device, dtype=torch.float32).contiguous()
         if tuple(d.shape) != (self.B, self.C, self.H, self.W):
             raise _lib.B200CAError(f"state shape {tuple(d.shape)} != {(self.B, self.C, self.H, self.W)}")
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.call("b200ca_frame_load", _lib.ptr(d), _lib.ptr(self.buf), self.B, self.C, self.H, self.W,
                       1 if self.wrap_rows else 0, self._stream())
         self._view = None
@@ -80,7 +80,7 @@ class FramedState:
     def refresh_if_edited(self):
         """Re-derives the frame when the interior view was mutated in place since the last step."""
         if self._view is not None and self._view._version != self._view_version:
-            with torch.cuda.device(self.device):
+            with _lib.device_guard(self.device):
                 _lib.call("b200ca_frame_refresh", _lib.ptr(self.buf), self.B, self.C, self.H, self.W,
                           1 if self.wrap_rows else 0, self._stream())
             self._view_version = self._view._version
@@ -90,7 +90,7 @@ class FramedState:
 
     def mass(self) -> torch.Tensor:
         out = torch.zeros((self.B, self.C), dtype=torch.float64, device=self.device)
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.call("b200ca_frame_mass", _lib.ptr(self.buf), _lib.ptr(out), self.B, self.C, self.H, self.W, self._stream())
         return out
 
@@ -196,7 +196,7 @@ class Lenia(Automaton):
         L = _lib.lib()
         n = L.b200ca_lenia_kprep_elems(self.batch, self.C, self.k_mult)
         self._kprep = torch.empty(n, dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.call("b200ca_lenia_prepare_kernel", _lib.ptr(self.k), _lib.ptr(self._kprep), self.batch, self.C, self.k_mult,
                       int(self.k_size), _lib.current_stream(self.device))
         # FFT path (optional): prepared kernel spectra + row-spectra workspace
@@ -208,7 +208,7 @@ class Lenia(Automaton):
         if self.use_fft:
             self._kfft = torch.empty(L.b200ca_lenia_fft_kernel_elems(self.batch, self.C, self.k_mult, self.h, self.w),
                                      dtype=torch.float32, device=self.device)
-            with torch.cuda.device(self.device):
+            with _lib.device_guard(self.device):
                 _lib.call("b200ca_lenia_fft_prepare_kernel", _lib.ptr(self.k), _lib.ptr(self._kfft), self.batch, self.C, self.k_mult,
                           int(self.k_size), self.h, self.w, _lib.current_stream(self.device))
             self._fft_ws = torch.empty(L.b200ca_lenia_fft_workspace_elems(self.batch, self.C, self.k_mult, self.h, self.w),
@@ -217,7 +217,7 @@ class Lenia(Automaton):
     # ---- hot path ---------------------------------------------------------------------------------
     def _conv(self, dst: torch.Tensor, mode: int):
         fs = self._fs
-        with torch.cuda.device(fs.device):
+        with _lib.device_guard(fs.device):
             if self.use_fft:
                 _lib.call("b200ca_lenia_step_fft", _lib.ptr(fs.buf), _lib.ptr(dst), _lib.ptr(self._kfft), _lib.ptr(self.mu),
                           _lib.ptr(self.sigma), _lib.ptr(self.weights), _lib.ptr(self._fft_ws), fs.B, fs.C, self.k_mult, fs.H, fs.W,
@@ -296,7 +296,7 @@ class MaCELenia(Lenia):
     def _mace_step(self, alpha_on=False, alpha=0.0):
         fs = self._fs
         self._compute_affinity()
-        with torch.cuda.device(fs.device):
+        with _lib.device_guard(fs.device):
             _lib.call("b200ca_mace_redistribute", _lib.ptr(fs.buf), _lib.ptr(self._aff), _lib.ptr(fs.other), fs.B, fs.C, fs.H,
                       fs.W, float(self.b), 1 if alpha_on else 0, float(alpha), 1, _lib.current_stream(fs.device))
         fs.swap()

@@ -36,7 +36,7 @@ class NCAWeights:
             raise _lib.B200CAError(f"NCA with n_states={self.n_states}, n_hidden={self.n_hidden} is not built (only 16/128)")
         self.W1, self.b1, self.W2, self.b2 = [t.detach().to(self.device, torch.float32).contiguous() for t in (W1, b1, W2, b2)]
         self.prep = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.call("b200ca_nca_prepare_weights", _lib.ptr(self.W1), _lib.ptr(self.b1), _lib.ptr(self.W2), _lib.ptr(self.b2),
                       _lib.ptr(self.prep), self.n_states, self.n_hidden, _lib.current_stream(self.device))
 
@@ -61,7 +61,7 @@ def nca_step(state: torch.Tensor, weights: NCAWeights, out: torch.Tensor = None,
     m = None
     if update_mask is not None:
         m = update_mask.to(device=state.device).reshape(B, H, W).to(torch.uint8).contiguous()
-    with torch.cuda.device(state.device):
+    with _lib.device_guard(state.device):
         _lib.call("b200ca_nca_step", _lib.ptr(state), _lib.ptr(out), _lib.ptr(weights.prep), _lib.ptr(m), seed, step_index,
                   _lib.ptr(scratch), B, n, weights.n_hidden, H, W, impl, _lib.current_stream(state.device))
     return out
