@@ -301,6 +301,97 @@ __global__ void __launch_bounds__(128, 6) gol_fast_kernel(const uint32_t *__rest
     }
 }
 
+// ---- small worlds: the whole torus lives in shared memory, nsteps generations per launch ---------------------------
+// A 250x250 world (simulate.py's default, BASELINE configs[0]) is 2000 words: a launch per generation is pure launch
+// latency (~5-10 us for ~0.1 us of work).  One CTA keeps both ping-pong copies in shared memory, runs all the
+// generations with a __syncthreads() between them and writes the result once.  Any width (partial last word) and
+// both vertical modes; used by b200ca_gol_run when H * words_per_row <= GOL_SMALL_WORDS (beyond that one SM is
+// slower than a launch per generation on 148 SMs).
+constexpr int GOL_SMALL_THREADS = 1024;
+constexpr int GOL_SMALL_WPT = 4;                                   // words per thread
+constexpr int GOL_SMALL_WORDS = GOL_SMALL_THREADS * GOL_SMALL_WPT;  // 4096 words = 131072 cells
+
+// Word j (j in [-1, wpr]) of a row as far as a 1-cell horizontal shift needs it: the wrap of a row whose last word is
+// partial (nb valid bits) is the last word moved up so cell W-1 sits in bit 31 (west of cell 0), resp. cell 0 injected
+// after cell W-1 (east of cell W-1).  Branch-light replacement of the generic bit gather.
+__device__ __forceinline__ uint32_t gol_fetch_any(const uint32_t *row, const GolGeom &g, int nb, int j) {
+    if (j >= 0 && j < g.wpr - 1) return row[j];
+    if (j == g.wpr - 1) return g.aligned ? row[j] : (row[j] | (row[0] << nb));
+    if (j < 0) return g.aligned ? row[g.wpr - 1] : (row[g.wpr - 1] << (32 - nb));
+    return g.aligned ? row[0] : 0u;
+}
+
+// 2-bit sum west+centre+east of word j of `row` (zeros when the row is outside an open world)
+__device__ __forceinline__ void gol_row_sum(const uint32_t *row, uint32_t live_mask, const GolGeom &g, int nb, int j, uint32_t &c,
+                                            uint32_t &s0, uint32_t &s1) {
+    const uint32_t C = gol_fetch_any(row, g, nb, j) & live_mask;
+    const uint32_t L = gol_fetch_any(row, g, nb, j - 1) & live_mask;
+    const uint32_t Rw = gol_fetch_any(row, g, nb, j + 1) & live_mask;
+    const uint32_t w = __funnelshift_l(L, C, 1), e = __funnelshift_r(C, Rw, 1);
+    c = C;
+    s0 = w ^ e ^ C;
+    s1 = (w & e) | (C & (w ^ e));
+}
+
+template <bool LIFE>
+__global__ void __launch_bounds__(GOL_SMALL_THREADS) gol_small_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, GolGeom g,
+                                                                        uint32_t s_mask, uint32_t b_mask, int nsteps) {
+    extern __shared__ uint32_t gsm[];
+    const int total = g.H * g.wpr;
+    const int nb = g.W - 32 * (g.wpr - 1);
+    uint32_t *cur = gsm, *nxt = gsm + total;
+    RuleMasks rm;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        rm.s[k] = ((s_mask >> k) & 1u) ? 0xffffffffu : 0u;
+        rm.b[k] = ((b_mask >> k) & 1u) ? 0xffffffffu : 0u;
+    }
+    // this thread's words and their row neighbourhood, fixed for all generations
+    int off_a[GOL_SMALL_WPT], off_q[GOL_SMALL_WPT], off_b[GOL_SMALL_WPT], jj[GOL_SMALL_WPT];
+    uint32_t ma[GOL_SMALL_WPT], mb[GOL_SMALL_WPT];
+#pragma unroll
+    for (int k = 0; k < GOL_SMALL_WPT; ++k) {
+        const int i = threadIdx.x + k * GOL_SMALL_THREADS;
+        const int r = i < total ? i / g.wpr : 0;
+        jj[k] = i < total ? i - r * g.wpr : -100;  // -100: no word
+        int ra = r - 1, rb = r + 1;
+        ma[k] = mb[k] = 0xffffffffu;
+        if (g.vert_open) {
+            if (ra < 0) { ra = 0; ma[k] = 0u; }
+            if (rb >= g.H) { rb = g.H - 1; mb[k] = 0u; }
+        } else {
+            ra = ra < 0 ? g.H - 1 : ra;
+            rb = rb >= g.H ? 0 : rb;
+        }
+        off_a[k] = ra * g.wpr;
+        off_q[k] = r * g.wpr;
+        off_b[k] = rb * g.wpr;
+        if (i < total) cur[i] = in[(size_t)r * g.stride + jj[k]];
+    }
+    __syncthreads();
+    for (int step = 0; step < nsteps; ++step) {
+#pragma unroll
+        for (int k = 0; k < GOL_SMALL_WPT; ++k) {
+            if (jj[k] < 0) continue;
+            const int j = jj[k];
+            uint32_t ca, a0, a1, cq, q0, q1, cb, b0, b1;
+            gol_row_sum(cur + off_a[k], ma[k], g, nb, j, ca, a0, a1);
+            gol_row_sum(cur + off_q[k], 0xffffffffu, g, nb, j, cq, q0, q1);
+            gol_row_sum(cur + off_b[k], mb[k], g, nb, j, cb, b0, b1);
+            uint32_t o = gol_rule9<LIFE>(a0, a1, q0, q1, b0, b1, cq, rm);
+            if (j == g.wpr - 1) o &= g.last_mask;
+            nxt[off_q[k] + j] = o;
+        }
+        __syncthreads();
+        uint32_t *t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+#pragma unroll
+    for (int k = 0; k < GOL_SMALL_WPT; ++k)
+        if (jj[k] >= 0) out[(size_t)(off_q[k] / g.wpr) * g.stride + jj[k]] = cur[off_q[k] + jj[k]];
+}
+
 // ---- pack / unpack / population / random fill ---------------------------------------------------
 template <typename T>
 __global__ void gol_pack_kernel(const T *__restrict__ world, uint32_t *__restrict__ bits, int H, int W, int stride, int wpr) {
@@ -492,6 +583,30 @@ extern "C" int b200ca_gol_step(const uint32_t *bits_in, uint32_t *bits_out, int 
 extern "C" int b200ca_gol_run(uint32_t *a, uint32_t *b, int H, int W, int stride_words, uint32_t s_mask, uint32_t b_mask,
                               int vert_open, int nsteps, void *stream) {
     B200CA_REQUIRE(nsteps >= 0, "gol_run: nsteps < 0");
+    {
+        // small worlds: all generations in one launch, world resident in shared memory; result lands where the
+        // ping-pong contract says (a for even nsteps, b for odd)
+        GolGeom g;
+        int rc = make_geom(g, H, W, stride_words, vert_open);
+        if (rc) return rc;
+        if (nsteps >= 2 && (long long)H * g.wpr <= GOL_SMALL_WORDS) {
+            B200CA_REQUIRE(a && b && a != b, "gol_run: null or aliased buffers");
+            B200CA_REQUIRE(s_mask < 512 && b_mask < 512, "gol_run: rule masks are 9-bit");
+            const size_t smem = (size_t)2 * H * g.wpr * sizeof(uint32_t);
+            const bool life = (s_mask == 0b1100u && b_mask == 0b1000u);
+            uint32_t *dst = (nsteps & 1) ? b : a;
+            cudaStream_t st = as_stream(stream);
+            if (life) {
+                if (smem > 48 * 1024) B200CA_CUDA(cudaFuncSetAttribute(gol_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                gol_small_kernel<true><<<1, GOL_SMALL_THREADS, smem, st>>>(a, dst, g, s_mask, b_mask, nsteps);
+            } else {
+                if (smem > 48 * 1024) B200CA_CUDA(cudaFuncSetAttribute(gol_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                gol_small_kernel<false><<<1, GOL_SMALL_THREADS, smem, st>>>(a, dst, g, s_mask, b_mask, nsteps);
+            }
+            B200CA_LAUNCH_CHECK("gol_small_kernel");
+            return 0;
+        }
+    }
     uint32_t *src = a, *dst = b;
     for (int i = 0; i < nsteps; ++i) {
         int rc = gol_step_impl(src, dst, H, W, stride_words, s_mask, b_mask, vert_open, as_stream(stream));

@@ -155,3 +155,29 @@ def test_host_entry_point():
     _lib.call("b200ca_gol_run_host", w0.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), 77, 131, 0b1100,
               0b1000, 9)
     assert np.array_equal(out, orc.gol_run(w0, 9))
+
+
+@pytest.mark.parametrize("shape", [(250, 250), (1, 1), (5, 31), (64, 64), (100, 257), (300, 1024), (37, 1000)])
+def test_small_world_multi_generation_kernel(shape):
+    """b200ca_gol_run with nsteps >= 2 on a world that fits in shared memory: all generations in one launch."""
+    import pyca_b200
+
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    w0 = (rng.random(shape) < 0.4).astype(np.int32)
+    for (s, b, steps) in [(0b1100, 0b1000, 7), (0b1100, 0b1000, 16), (int(rng.integers(0, 512)), int(rng.integers(0, 512)), 5)]:
+        pw = pyca_b200.PackedWorld(shape[0], shape[1], "cuda")
+        pw.pack_from(torch.from_numpy(w0).cuda())
+        pw.step(s, b, steps)
+        assert np.array_equal(pw.unpack().cpu().numpy(), orc.gol_run(w0, steps, s, b)), f"{shape} S={s:b} B={b:b} x{steps}"
+    # open-rows mode, 3 generations == oracle on a world padded with enough dead rows
+    pw = pyca_b200.PackedWorld(shape[0], shape[1], "cuda")
+    pw.pack_from(torch.from_numpy(w0).cuda())
+    pw.step(0b1100, 0b1000, 2, vert_open=True)
+    got = pw.unpack().cpu().numpy()
+    pad = np.zeros((shape[0] + 2, shape[1]), dtype=np.int32)
+    pad[1:-1] = w0
+    one = orc.gol_step(pad)
+    one[0] = 0
+    one[-1] = 0   # rows outside stay dead in open mode
+    two = orc.gol_step(one)[1:-1]
+    assert np.array_equal(got, two)
