@@ -154,6 +154,8 @@ class LeniaWL(Workload):
         self.H, self.W, self.C, self.name = H, W, C, name
         # replicas: one independent world per GPU (no communication, weak scaling); else one world in row slabs
         self.replicas = replicas and world > 1
+        self.slab = None
+        self.auto = None
         if self.replicas:
             self.scaling = "weak"
 
@@ -192,7 +194,13 @@ class LeniaWL(Workload):
         return self.H * self.W * (self.world if self.replicas else 1)
 
     def _fft(self):
-        return self.slab is None and getattr(self, "auto", None) is not None and self.auto.use_fft
+        if self.slab is not None:
+            return self.slab.use_fft
+        if self.auto is not None:
+            return self.auto.use_fft
+        import pyca_b200  # (reference arm on CPU: say which path the CUDA arm would take for this shape)
+
+        return pyca_b200.lib().b200ca_lenia_fft_length(self.H, self.W) > 0
 
     def launches_per_step(self):
         if self.slab is not None:
