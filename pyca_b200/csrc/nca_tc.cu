@@ -16,8 +16,10 @@
 //   mbarrier -> tcgen05.ld of the thread's own accumulator row -> bias/ReLU/split -> A operand of GEMM 2, fed in
 //   16-column chunks so the second GEMM's MMAs trail the epilogue of the first -> sigmoid, masks, coalesced NCHW
 //   stores + the two bit planes for the life-mask pass.
-// CTAs are persistent (grid = 2 x SMs, weights staged in shared memory once) and two CTAs share an SM so one
-// tile's CUDA-core phases overlap the other's tensor phases.  256 TMEM columns per CTA.
+// A CTA holds NG = 4 independent 128-thread groups (16 warps per SM) that share ONE copy of the weight images in shared
+// memory; each group walks its own tiles with its own A buffers, mbarriers, named barrier and 128 TMEM columns (D2
+// reuses D1's first 16 columns, which the first epilogue chunk has drained before the first GEMM-2 MMA is issued), so
+// the CUDA-core phases of three groups overlap the tensor phases of the fourth.  CTAs are persistent (grid = #SMs).
 #include <stdlib.h>
 
 #include <algorithm>
@@ -49,13 +51,15 @@ constexpr int SM_A1LO = SM_A1HI + 20 * 1024;
 // after the last GEMM-2 commits (bar2)
 constexpr int SM_A2 = SM_A1HI;            // buffer b at SM_A2 + b * 16 KB: hi then lo
 constexpr int A2_BUF = 16 * 1024;
-constexpr int SM_BAR = SM_A1LO + 20 * 1024;               // mbarriers + tmem address
-constexpr int SM_TOTAL = SM_BAR + 64;                     // 97 KB + 64 -> two CTAs per SM (<= 113 KB each)
-static_assert(2 * (SM_TOTAL + 1024) <= 227 * 1024, "two CTAs must fit in one SM");
+constexpr int NG = 4;                                     // 128-thread groups per CTA
+constexpr int SM_GROUP = 40 * 1024;                       // per-group A region (A1hi + A1lo; A2 buffers alias it)
+constexpr int SM_BAR = SM_A1HI + NG * SM_GROUP;           // mbarriers (3 per group) + tmem address
+constexpr int SM_TOTAL = SM_BAR + 128;                    // 217 KB + 128: one CTA per SM
+static_assert(SM_TOTAL + 1024 <= 227 * 1024, "CTA must fit in one SM");
 static_assert(TC_WBYTES <= SM_A1HI, "weights overflow their smem region");
 
-constexpr int TMEM_COLS = 256;  // D1: columns [0,128), D2: [128,144)
-constexpr int D2_COL = 128;
+constexpr int TMEM_COLS = 512;  // 128 columns per group: D1 = [0,128), D2 = [0,16) once the first chunk is drained
+constexpr int D2_COL = 0;
 constexpr int H2CHUNK = 16;     // hidden columns per GEMM-2 chunk (two K=8 steps)
 
 // tf32 split: hi = x rounded to 10 explicit mantissa bits (low 13 bits zero, so the tensor core's truncation is exact);
@@ -114,19 +118,24 @@ __device__ __forceinline__ float sigmoid_rn(float x) {
     return r;
 }
 
-__global__ void __launch_bounds__(128, 2) nca_update_tc_kernel(const NcaArgs a, int tiles_x, int tiles_y) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float *sw = reinterpret_cast<float *>(smem + SM_W);
-    uint64_t *bar1 = reinterpret_cast<uint64_t *>(smem + SM_BAR);      // GEMM 1 done
-    uint64_t *bar2 = bar1 + 1;                                         // bar2[b]: GEMM 2 chunk using A2 buffer b done
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar1 + 3);
+__device__ __forceinline__ void group_sync(int gid) { asm volatile("bar.sync %0, 128;" ::"r"(gid + 1) : "memory"); }
+
+__global__ void __launch_bounds__(128 * NG, 1) nca_update_tc_kernel(const NcaArgs a, int tiles_x, int tiles_y) {
+    extern __shared__ __align__(1024) unsigned char smem_all[];
+    const int gid = threadIdx.x >> 7;           // group of this thread
+    const int tid = threadIdx.x & 127;          // thread within the group = tile row = TMEM lane
+    const int lane = tid & 31, warp = tid >> 5;
+    unsigned char *smem = smem_all + gid * SM_GROUP;  // group view: the SM_A* offsets below land in this group's region
+    float *sw = reinterpret_cast<float *>(smem_all + SM_W);
+    uint64_t *bar1 = reinterpret_cast<uint64_t *>(smem_all + SM_BAR) + 3 * gid;  // GEMM 1 done
+    uint64_t *bar2 = bar1 + 1;                                                   // bar2[b]: GEMM 2 chunk using A2 buffer b done
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_all + SM_BAR + 3 * NG * 8);
 
     // ---- one-time setup: weights -> smem, barriers, TMEM
     {
         const float4 *src = reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(a.wp) + WP_TC_OFF);
         float4 *dst = reinterpret_cast<float4 *>(sw);
-        for (int t = tid; t < TC_WBYTES / 16; t += 128) dst[t] = __ldg(src + t);
+        for (int t = threadIdx.x; t < TC_WBYTES / 16; t += 128 * NG) dst[t] = __ldg(src + t);
     }
     if (tid == 0) {
         mbar_init(bar1, 1);
@@ -134,7 +143,7 @@ __global__ void __launch_bounds__(128, 2) nca_update_tc_kernel(const NcaArgs a, 
         mbar_init(bar2 + 1, 1);
         mbar_fence_init();
     }
-    if (warp == 0) {
+    if (threadIdx.x < 32) {
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -143,13 +152,13 @@ __global__ void __launch_bounds__(128, 2) nca_update_tc_kernel(const NcaArgs a, 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = *tmem_slot + gid * 128;                   // this group's 128 columns
     const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
 
     const uint32_t sA1hi = smem_u32(smem + SM_A1HI), sA1lo = smem_u32(smem + SM_A1LO);
     const uint32_t sA2 = smem_u32(smem + SM_A2);
-    const uint32_t sB1hi = smem_u32(smem + SM_W + TC_B1HI), sB1lo = smem_u32(smem + SM_W + TC_B1LO);
-    const uint32_t sB2hi = smem_u32(smem + SM_W + TC_B2HI), sB2lo = smem_u32(smem + SM_W + TC_B2LO);
+    const uint32_t sB1hi = smem_u32(smem_all + SM_W + TC_B1HI), sB1lo = smem_u32(smem_all + SM_W + TC_B1LO);
+    const uint32_t sB2hi = smem_u32(smem_all + SM_W + TC_B2HI), sB2lo = smem_u32(smem_all + SM_W + TC_B2LO);
     const float *bias2 = sw + TC_BIAS2 / 4;
     // descriptor strides: A operands [chunk][128 rows][16 B], B1 [chunk][128 n][16 B], B2 [chunk][16 n][16 B]
     constexpr uint32_t lboA = 128 * 16, lboB1 = 128 * 16, lboB2 = 16 * 16, sboA = 128, sboB1 = 128, sboB2 = 128;
@@ -159,7 +168,7 @@ __global__ void __launch_bounds__(128, 2) nca_update_tc_kernel(const NcaArgs a, 
     const int ntiles = tiles_x * tiles_y * a.B;
     uint32_t ph1 = 0, ph2[2] = {0, 0};
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x * NG + gid; tile < ntiles; tile += gridDim.x * NG) {
         const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
         const int x = tx * 32 + lane, y = ty * 4 + warp;
         const bool valid = x < a.W && y < a.H;
@@ -220,7 +229,7 @@ __global__ void __launch_bounds__(128, 2) nca_update_tc_kernel(const NcaArgs a, 
         }
         fence_proxy_async();
         tc_fence_before();
-        __syncthreads();
+        group_sync(gid);
 
         // ---- GEMM 1: D1 = [P | 1 | 0] * [W1f | b1 | 0]^T, K = 40 = 5 k-steps x (hi*hi + hi*lo + lo*hi)
         if (tid == 0) {
@@ -262,7 +271,7 @@ __global__ void __launch_bounds__(128, 2) nca_update_tc_kernel(const NcaArgs a, 
             }
             fence_proxy_async();
             tc_fence_before();
-            __syncthreads();
+            group_sync(gid);
             if (tid == 0) {
                 tc_fence_after();
                 const uint32_t sA2hi = sA2 + bsel * A2_BUF, sA2lo = sA2hi + A2_BUF / 2;
@@ -309,13 +318,14 @@ __global__ void __launch_bounds__(128, 2) nca_update_tc_kernel(const NcaArgs a, 
         }
         // all TMEM reads of this tile are done before the next tile's MMAs overwrite D1/D2
         tc_fence_before();
-        __syncthreads();
+        group_sync(gid);
     }
 
-    if (warp == 0) {
+    __syncthreads();
+    if (threadIdx.x < 32) {
         __syncwarp();
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -363,8 +373,8 @@ int nca_step_tc(const NcaArgs &a, cudaStream_t st) {
     }
     const int tiles_x = ceil_div(a.W, 32), tiles_y = ceil_div(a.H, 4);
     const long long ntiles = (long long)tiles_x * tiles_y * a.B;
-    const int grid = (int)std::min<long long>(ntiles, 2LL * num_sms());
-    nca_update_tc_kernel<<<grid, 128, SM_TOTAL, st>>>(a, tiles_x, tiles_y);
+    const int grid = (int)std::min<long long>(ceil_div64(ntiles, NG), (long long)num_sms());
+    nca_update_tc_kernel<<<grid, 128 * NG, SM_TOTAL, st>>>(a, tiles_x, tiles_y);
     B200CA_LAUNCH_CHECK("nca_update_tc_kernel");
     return 0;
 }
