@@ -71,6 +71,30 @@ __device__ __forceinline__ void dit4_inv(float2 &a, float2 &b, float2 &c, float2
     d = csub(t1, t3);
 }
 
+// Programmatic dependent launch: the three kernels of a step (and consecutive steps) are chained on one stream.
+// Each kernel does its input-independent prologue, then waits for the previous grid (griddepcontrol.wait) and
+// immediately lets the next grid start ITS prologue (griddepcontrol.launch_dependents), which takes the launch
+// latency off the critical path of small worlds.
+__device__ __forceinline__ void pdl_wait_then_release() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename Kern, typename... Args>
+static cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // shared-memory index swizzle for float2 arrays: keeps the radix-4 stages with span 4 and 1 (and the linear
 // passes) free of bank conflicts.  Only the low 4 bits change, so 16-element aligned blocks stay blocks.
 __device__ __forceinline__ int swz(int i) { return i ^ (5 * ((i >> 4) & 3)); }
@@ -110,6 +134,7 @@ __global__ void __launch_bounds__(N / 4) lenia_fft_rows_kernel(const float *__re
             sp >>= 2;
         }
     }
+    pdl_wait_then_release();  // the state is the previous step's output
     // first stage straight from global memory (span = N/4, k = tid)
     {
         const float2 w1 = tw1[0], w2 = tw2[0], w3 = tw3[0];
@@ -198,6 +223,7 @@ __global__ void __launch_bounds__(FIR_THREADS) lenia_fft_fir_kernel(const FftFir
         const float w = __ldg(kf + dy * N);
         kt[dy] = make_float2(w, w);
     }
+    pdl_wait_then_release();  // taps are static; the spectra come from the row-FFT kernel
     const size_t zstride = (size_t)a.g.nseg * N;
     const float2 *zp = a.Z + ((size_t)src_plane * a.g.zrows * a.g.nseg + seg) * N + k;
     float2 acc[FT];
@@ -266,6 +292,7 @@ __global__ void __launch_bounds__(N / 4, (FFT_RPC == 1 && N == 1024) ? 4 : 1) le
 #pragma unroll
         for (int r = 0; r < 4; ++r) dx[q][r] = sv[q][r] = make_float2(0.f, 0.f);
     const size_t plane_off = (size_t)(b * a.C + j) * (a.H + 2 * F) * a.pitch;
+    pdl_wait_then_release();  // filtered spectra come from the FIR kernel
     for (int i = 0; i < a.NS; ++i) {
         const int pidx = (b * a.NS + i) * a.C + j;
         if (i > 0) __syncthreads();  // previous source done with the buffers
@@ -536,13 +563,13 @@ extern "C" int b200ca_lenia_step_fft(const float *state_in, float *state_out, co
         const size_t smem = (size_t)rpc_rows * g.N * sizeof(float2);
         dim3 grid(ceil_div(g.zrows, rpc_rows), g.nseg, B * C);
         if (g.N == 1024) {
-            if (rpc_rows == 1) lenia_fft_rows_kernel<1, 1024><<<grid, 256, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
-            else if (rpc_rows == 2) lenia_fft_rows_kernel<2, 1024><<<grid, 256, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
-            else lenia_fft_rows_kernel<4, 1024><<<grid, 256, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
+            if (rpc_rows == 1) B200CA_CUDA(launch_pdl(lenia_fft_rows_kernel<1, 1024>, grid, dim3(256), smem, st, state_in, Z, tw, g, H, W, pitch));
+            else if (rpc_rows == 2) B200CA_CUDA(launch_pdl(lenia_fft_rows_kernel<2, 1024>, grid, dim3(256), smem, st, state_in, Z, tw, g, H, W, pitch));
+            else B200CA_CUDA(launch_pdl(lenia_fft_rows_kernel<4, 1024>, grid, dim3(256), smem, st, state_in, Z, tw, g, H, W, pitch));
         } else {
-            if (rpc_rows == 1) lenia_fft_rows_kernel<1, 256><<<grid, 64, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
-            else if (rpc_rows == 2) lenia_fft_rows_kernel<2, 256><<<grid, 64, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
-            else lenia_fft_rows_kernel<4, 256><<<grid, 64, smem, st>>>(state_in, Z, tw, g, H, W, pitch);
+            if (rpc_rows == 1) B200CA_CUDA(launch_pdl(lenia_fft_rows_kernel<1, 256>, grid, dim3(64), smem, st, state_in, Z, tw, g, H, W, pitch));
+            else if (rpc_rows == 2) B200CA_CUDA(launch_pdl(lenia_fft_rows_kernel<2, 256>, grid, dim3(64), smem, st, state_in, Z, tw, g, H, W, pitch));
+            else B200CA_CUDA(launch_pdl(lenia_fft_rows_kernel<4, 256>, grid, dim3(64), smem, st, state_in, Z, tw, g, H, W, pitch));
         }
         B200CA_LAUNCH_CHECK("lenia_fft_rows_kernel");
     }
@@ -560,10 +587,10 @@ extern "C" int b200ca_lenia_step_fft(const float *state_in, float *state_out, co
         const long long ctas32 = (long long)(g.N / FIR_THREADS) * g.nseg * ceil_div(g.D, 32) * B * NS * C;
         if (ctas32 >= (long long)num_sms() * 16) {
             dim3 grid((g.N / FIR_THREADS) * g.nseg, ceil_div(g.D, 32), B * NS * C);
-            lenia_fft_fir_kernel<32><<<grid, FIR_THREADS, 0, st>>>(a);
+            B200CA_CUDA(launch_pdl(lenia_fft_fir_kernel<32>, grid, dim3(FIR_THREADS), 0, st, a));
         } else {
             dim3 grid((g.N / FIR_THREADS) * g.nseg, ceil_div(g.D, 8), B * NS * C);
-            lenia_fft_fir_kernel<8><<<grid, FIR_THREADS, 0, st>>>(a);
+            B200CA_CUDA(launch_pdl(lenia_fft_fir_kernel<8>, grid, dim3(FIR_THREADS), 0, st, a));
         }
         B200CA_LAUNCH_CHECK("lenia_fft_fir_kernel");
     }
@@ -589,13 +616,13 @@ extern "C" int b200ca_lenia_step_fft(const float *state_in, float *state_out, co
         const size_t smem = (size_t)rpc_inv * g.N * sizeof(float2);
         dim3 grid(ceil_div(g.D, rpc_inv), g.nseg, B * C);
         if (g.N == 1024) {
-            if (rpc_inv == 1) lenia_fft_inv_kernel<1, 1024><<<grid, 256, smem, st>>>(a);
-            else if (rpc_inv == 2) lenia_fft_inv_kernel<2, 1024><<<grid, 256, smem, st>>>(a);
-            else lenia_fft_inv_kernel<4, 1024><<<grid, 256, smem, st>>>(a);
+            if (rpc_inv == 1) B200CA_CUDA(launch_pdl(lenia_fft_inv_kernel<1, 1024>, grid, dim3(256), smem, st, a));
+            else if (rpc_inv == 2) B200CA_CUDA(launch_pdl(lenia_fft_inv_kernel<2, 1024>, grid, dim3(256), smem, st, a));
+            else B200CA_CUDA(launch_pdl(lenia_fft_inv_kernel<4, 1024>, grid, dim3(256), smem, st, a));
         } else {
-            if (rpc_inv == 1) lenia_fft_inv_kernel<1, 256><<<grid, 64, smem, st>>>(a);
-            else if (rpc_inv == 2) lenia_fft_inv_kernel<2, 256><<<grid, 64, smem, st>>>(a);
-            else lenia_fft_inv_kernel<4, 256><<<grid, 64, smem, st>>>(a);
+            if (rpc_inv == 1) B200CA_CUDA(launch_pdl(lenia_fft_inv_kernel<1, 256>, grid, dim3(64), smem, st, a));
+            else if (rpc_inv == 2) B200CA_CUDA(launch_pdl(lenia_fft_inv_kernel<2, 256>, grid, dim3(64), smem, st, a));
+            else B200CA_CUDA(launch_pdl(lenia_fft_inv_kernel<4, 256>, grid, dim3(64), smem, st, a));
         }
         B200CA_LAUNCH_CHECK("lenia_fft_inv_kernel");
     }
