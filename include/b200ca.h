@@ -129,6 +129,12 @@ int b200ca_lenia_fft_prepare_kernel(const float *K, float *Kfft, int B, int C, i
 int b200ca_lenia_step_fft(const float *state_in, float *state_out, const float *Kfft, const float *mu, const float *sigma,
                           const float *weights, float *workspace, int B, int C, int k_mult, int H, int W, float dt, int mode,
                           int row_wrap, void *stream);
+/* The same step in two parts, for a row slab that overlaps its halo exchange with compute: phase 1 = row FFTs of the
+ * spectra rows built from owned rows only (needs no ghost rows), phase 2 = the remaining 30 row FFTs + FIR + inverse
+ * (after the ghost rows arrived); phase 0 = everything (what b200ca_lenia_step_fft does). */
+int b200ca_lenia_step_fft_phase(const float *state_in, float *state_out, const float *Kfft, const float *mu, const float *sigma,
+                                const float *weights, float *workspace, int B, int C, int k_mult, int H, int W, float dt,
+                                int mode, int row_wrap, int phase, void *stream);
 
 /* Mass-conserving redistribution (+ optional cross-channel mixing).  Replaces
  * MaCELenia._mace_step (macelenia.py:89-120) after the affinity, and

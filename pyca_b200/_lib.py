@@ -42,6 +42,8 @@ SIGNATURES = {
     "b200ca_lenia_fft_prepare_kernel": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200ca_lenia_step_fft": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_int, c_int, c_float, c_int, c_int, c_void_p]),
+    "b200ca_lenia_step_fft_phase": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                            c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p]),
     "b200ca_mace_redistribute": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_float,
                                          c_int, c_void_p]),
     "b200ca_frame_mass": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -38,6 +38,8 @@ struct FftGeom {
     int periodic;      // W == N: exact circular convolution, no halo in x
     int D;             // H / 2 (row pairing distance)
     int zrows;         // D + 2R spectra rows per plane
+    // sub-range of spectra rows one row-FFT launch covers: zr = zr_begin + i (+ zr_gap once i >= zr_gap_at), i < zr_count
+    int zr_begin, zr_count, zr_gap_at, zr_gap;
 };
 
 // complex helpers on float2
@@ -122,7 +124,10 @@ __global__ void __launch_bounds__(N / 4) lenia_fft_rows_kernel(const float *__re
     const int xoff = g.periodic ? F : seg * g.V - R + F;  // framed column of sample n = 0
     int zr[FFT_RPC];
 #pragma unroll
-    for (int q = 0; q < FFT_RPC; ++q) zr[q] = min((int)blockIdx.x * FFT_RPC + q, g.zrows - 1);
+    for (int q = 0; q < FFT_RPC; ++q) {
+        const int i = min((int)blockIdx.x * FFT_RPC + q, g.zr_count - 1);
+        zr[q] = g.zr_begin + i + (i >= g.zr_gap_at ? g.zr_gap : 0);
+    }
     // twiddles of every stage are fetched up front so their latency overlaps the first global loads instead of sitting
     // on the critical path of each stage (stage s: span = T >> 2s; the last stage, span 1, needs none)
     float2 tw1[5], tw2[5], tw3[5];
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(N / 4) lenia_fft_rows_kernel(const float *__re
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < FFT_RPC; ++q) {
-        if ((int)blockIdx.x * FFT_RPC + q >= g.zrows) break;
+        if ((int)blockIdx.x * FFT_RPC + q >= g.zr_count) break;
         const float2 *buf = fsm + q * N;
         const int i0 = tid << 2;
         float2 a = buf[swz(i0)], b = buf[swz(i0 + 1)], c = buf[swz(i0 + 2)], d = buf[swz(i0 + 3)];
@@ -458,6 +463,10 @@ static int fft_geom(FftGeom &g, int H, int W) {
         g.nseg = ceil_div(W, g.V);
     }
     g.logN4 = g.N == 256 ? 4 : (g.N == 1024 ? 5 : 6);
+    g.zr_begin = 0;
+    g.zr_count = g.zrows;
+    g.zr_gap_at = g.zrows;
+    g.zr_gap = 0;
     return 0;
 }
 
@@ -532,6 +541,14 @@ extern "C" int b200ca_lenia_fft_prepare_kernel(const float *K, float *Kfft, int 
 extern "C" int b200ca_lenia_step_fft(const float *state_in, float *state_out, const float *Kfft, const float *mu, const float *sigma,
                                      const float *weights, float *workspace, int B, int C, int k_mult, int H, int W, float dt, int mode,
                                      int row_wrap, void *stream) {
+    return b200ca_lenia_step_fft_phase(state_in, state_out, Kfft, mu, sigma, weights, workspace, B, C, k_mult, H, W, dt, mode, row_wrap,
+                                       0, stream);
+}
+
+extern "C" int b200ca_lenia_step_fft_phase(const float *state_in, float *state_out, const float *Kfft, const float *mu,
+                                           const float *sigma, const float *weights, float *workspace, int B, int C, int k_mult, int H,
+                                           int W, float dt, int mode, int row_wrap, int phase, void *stream) {
+    B200CA_REQUIRE(phase >= 0 && phase <= 2, "lenia_step_fft_phase: phase must be 0 (all), 1 (interior row FFTs) or 2 (rest)");
     B200CA_REQUIRE(state_in && state_out && Kfft && mu && sigma && weights && workspace, "lenia_step_fft: null pointer");
     B200CA_REQUIRE(state_in != state_out, "lenia_step_fft: in-place update is not supported");
     B200CA_REQUIRE(mode == B200CA_MODE_LENIA || mode == B200CA_MODE_AFF, "lenia_step_fft: bad mode %d", mode);
@@ -560,8 +577,18 @@ extern "C" int b200ca_lenia_step_fft(const float *state_in, float *state_out, co
         if (rpc_inv != 2 && rpc_inv != 4) rpc_inv = 1;
     }
     if (only == 0 || only == 1) {
+        // phase 1: spectra rows made of owned rows only (zr in [R, D+R)); phase 2: the 2R rows that touch ghost rows
+        if (phase == 1) {
+            g.zr_begin = R;
+            g.zr_count = g.D;
+        } else if (phase == 2) {
+            g.zr_begin = 0;
+            g.zr_count = 2 * R;
+            g.zr_gap_at = R;
+            g.zr_gap = g.D;
+        }
         const size_t smem = (size_t)rpc_rows * g.N * sizeof(float2);
-        dim3 grid(ceil_div(g.zrows, rpc_rows), g.nseg, B * C);
+        dim3 grid(ceil_div(g.zr_count, rpc_rows), g.nseg, B * C);
         if (g.N == 1024) {
             if (rpc_rows == 1) B200CA_CUDA(launch_pdl(lenia_fft_rows_kernel<1, 1024>, grid, dim3(256), smem, st, state_in, Z, tw, g, H, W, pitch));
             else if (rpc_rows == 2) B200CA_CUDA(launch_pdl(lenia_fft_rows_kernel<2, 1024>, grid, dim3(256), smem, st, state_in, Z, tw, g, H, W, pitch));
@@ -573,6 +600,7 @@ extern "C" int b200ca_lenia_step_fft(const float *state_in, float *state_out, co
         }
         B200CA_LAUNCH_CHECK("lenia_fft_rows_kernel");
     }
+    if (phase == 1) return 0;
     if (only == 0 || only == 2) {
         FftFirArgs a;
         a.Z = Z;

@@ -115,9 +115,12 @@ class GolSlab:
         while done < nsteps:
             if self.fresh == 0:
                 self.exchange(group)
-            n = min(self.fresh, nsteps - done)
+            n = nsteps - done
+            if n > self.fresh:
+                n = self.fresh
             out = step_fn(self.bufs[self.cur], self.bufs[self.cur ^ 1], self.rows, n)
-            self.cur = 0 if out is self.bufs[0] else 1
+            if out is not self.bufs[self.cur]:
+                self.cur ^= 1
             self.fresh -= n
             done += n
 
@@ -147,6 +150,8 @@ class LeniaSlab:
 
     def interior(self, t=None) -> torch.Tensor:
         t = self.buf if t is None else t
+        if getattr(self, "_pending_exchange", False) and getattr(self, "comm_stream", None) is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)  # readers see a settled buffer
         return t[:, :, self.F:self.F + self.hl, self.F:self.F + self.W]
 
     def ghost_blocks(self, t: torch.Tensor):
@@ -176,16 +181,23 @@ class GolSlabCUDA(GolSlab):
     """GolSlab whose local generations run through b200ca_gol_run(vert_open=1)."""
 
     def __init__(self, H, W, rank, world, ghost=16, device="cuda", s_mask=0b1100, b_mask=0b1000):
+        from . import _lib
+
         super().__init__(H, W, rank, world, ghost, device)
         self.s_mask, self.b_mask = s_mask, b_mask
         self.device = torch.device(device)
+        self._run = _lib.lib().b200ca_gol_run
+        self._ptrs = [b.data_ptr() for b in self.bufs]
 
     def _step_fn(self, src, dst, rows, n):
+        # hot: a 65536^2 slab generation takes ~20 us on 8 GPUs, so the host side of a launch has to stay well below that
         from . import _lib
 
-        with torch.cuda.device(self.device):
-            _lib.call("b200ca_gol_run", _lib.ptr(src), _lib.ptr(dst), rows, self.W, self.stride, self.s_mask, self.b_mask, 1, n,
-                      _lib.current_stream(self.device))
+        with _lib.device_guard(self.device):
+            rc = self._run(self._ptrs[self.cur], self._ptrs[self.cur ^ 1], rows, self.W, self.stride, self.s_mask, self.b_mask, 1, n,
+                           torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            _lib.check(rc, "b200ca_gol_run")
         return dst if (n & 1) else src
 
     def random_fill(self, seed: int):
@@ -250,9 +262,13 @@ class LeniaSlabCUDA(LeniaSlab):
         self.tile_rows = L.b200ca_lenia_tile_rows(self.hl, W, B, C)
         self.n_tile_rows = (self.hl + self.tile_rows - 1) // self.tile_rows
         self.n_boundary = (self.F + self.tile_rows - 1) // self.tile_rows  # tile rows covering F owned rows
-        self.overlap = overlap and world > 1 and self.n_tile_rows > 2 * self.n_boundary and not self.use_fft
+        if self.use_fft:
+            self.overlap = overlap and world > 1
+        else:
+            self.overlap = overlap and world > 1 and self.n_tile_rows > 2 * self.n_boundary
         self.comm_stream = torch.cuda.Stream(device=self.device) if world > 1 else None
-        self.launches_per_step = 3 if (self.overlap or self.use_fft) else 1
+        self._pending_exchange = False  # FFT path: the ghost rows of `buf` are still in flight on comm_stream
+        self.launches_per_step = (4 if self.overlap else 3) if self.use_fft else (3 if self.overlap else 1)
 
     def set_interior(self, dense: torch.Tensor, group=None):
         """dense: (B,C,hl,W) rows [r0,r1) of the global state."""
@@ -269,9 +285,10 @@ class LeniaSlabCUDA(LeniaSlab):
         from . import _lib
 
         if self.use_fft:
-            _lib.call("b200ca_lenia_step_fft", _lib.ptr(self.buf), _lib.ptr(self.other), _lib.ptr(self._kfft), _lib.ptr(self.mu),
+            # (t0 is the phase here: 0 = whole step, 1 = row FFTs of owned rows, 2 = boundary row FFTs + FIR + inverse)
+            _lib.call("b200ca_lenia_step_fft_phase", _lib.ptr(self.buf), _lib.ptr(self.other), _lib.ptr(self._kfft), _lib.ptr(self.mu),
                       _lib.ptr(self.sigma), _lib.ptr(self.weights), _lib.ptr(self._fft_ws), self.B, self.C, self.k_mult, self.hl,
-                      self.W, float(self.dt), 0, 1 if self.world == 1 else 0, _lib.current_stream(self.device))
+                      self.W, float(self.dt), 0, 1 if self.world == 1 else 0, t0, _lib.current_stream(self.device))
             return
         _lib.call("b200ca_lenia_step", _lib.ptr(self.buf), _lib.ptr(self.other), _lib.ptr(self._kprep), _lib.ptr(self.mu),
                   _lib.ptr(self.sigma), _lib.ptr(self.weights), self.B, self.C, self.k_mult, self.hl, self.W, float(self.dt), 0,
@@ -281,6 +298,17 @@ class LeniaSlabCUDA(LeniaSlab):
         with torch.cuda.device(self.device):
             if self.world == 1:
                 self._launch(0, 0)
+            elif self.use_fft and self.overlap:
+                # the row FFTs of the owned rows run while the previous step's ghost rows are still travelling
+                main = torch.cuda.current_stream(self.device)
+                self._launch(1, 0)
+                if self._pending_exchange:
+                    main.wait_stream(self.comm_stream)
+                self._launch(2, 0)
+                self.comm_stream.wait_stream(main)
+                with torch.cuda.stream(self.comm_stream):
+                    self.exchange(self.other, group)
+                self._pending_exchange = True
             elif not self.overlap:
                 self._launch(0, 0)
                 self.exchange(self.other, group)

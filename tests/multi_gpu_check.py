@@ -47,7 +47,7 @@ def main():
         single = pyca_b200.Lenia((Hh, Ww), num_channels=C, params=dict(dd), state_init=full, device=dev, conv_path="direct")
         for _ in range(3):
             single.step()
-        for overlap, path in ((True, "direct"), (False, "direct"), (False, "fft")):
+        for overlap, path in ((True, "direct"), (False, "direct"), (False, "fft"), (True, "fft")):
             params = pyca_b200.LeniaParams(param_dict=dict(dd), channels=C)
             sl = LeniaSlabCUDA(params, C, Hh, Ww, rank, world, device=dev, overlap=overlap, conv_path=path)
             sl.set_interior(full[:, :, sl.r0:sl.r1].to(dev))
