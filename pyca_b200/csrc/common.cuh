@@ -68,4 +68,30 @@ struct Philox {
     }
 };
 
+
+#ifdef __CUDACC__
+// Programmatic dependent launch (PDL): kernels chained on one stream.  Each kernel does its input-independent prologue,
+// waits for the previous grid (griddepcontrol.wait) and immediately lets the next grid start ITS prologue
+// (griddepcontrol.launch_dependents): the launch latency leaves the critical path of short kernels.
+__device__ __forceinline__ void pdl_wait_then_release() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename Kern, typename... Args>
+static cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+#endif
+
 }  // namespace b200ca

@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(128, 6) gol_fast_kernel(const uint32_t *__rest
             rm.b[k] = ((b_mask >> k) & 1u) ? 0xffffffffu : 0u;
         }
     }
+    pdl_wait_then_release();  // generations are chained with programmatic dependent launch
     // rows r0 .. r0+RPT-1 are contiguous; only the row above the first and below the last may wrap / be dead
     const int ra = r0 == 0 ? (OPEN ? 0 : H - 1) : r0 - 1;
     const int rb = r0 + RPT == H ? (OPEN ? H - 1 : 0) : r0 + RPT;
@@ -495,22 +496,35 @@ static int launch_fast_t(const uint32_t *in, uint32_t *out, const GolGeom &g, ui
     const int units = g.wpr / 4;
     const int bx = units >= 128 ? 128 : ceil_div(units, 32) * 32;
     dim3 grid(ceil_div(units, bx), ceil_div(g.H, RPT));
-    gol_fast_kernel<LIFE, OPEN, RPT><<<grid, bx, 0, st>>>(in, out, g.H, g.wpr, g.stride, s, b);
-    B200CA_LAUNCH_CHECK("gol_fast_kernel");
+    B200CA_CUDA(launch_pdl(gol_fast_kernel<LIFE, OPEN, RPT>, grid, dim3(bx), 0, st, in, out, g.H, g.wpr, g.stride, s, b));
     return 0;
 }
 
 static int launch_fast(const uint32_t *in, uint32_t *out, const GolGeom &g, uint32_t s, uint32_t b, cudaStream_t st) {
     const bool life = (s == 0b1100u && b == 0b1000u);
-    // 16 rows per thread when that still gives every SM several blocks, else 4
-    const long long blocks16 = (long long)ceil_div(g.wpr / 4, 128) * ceil_div(g.H, 16);
-    const bool big = (g.H % 16 == 0) && blocks16 >= (long long)num_sms() * 12;
-    if (life) {
-        if (g.vert_open) return big ? launch_fast_t<true, true, 16>(in, out, g, s, b, st) : launch_fast_t<true, true, 4>(in, out, g, s, b, st);
-        return big ? launch_fast_t<true, false, 16>(in, out, g, s, b, st) : launch_fast_t<true, false, 4>(in, out, g, s, b, st);
+    // Rows per thread: 16 amortises the two halo rows best, but a slab of a sharded world may then be only 2-3 waves of
+    // blocks and lose a quarter of the machine to the last partial wave: take the largest of {16, 8, 4} that divides H
+    // and keeps the wave quantisation loss under 10 % (6 resident blocks of 128 threads per SM).
+    const long long slots = (long long)num_sms() * 6;
+    int rpt = 4;
+    double best = -1.0;
+    const int cand[3] = {16, 8, 4};
+    for (int c = 0; c < 3; ++c) {
+        if (g.H % cand[c]) continue;
+        const long long blocks = (long long)ceil_div(g.wpr / 4, 128) * (g.H / cand[c]);
+        const double eff = (double)blocks / (double)(ceil_div64(blocks, slots) * slots);
+        const double score = eff >= 0.9 ? 2.0 + cand[c] : eff;   // first (largest) candidate above 90 % wins
+        if (score > best) {
+            best = score;
+            rpt = cand[c];
+        }
     }
-    if (g.vert_open) return big ? launch_fast_t<false, true, 16>(in, out, g, s, b, st) : launch_fast_t<false, true, 4>(in, out, g, s, b, st);
-    return big ? launch_fast_t<false, false, 16>(in, out, g, s, b, st) : launch_fast_t<false, false, 4>(in, out, g, s, b, st);
+#define B200CA_GOL_DISPATCH(LIFE_, OPEN_)                                                        \
+    (rpt == 16 ? launch_fast_t<LIFE_, OPEN_, 16>(in, out, g, s, b, st)                           \
+               : (rpt == 8 ? launch_fast_t<LIFE_, OPEN_, 8>(in, out, g, s, b, st) : launch_fast_t<LIFE_, OPEN_, 4>(in, out, g, s, b, st)))
+    if (life) return g.vert_open ? B200CA_GOL_DISPATCH(true, true) : B200CA_GOL_DISPATCH(true, false);
+    return g.vert_open ? B200CA_GOL_DISPATCH(false, true) : B200CA_GOL_DISPATCH(false, false);
+#undef B200CA_GOL_DISPATCH
 }
 
 static int gol_step_impl(const uint32_t *in, uint32_t *out, int H, int W, int stride, uint32_t s, uint32_t b, int vert_open,

@@ -77,26 +77,6 @@ __device__ __forceinline__ void dit4_inv(float2 &a, float2 &b, float2 &c, float2
 // Each kernel does its input-independent prologue, then waits for the previous grid (griddepcontrol.wait) and
 // immediately lets the next grid start ITS prologue (griddepcontrol.launch_dependents), which takes the launch
 // latency off the critical path of small worlds.
-__device__ __forceinline__ void pdl_wait_then_release() {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
-
-template <typename Kern, typename... Args>
-static cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, args...);
-}
-
 // shared-memory index swizzle for float2 arrays: keeps the radix-4 stages with span 4 and 1 (and the linear
 // passes) free of bank conflicts.  Only the low 4 bits change, so 16-element aligned blocks stay blocks.
 __device__ __forceinline__ int swz(int i) { return i ^ (5 * ((i >> 4) & 3)); }
