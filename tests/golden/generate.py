@@ -168,6 +168,25 @@ def gen_lenia_family():
          alpha_used=np.array(float(auto.alpha)), k_size=np.array(pd["k_size"]), **raw)
 
 
+def gen_kmult():
+    """k_mult = 2 (two kernels per source channel; no demo_data file has it): synthetic parameters, reference step."""
+    torch.manual_seed(5)
+    C, km, R = 2, 2, 3
+    d = {"mu": 0.1 + 0.2 * torch.rand(1, C * km, C), "sigma": 0.03 + 0.1 * torch.rand(1, C * km, C),
+         "beta": torch.rand(1, C * km, C, R), "mu_k": torch.rand(1, C * km, C, R),
+         "sigma_k": 0.05 + 0.2 * torch.rand(1, C * km, C, R), "weights": torch.rand(1, C * km, C), "k_size": 31, "k_mult": km,
+         "num_channels": C}
+    g = torch.Generator().manual_seed(1)
+    s0 = torch.rand(1, C, 64, 128, generator=g)
+    raw = {k: v.clone() for k, v in d.items() if isinstance(v, torch.Tensor)}
+    p = REF.LeniaParams(param_dict=dict(d), channels=C, k_mult=km)
+    a = REF.Lenia((64, 128), num_channels=C, params=p, state_init=s0.clone())
+    K, mu_s, sg_s, w_s = a.k.clone(), a.mu.clone(), a.sigma.clone(), a.weights.clone()
+    a.step()
+    save("lenia_kmult2.npz", state_in=s0, state_out=a.state, K=K, mu_s=mu_s, sigma_s=sg_s, weights_s=w_s, k_size=np.array(31),
+         k_mult=np.array(km), dt=np.array(a.dt), **raw)
+
+
 # ------------------------------------------------------------------ NCA
 def gen_nca():
     folder = os.path.join(DEMO, "NCA_models")
@@ -200,4 +219,5 @@ def gen_nca():
 if __name__ == "__main__":
     gen_gol()
     gen_lenia_family()
+    gen_kmult()
     gen_nca()

@@ -265,3 +265,31 @@ def test_host_entry_point():
               _lib.ptr(a._kprep), _lib.ptr(a.mu), _lib.ptr(a.sigma), _lib.ptr(a.weights), 1, 3, 1, 64, 80, 0.1, 0, 0.0, 0.0, 2)
     ref = orc.lenia_step(orc.lenia_step(s0, K, mu, sg, w), K, mu, sg, w)
     assert (torch.from_numpy(h_out) - ref).abs().max().item() <= 2 * TOL
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_k_mult_2_vs_oracle(path):
+    """k_mult > 1 (several kernels per source channel, lenia.py:77, index i*k_mult+m): synthetic parameters, since every
+    demo_data file has k_mult = 1."""
+    import pyca_b200
+
+    torch.manual_seed(5)
+    C, km, R = 2, 2, 3
+    d = {"mu": 0.1 + 0.2 * torch.rand(1, C * km, C), "sigma": 0.03 + 0.1 * torch.rand(1, C * km, C),
+         "beta": torch.rand(1, C * km, C, R), "mu_k": torch.rand(1, C * km, C, R), "sigma_k": 0.05 + 0.2 * torch.rand(1, C * km, C, R),
+         "weights": torch.rand(1, C * km, C), "k_size": 31, "k_mult": km, "num_channels": C}
+    q = orc.sanitize_params({k: v for k, v in d.items() if isinstance(v, torch.Tensor)})
+    K = orc.lenia_kernel(q["beta"], q["mu_k"], q["sigma_k"], 31)
+    g = torch.Generator().manual_seed(1)
+    s0 = torch.rand(1, C, 64, 128, generator=g)
+    a = pyca_b200.Lenia((64, 128), num_channels=C, params=dict(d), state_init=s0, device="cuda", conv_path=path)
+    assert a.k_mult == km
+    a.step()
+    ref = orc.lenia_step(s0, K, q["mu"], q["sigma"], q["weights"], 0.1)
+    assert (a.state.cpu() - ref).abs().max().item() <= TOL
+    fx = load_npz("lenia_kmult2.npz")  # the same case run by the unmodified reference
+    assert torch.equal(s0, t(fx["state_in"])) and (a.state.cpu() - t(fx["state_out"])).abs().max().item() <= TOL
+    m = pyca_b200.MaCELeniaXChan((64, 128), num_channels=C, params=dict(d), state_init=s0, device="cuda", conv_path=path)
+    m.step()
+    refm = orc.xchan_step(s0, K, q["mu"], q["sigma"], q["weights"], 6.0, 0.03)
+    assert (m.state.cpu() - refm).abs().max().item() <= TOL

@@ -95,3 +95,13 @@ def test_perception_channel_quirk():
                 ref += k[a, b] * torch.roll(s[0, c], (1 - a, 1 - b), dims=(0, 1))
         assert torch.allclose(p[0, o], ref, atol=1e-6)
     assert torch.equal(p[:, 32:], s)
+
+
+def test_lenia_k_mult_2():
+    fx = load_npz("lenia_kmult2.npz")
+    raw = {k: t(fx[k]) for k in ["mu", "sigma", "beta", "mu_k", "sigma_k", "weights"]}
+    q = orc.sanitize_params(raw)
+    K = orc.lenia_kernel(q["beta"], q["mu_k"], q["sigma_k"], 31)
+    assert torch.allclose(K, t(fx["K"]), atol=1e-9, rtol=0) and torch.equal(q["weights"], t(fx["weights_s"]))
+    out = orc.lenia_step(t(fx["state_in"]), K, q["mu"], q["sigma"], q["weights"], float(fx["dt"]))
+    assert (out - t(fx["state_out"])).abs().max().item() <= TOL
