@@ -94,7 +94,8 @@ __device__ __forceinline__ void load_tw(const float2 *__restrict__ tws, int span
 
 // ---- kernel A: forward row FFTs -------------------------------------------------------------------
 // grid (ceil(zrows / FFT_RPC), nseg, B*C), block N/4 threads, smem FFT_RPC * N float2
-template <int FFT_RPC, int N>
+// SPLIT: adjacent frequency pairs are stored as (re0, re1, im0, im1) -- the operand layout of the fused FIR kernel
+template <int FFT_RPC, int N, bool SPLIT>
 __global__ void __launch_bounds__(N / 4) lenia_fft_rows_kernel(const float *__restrict__ state, float2 *__restrict__ Z,
                                                               const float2 *__restrict__ tws, FftGeom g, int H, int W, int pitch) {
     extern __shared__ __align__(16) float2 fsm[];
@@ -173,8 +174,8 @@ __global__ void __launch_bounds__(N / 4) lenia_fft_rows_kernel(const float *__re
         const float2 one = make_float2(1.f, 0.f);
         dif4(a, b, c, d, one, one, one);
         float4 *out = reinterpret_cast<float4 *>(Z + (((size_t)plane * g.zrows + zr[q]) * g.nseg + seg) * N + i0);
-        out[0] = make_float4(a.x, a.y, b.x, b.y);
-        out[1] = make_float4(c.x, c.y, d.x, d.y);
+        out[0] = SPLIT ? make_float4(a.x, b.x, a.y, b.y) : make_float4(a.x, a.y, b.x, b.y);
+        out[1] = SPLIT ? make_float4(c.x, d.x, c.y, d.y) : make_float4(c.x, c.y, d.x, d.y);
     }
 }
 
@@ -235,6 +236,9 @@ struct FftInvArgs {
     const float *state_in;
     float *out;
     const float2 *O;
+    const float2 *Z;     // fused FIR + inverse kernel only: the row spectra and the real tap spectra
+    const float *kfft;
+    int k_mult;
     const float2 *tws;
     const float *mu, *sigma, *weights;
     FftGeom g;
@@ -374,6 +378,251 @@ __global__ void __launch_bounds__(N / 4, (FFT_RPC == 1 && N == 1024) ? 4 : 1) le
             const bool xe = (x < F) || (x >= a.W - F);
             if (xe || re0) fft_store_mirrors(oplane, a.H, a.W, a.pitch, row0, x, v0, a.row_wrap != 0);
             if (xe || re1) fft_store_mirrors(oplane, a.H, a.W, a.pitch, row1, x, v1, a.row_wrap != 0);
+        }
+    }
+}
+
+// ---- radix-16 variants for N = 1024 (the production kernels; the radix-4 ones above serve N = 256) -------------
+// Same five radix-4 DIF/DIT stages (same butterflies, same digit-reversed spectrum order), but executed two stages at a
+// time on 16 values held in registers by one thread, so a row takes 64 threads and TWO shared-memory exchanges instead
+// of four (tools/fft16_proto.py is the numpy model of this mapping and of the bank-conflict-free layouts):
+//   forward  R16(span 256, 64) on idx t + 64 q  ->  exchange 1  ->  R16(16, 4) on idx 64 B + k3 + 4 q  ->  exchange 2
+//            ->  R4(1) on idx 16 t + e  ->  128 contiguous bytes per thread to global memory
+//   inverse  the mirror image; the last R16 leaves samples n = t + 64 q in registers for the growth epilogue.
+constexpr int XB = 1152;  // float2 per row buffer: 1024 + up to 128 pad (idx + idx/16, or idx + 2*(idx/16) for split spectra)
+// barrier among the 64 threads (two warps) that own one row of a multi-row CTA
+__device__ __forceinline__ void row_sync(int rw) { asm volatile("bar.sync %0, 64;" ::"r"(rw + 1) : "memory"); }
+__device__ __forceinline__ int swz_a(int i) { return i ^ (4 * ((i >> 6) & 3)); }
+
+__device__ __forceinline__ void dit4_nt(float2 &a, float2 &b, float2 &c, float2 &d) {
+    const float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d);
+    const float2 bd = csub(b, d);
+    const float2 t3 = make_float2(-bd.y, bd.x);
+    a = cadd(t0, t2);
+    b = cadd(t1, t3);
+    c = csub(t0, t2);
+    d = csub(t1, t3);
+}
+
+// two fused DIT stages: span SB on legs 4 blk + r first, then span SA on legs (m, m+4, m+8, m+12) with twiddle index ka0 + kas*m
+template <int SB, int SA>
+__device__ __forceinline__ void r16_dit(float2 (&v)[16], const float2 *__restrict__ tws, int kb, int ka0, int kas) {
+    float2 w1, w2, w3;
+    load_tw(tws, SB, kb, w1, w2, w3);
+#pragma unroll
+    for (int blk = 0; blk < 4; ++blk) dit4_inv(v[4 * blk], v[4 * blk + 1], v[4 * blk + 2], v[4 * blk + 3], w1, w2, w3);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        load_tw(tws, SA, ka0 + kas * m, w1, w2, w3);
+        dit4_inv(v[m], v[m + 4], v[m + 8], v[m + 12], w1, w2, w3);
+    }
+}
+
+__device__ __forceinline__ void cp_async4(unsigned dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// Stages the state values (rows yy and yy + D) under one thread's 16 samples n = t + 64 q into the row's (free)
+// shared-memory buffer as float2 slot n, by cp.async: no registers held while the copies are in flight.
+// Columns are clamped into the framed row, so samples that are never stored (segment halo, beyond W) read legal memory.
+__device__ __forceinline__ void inv16_stage_state(const FftInvArgs &a, float2 *buf, size_t plane_off, int yy, int seg, int t) {
+    const int xb = a.g.periodic ? t : seg * a.g.V - R + t;
+    const float *sp0 = a.state_in + plane_off + (size_t)(yy + F) * a.pitch + F;
+    const float *sp1 = sp0 + (size_t)a.g.D * a.pitch;
+    const int xmax = a.W + F - 1;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + t);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int x = min(xb + 64 * q, xmax);
+        cp_async4(dst + 512 * q, sp0 + x);
+        cp_async4(dst + 512 * q + 4, sp1 + x);
+    }
+}
+
+// Euler step / clamp (or affinity) and the stores of one thread's 16 samples n = t + 64 q of rows yy and yy + D;
+// `sv` is the row buffer holding the staged state (inv16_stage_state).
+// EDGE = false: an inner segment of a row with no frame images -- no bounds or mirror logic at all.
+template <bool EDGE>
+__device__ __forceinline__ void inv16_store(const FftInvArgs &a, const float2 (&dx)[16], const float2 *sv, size_t plane_off, int yy, int seg,
+                                            int t) {
+    constexpr int N = 1024;
+    float *oplane = a.out + plane_off;
+    const bool lenia = a.mode == B200CA_MODE_LENIA;
+    const int row0 = yy, row1 = yy + a.g.D;
+    const int xb = a.g.periodic ? t : seg * a.g.V - R + t;  // x of sample q = 0
+    float *rp0 = oplane + (size_t)(row0 + F) * a.pitch + F + xb;
+    float *rp1 = rp0 + (size_t)a.g.D * a.pitch;
+    const bool re0 = EDGE && a.row_wrap && (row0 < F || row0 >= a.H - F);
+    const bool re1 = EDGE && a.row_wrap && (row1 < F || row1 >= a.H - F);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int n = t + 64 * q;
+        const int x = xb + 64 * q;
+        if (!a.g.periodic) {
+            if ((q == 0 && n < R) || (q == 15 && n >= N - R)) continue;
+            if (EDGE && x >= a.W) continue;
+        }
+        float v0 = dx[q].x, v1 = dx[q].y;
+        if (lenia) {
+            const float2 s = sv[n];
+            v0 = fminf(fmaxf(s.x + a.dt * v0, 0.f), 1.f);
+            v1 = fminf(fmaxf(s.y + a.dt * v1, 0.f), 1.f);
+        }
+        rp0[64 * q] = v0;
+        rp1[64 * q] = v1;
+        if (EDGE) {
+            const bool xe = (x < F) || (x >= a.W - F);
+            if (xe || re0) fft_store_mirrors(oplane, a.H, a.W, a.pitch, row0, x, v0, a.row_wrap != 0);
+            if (xe || re1) fft_store_mirrors(oplane, a.H, a.W, a.pitch, row1, x, v1, a.row_wrap != 0);
+        }
+    }
+}
+
+// ---- fused kernel B (N = 1024): column FIR on the spectra + inverse row FFT + growth/Euler epilogue -----------------
+// One CTA makes FT output row pairs of one segment of one destination plane.  Phase 1 is the FIR: two adjacent
+// frequencies per thread, so the real taps (w_p0, w_p1) and the split spectra (re_p0, re_p1), (im_p0, im_p1) are
+// natural fp32x2 operands; a spectrum row is read once per CTA -- (FT+30)/FT = 4.75x read amplification at FT = 8,
+// served by L2 because neighbouring row blocks run at the same time.  The filtered spectra stay in shared memory,
+// where phase 2 runs the radix-16 inverse transforms (4 rows per pass) and the epilogue; they never go to HBM.
+// grid (ceil(D / FT), nseg, B*C), block 256 threads, smem FT * XB float2
+template <int FT, bool MULTI, int MINB>
+__global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftInvArgs a) {
+    extern __shared__ __align__(16) float2 fism[];
+    constexpr int N = 1024, NP = FT / 4;
+    const int tid = threadIdx.x, t = tid & 63, rw = tid >> 6;
+    const int seg = blockIdx.y;
+    const int b = blockIdx.z / a.C, j = blockIdx.z % a.C;
+    const int y0 = (int)blockIdx.x * FT;
+    const int B4 = t >> 2, k3 = t & 3;
+    const bool lenia = a.mode == B200CA_MODE_LENIA;
+    float2 dx[MULTI ? NP : 1][16];
+    if (MULTI) {
+#pragma unroll
+        for (int ps = 0; ps < NP; ++ps)
+#pragma unroll
+            for (int q = 0; q < 16; ++q) dx[ps][q] = make_float2(0.f, 0.f);
+    }
+    const size_t plane_off = (size_t)(b * a.C + j) * (a.H + 2 * F) * a.pitch;
+    const size_t zstride = (size_t)a.g.nseg * N;
+    pdl_wait_then_release();  // the spectra come from the row-FFT kernel
+    for (int i = 0; i < a.NS; ++i) {
+        const int pidx = (b * a.NS + i) * a.C + j;
+        const int src_plane = b * a.C + i / a.k_mult;
+        if (i > 0) __syncthreads();  // previous source done with the buffers
+        // phase 1: FIR.  Out^[y][p] = sum_dy Khat[|dy|][p] * Z[y + dy][p] for p = p0, p0 + 1
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            const int p0 = 2 * tid + 512 * c;
+            float2 kt[KROWS];
+            {
+                const float *kf = a.kfft + (size_t)pidx * KROWS * N + p0;
+#pragma unroll
+                for (int dy = 0; dy < KROWS; ++dy) kt[dy] = __ldg(reinterpret_cast<const float2 *>(kf + dy * N));
+            }
+            const float2 *zp = a.Z + (((size_t)src_plane * a.g.zrows + y0) * a.g.nseg + seg) * N + p0;
+            float2 are[FT], aim[FT];
+#pragma unroll
+            for (int y = 0; y < FT; ++y) are[y] = aim[y] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int rr = 0; rr < FT + 2 * R; ++rr) {
+                // spectra row y0 + rr holds image rows (y0 + rr - R, y0 + rr - R + D).  Rows past the last one (only the
+                // discarded outputs yy >= D use them) fall into the next plane or the workspace behind Z: legal, unused.
+                const float4 z = __ldg(reinterpret_cast<const float4 *>(zp + rr * zstride));  // (re0, re1, im0, im1)
+                const float2 zre = make_float2(z.x, z.y), zim = make_float2(z.z, z.w);
+#pragma unroll
+                for (int y = 0; y < FT; ++y) {
+                    const int dy = rr - R - y;
+                    if (dy >= -R && dy <= R) {
+                        are[y] = __ffma2_rn(kt[dy < 0 ? -dy : dy], zre, are[y]);
+                        aim[y] = __ffma2_rn(kt[dy < 0 ? -dy : dy], zim, aim[y]);
+                    }
+                }
+            }
+            // filtered spectra stay split, 16 elements + 2 pad per block (16-byte aligned, conflict-free both ways)
+            float4 *fo = reinterpret_cast<float4 *>(fism) + (p0 >> 1) + (p0 >> 4);
+#pragma unroll
+            for (int y = 0; y < FT; ++y) fo[y * (XB / 2)] = make_float4(are[y].x, are[y].y, aim[y].x, aim[y].y);
+        }
+        __syncthreads();
+        // phase 2: inverse transforms, 4 rows per pass; a row belongs to 64 threads (2 warps) with their own named barrier
+        const float mu = __ldg(a.mu + pidx), sg = __ldg(a.sigma + pidx), wt = __ldg(a.weights + pidx);
+        const float c2 = 1.4426950408889634f / (2.f * sg * sg);
+#pragma unroll
+        for (int ps = 0; ps < NP; ++ps) {
+            float2 *buf = fism + (ps * 4 + rw) * XB;
+            const int yy = y0 + ps * 4 + rw;
+            float2 v[16];
+            {
+                // first DIT stage (span 1, no twiddles) on the split layout: quad m = (A, Cq) = (a.re b.re a.im b.im), (c.., d..)
+                const float4 *b4 = reinterpret_cast<const float4 *>(buf) + 9 * t;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const float4 A = b4[2 * m], Cq = b4[2 * m + 1];
+                    const float2 S0 = cadd(make_float2(A.x, A.y), make_float2(Cq.x, Cq.y));  // (t0.re, t2.re)
+                    const float2 S1 = cadd(make_float2(A.z, A.w), make_float2(Cq.z, Cq.w));  // (t0.im, t2.im)
+                    const float2 D0 = csub(make_float2(A.x, A.y), make_float2(Cq.x, Cq.y));  // (t1.re, bd.re)
+                    const float2 D1 = csub(make_float2(A.z, A.w), make_float2(Cq.z, Cq.w));  // (t1.im, bd.im)
+                    v[4 * m] = make_float2(S0.x + S0.y, S1.x + S1.y);
+                    v[4 * m + 1] = make_float2(D0.x - D1.y, D1.x + D0.y);
+                    v[4 * m + 2] = make_float2(S0.x - S0.y, S1.x - S1.y);
+                    v[4 * m + 3] = make_float2(D0.x + D1.y, D1.x - D0.y);
+                }
+            }
+            row_sync(rw);  // the row's split spectra are consumed before the buffer changes layout
+#pragma unroll
+            for (int e = 0; e < 16; ++e) buf[17 * t + e] = v[e];
+            row_sync(rw);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = buf[68 * B4 + k3 + 4 * q + (q >> 2)];
+            r16_dit<4, 16>(v, a.tws, k3, k3, 4);
+            row_sync(rw);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) buf[64 * B4 + k3 + 4 * (q ^ (B4 & 3))] = v[q];
+            row_sync(rw);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = buf[(t ^ (4 * (q & 3))) + 64 * q];
+            // the row buffer is free now: the state values of the Euler step are staged into it by cp.async, their
+            // latency hidden behind the last two stages + growth
+            const bool stage = lenia && i == a.NS - 1;
+            if (stage) {
+                row_sync(rw);
+                inv16_stage_state(a, buf, plane_off, min(yy, a.g.D - 1), seg, t);
+            }
+            r16_dit<64, 256>(v, a.tws, t, t, 64);
+            // growth + weighted source sum (lenia.py:423-426, :444-446): 2*exp(-(u-mu)^2/(2 sigma^2)) - 1
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const float d0 = v[q].x - mu, d1 = v[q].y - mu;
+                const float g0 = 2.f * exp2f(-d0 * d0 * c2) - 1.f, g1 = 2.f * exp2f(-d1 * d1 * c2) - 1.f;
+                if (MULTI) {
+                    dx[ps][q].x = fmaf(g0, wt, dx[ps][q].x);
+                    dx[ps][q].y = fmaf(g1, wt, dx[ps][q].y);
+                } else {
+                    v[q] = make_float2(g0 * wt, g1 * wt);
+                }
+            }
+            if (stage) cp_async_commit_wait_all();  // own slots only: no barrier needed before reading them back
+            if (!MULTI && yy < a.g.D) {
+                const bool rows_edge = a.row_wrap && (yy < F || yy >= a.g.D - F);
+                const bool edge = rows_edge || a.g.periodic || seg == 0 || seg == a.g.nseg - 1;
+                if (edge) inv16_store<true>(a, v, buf, plane_off, yy, seg, t);
+                else inv16_store<false>(a, v, buf, plane_off, yy, seg, t);
+            }
+        }
+    }
+    if (MULTI) {
+#pragma unroll
+        for (int ps = 0; ps < NP; ++ps) {
+            const int yy = y0 + ps * 4 + rw;
+            if (yy >= a.g.D) continue;
+            const float2 *buf = fism + (ps * 4 + rw) * XB;
+            const bool rows_edge = a.row_wrap && (yy < F || yy >= a.g.D - F);
+            const bool edge = rows_edge || a.g.periodic || seg == 0 || seg == a.g.nseg - 1;
+            if (edge) inv16_store<true>(a, dx[ps], buf, plane_off, yy, seg, t);
+            else inv16_store<false>(a, dx[ps], buf, plane_off, yy, seg, t);
         }
     }
 }
@@ -546,92 +795,116 @@ extern "C" int b200ca_lenia_step_fft_phase(const float *state_in, float *state_o
     const int NS = C * k_mult;
     float2 *Z = reinterpret_cast<float2 *>(workspace);
     float2 *O = Z + (size_t)B * C * g.zrows * g.nseg * g.N;
-    static int rpc_rows = 0, rpc_inv = 0, only = 0;  // `only`: developer switch, run a single phase (timing)
+    // developer switches (timing / A-B runs): B200CA_FFT_ONLY = 1|2|3 runs one kernel of the step only;
+    // B200CA_FFT_FUSED = 0 unfuses FIR and inverse (N = 1024), 4|8 forces the rows per CTA of the fused kernel;
+    static int rpc_rows = 0, rpc_inv = 0, only = 0, fused = -1;
     if (!rpc_rows) {
-        const char *e3 = getenv("B200CA_FFT_ONLY");
-        only = e3 ? atoi(e3) : 0;
-        const char *e1 = getenv("B200CA_FFT_RPC_ROWS"), *e2 = getenv("B200CA_FFT_RPC_INV");
-        rpc_rows = e1 ? atoi(e1) : 2;
-        rpc_inv = e2 ? atoi(e2) : 1;
-        if (rpc_rows != 1 && rpc_rows != 4) rpc_rows = 2;
+        auto env = [](const char *n, int dflt) {
+            const char *e = getenv(n);
+            return e ? atoi(e) : dflt;
+        };
+        only = env("B200CA_FFT_ONLY", 0);
+        fused = env("B200CA_FFT_FUSED", -1);
+        rpc_inv = env("B200CA_FFT_RPC_INV", 1);
         if (rpc_inv != 2 && rpc_inv != 4) rpc_inv = 1;
+        rpc_rows = env("B200CA_FFT_RPC_ROWS", 2);
+        if (rpc_rows != 1 && rpc_rows != 4) rpc_rows = 2;
     }
     if (only == 0 || only == 1) {
         // phase 1: spectra rows made of owned rows only (zr in [R, D+R)); phase 2: the 2R rows that touch ghost rows
+        FftGeom gr = g;
         if (phase == 1) {
-            g.zr_begin = R;
-            g.zr_count = g.D;
+            gr.zr_begin = R;
+            gr.zr_count = g.D;
         } else if (phase == 2) {
-            g.zr_begin = 0;
-            g.zr_count = 2 * R;
-            g.zr_gap_at = R;
-            g.zr_gap = g.D;
+            gr.zr_begin = 0;
+            gr.zr_count = 2 * R;
+            gr.zr_gap_at = R;
+            gr.zr_gap = g.D;
         }
-        const size_t smem = (size_t)rpc_rows * g.N * sizeof(float2);
-        dim3 grid(ceil_div(g.zr_count, rpc_rows), g.nseg, B * C);
-        if (g.N == 1024) {
-            if (rpc_rows == 1) B200CA_CUDA(launch_pdl(lenia_fft_rows_kernel<1, 1024>, grid, dim3(256), smem, st, state_in, Z, tw, g, H, W, pitch));
-            else if (rpc_rows == 2) B200CA_CUDA(launch_pdl(lenia_fft_rows_kernel<2, 1024>, grid, dim3(256), smem, st, state_in, Z, tw, g, H, W, pitch));
-            else B200CA_CUDA(launch_pdl(lenia_fft_rows_kernel<4, 1024>, grid, dim3(256), smem, st, state_in, Z, tw, g, H, W, pitch));
-        } else {
-            if (rpc_rows == 1) B200CA_CUDA(launch_pdl(lenia_fft_rows_kernel<1, 256>, grid, dim3(64), smem, st, state_in, Z, tw, g, H, W, pitch));
-            else if (rpc_rows == 2) B200CA_CUDA(launch_pdl(lenia_fft_rows_kernel<2, 256>, grid, dim3(64), smem, st, state_in, Z, tw, g, H, W, pitch));
-            else B200CA_CUDA(launch_pdl(lenia_fft_rows_kernel<4, 256>, grid, dim3(64), smem, st, state_in, Z, tw, g, H, W, pitch));
-        }
+#define ROWS4(RPC, NN, SP) launch_pdl(lenia_fft_rows_kernel<RPC, NN, SP>, dim3(ceil_div(gr.zr_count, RPC), g.nseg, B * C), dim3(NN / 4), \
+                                  (size_t)RPC * NN * sizeof(float2), st, state_in, Z, tw, gr, H, W, pitch)
+        const bool split = g.N == 1024 && fused != 0;  // the fused FIR + inverse kernel reads split spectra
+        if (split) B200CA_CUDA(rpc_rows == 1 ? ROWS4(1, 1024, true) : (rpc_rows == 4 ? ROWS4(4, 1024, true) : ROWS4(2, 1024, true)));
+        else if (g.N == 1024) B200CA_CUDA(rpc_rows == 1 ? ROWS4(1, 1024, false) : (rpc_rows == 4 ? ROWS4(4, 1024, false) : ROWS4(2, 1024, false)));
+        else B200CA_CUDA(rpc_rows == 1 ? ROWS4(1, 256, false) : (rpc_rows == 4 ? ROWS4(4, 256, false) : ROWS4(2, 256, false)));
+#undef ROWS4
         B200CA_LAUNCH_CHECK("lenia_fft_rows_kernel");
     }
     if (phase == 1) return 0;
+    FftInvArgs a;
+    a.state_in = state_in;
+    a.out = state_out;
+    a.O = O;
+    a.Z = Z;
+    a.kfft = Kfft;
+    a.k_mult = k_mult;
+    a.tws = tw;
+    a.mu = mu;
+    a.sigma = sigma;
+    a.weights = weights;
+    a.g = g;
+    a.B = B;
+    a.C = C;
+    a.NS = NS;
+    a.H = H;
+    a.W = W;
+    a.pitch = pitch;
+    a.dt = dt;
+    a.mode = mode;
+    a.row_wrap = row_wrap;
+    if (g.N == 1024 && fused != 0) {
+        if (only != 0 && only != 3) return 0;
+        static int minb = 0;
+        if (!minb) minb = getenv("B200CA_FFT_MINB") ? atoi(getenv("B200CA_FFT_MINB")) : 2;
+        // 8 row pairs per CTA when that still gives every SM its resident CTAs, else 4 (more, smaller CTAs)
+        const int ft = fused == 4 || fused == 8 ? fused : ((long long)ceil_div(g.D, 8) * g.nseg * B * C >= 2LL * num_sms() ? 8 : 4);
+        const size_t smem = (size_t)ft * XB * sizeof(float2);
+        static bool attr_done = false;
+        if (!attr_done) {
+            const int big = (int)(8 * XB * sizeof(float2));
+            B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_firinv_kernel<8, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_firinv_kernel<8, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_firinv_kernel<8, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            attr_done = true;
+        }
+        dim3 grid(ceil_div(g.D, ft), g.nseg, B * C);
+        if (NS > 1) B200CA_CUDA(ft == 8 ? launch_pdl(lenia_fft_firinv_kernel<8, true, 2>, grid, dim3(256), smem, st, a)
+                                        : launch_pdl(lenia_fft_firinv_kernel<4, true, 2>, grid, dim3(256), smem, st, a));
+        else if (minb != 3) B200CA_CUDA(ft == 8 ? launch_pdl(lenia_fft_firinv_kernel<8, false, 2>, grid, dim3(256), smem, st, a)
+                                                : launch_pdl(lenia_fft_firinv_kernel<4, false, 2>, grid, dim3(256), smem, st, a));
+        else B200CA_CUDA(ft == 8 ? launch_pdl(lenia_fft_firinv_kernel<8, false, 3>, grid, dim3(256), smem, st, a)
+                                 : launch_pdl(lenia_fft_firinv_kernel<4, false, 3>, grid, dim3(256), smem, st, a));
+        B200CA_LAUNCH_CHECK("lenia_fft_firinv_kernel");
+        return 0;
+    }
     if (only == 0 || only == 2) {
-        FftFirArgs a;
-        a.Z = Z;
-        a.O = O;
-        a.kfft = Kfft;
-        a.g = g;
-        a.B = B;
-        a.C = C;
-        a.NS = NS;
-        a.k_mult = k_mult;
+        FftFirArgs f;
+        f.Z = Z;
+        f.O = O;
+        f.kfft = Kfft;
+        f.g = g;
+        f.B = B;
+        f.C = C;
+        f.NS = NS;
+        f.k_mult = k_mult;
         // 32 output rows per thread (1.9x read amplification) when that still fills the machine, else 8 (4.75x, from L2)
         const long long ctas32 = (long long)(g.N / FIR_THREADS) * g.nseg * ceil_div(g.D, 32) * B * NS * C;
         if (ctas32 >= (long long)num_sms() * 16) {
             dim3 grid((g.N / FIR_THREADS) * g.nseg, ceil_div(g.D, 32), B * NS * C);
-            B200CA_CUDA(launch_pdl(lenia_fft_fir_kernel<32>, grid, dim3(FIR_THREADS), 0, st, a));
+            B200CA_CUDA(launch_pdl(lenia_fft_fir_kernel<32>, grid, dim3(FIR_THREADS), 0, st, f));
         } else {
             dim3 grid((g.N / FIR_THREADS) * g.nseg, ceil_div(g.D, 8), B * NS * C);
-            B200CA_CUDA(launch_pdl(lenia_fft_fir_kernel<8>, grid, dim3(FIR_THREADS), 0, st, a));
+            B200CA_CUDA(launch_pdl(lenia_fft_fir_kernel<8>, grid, dim3(FIR_THREADS), 0, st, f));
         }
         B200CA_LAUNCH_CHECK("lenia_fft_fir_kernel");
     }
     if (only == 0 || only == 3) {
-        FftInvArgs a;
-        a.state_in = state_in;
-        a.out = state_out;
-        a.O = O;
-        a.tws = tw;
-        a.mu = mu;
-        a.sigma = sigma;
-        a.weights = weights;
-        a.g = g;
-        a.B = B;
-        a.C = C;
-        a.NS = NS;
-        a.H = H;
-        a.W = W;
-        a.pitch = pitch;
-        a.dt = dt;
-        a.mode = mode;
-        a.row_wrap = row_wrap;
-        const size_t smem = (size_t)rpc_inv * g.N * sizeof(float2);
-        dim3 grid(ceil_div(g.D, rpc_inv), g.nseg, B * C);
-        if (g.N == 1024) {
-            if (rpc_inv == 1) B200CA_CUDA(launch_pdl(lenia_fft_inv_kernel<1, 1024>, grid, dim3(256), smem, st, a));
-            else if (rpc_inv == 2) B200CA_CUDA(launch_pdl(lenia_fft_inv_kernel<2, 1024>, grid, dim3(256), smem, st, a));
-            else B200CA_CUDA(launch_pdl(lenia_fft_inv_kernel<4, 1024>, grid, dim3(256), smem, st, a));
-        } else {
-            if (rpc_inv == 1) B200CA_CUDA(launch_pdl(lenia_fft_inv_kernel<1, 256>, grid, dim3(64), smem, st, a));
-            else if (rpc_inv == 2) B200CA_CUDA(launch_pdl(lenia_fft_inv_kernel<2, 256>, grid, dim3(64), smem, st, a));
-            else B200CA_CUDA(launch_pdl(lenia_fft_inv_kernel<4, 256>, grid, dim3(64), smem, st, a));
-        }
+#define INV4(RPC, NN) launch_pdl(lenia_fft_inv_kernel<RPC, NN>, dim3(ceil_div(g.D, RPC), g.nseg, B * C), dim3(NN / 4), \
+                                 (size_t)RPC * NN * sizeof(float2), st, a)
+        if (g.N == 1024) B200CA_CUDA(rpc_inv == 1 ? INV4(1, 1024) : (rpc_inv == 4 ? INV4(4, 1024) : INV4(2, 1024)));
+        else B200CA_CUDA(rpc_inv == 1 ? INV4(1, 256) : (rpc_inv == 4 ? INV4(4, 256) : INV4(2, 256)));
+#undef INV4
         B200CA_LAUNCH_CHECK("lenia_fft_inv_kernel");
     }
     return 0;

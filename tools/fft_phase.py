@@ -4,7 +4,8 @@ import pyca_b200
 from tools.quick_bench import timeit, pd
 d3 = pd("params_lenia_abominable_mongolic.npz")
 d1 = {k: (v[:, :1, :1].clone() if isinstance(v, torch.Tensor) else v) for k, v in d3.items()}
-for (H, W) in [(1024, 1024), (4096, 3976)]:
+SIZES = [tuple(int(v) for v in a.split('x')) for a in sys.argv[1:]] or [(1024, 1024), (4096, 3976), (16384, 16384)]
+for (H, W) in SIZES:
     a = pyca_b200.Lenia((H, W), num_channels=1, params=d1, state_init=torch.rand(1, 1, H, W), device="cuda", conv_path="fft")
     a.step()
     fs = a._fs
