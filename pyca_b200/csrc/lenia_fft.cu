@@ -404,16 +404,23 @@ __device__ __forceinline__ void dit4_nt(float2 &a, float2 &b, float2 &c, float2 
     d = csub(t1, t3);
 }
 
-// two fused DIT stages: span SB on legs 4 blk + r first, then span SA on legs (m, m+4, m+8, m+12) with twiddle index ka0 + kas*m
+// two fused DIT stages: span SB on legs 4 blk + r first, then span SA on legs (m, m+4, m+8, m+12) with twiddle index ka0 + kas*m.
+// `tws` is the shared-memory copy of the twiddle tables (plain loads).
+__device__ __forceinline__ void load_tw_s(const float2 *tws, int span, int k, float2 &w1, float2 &w2, float2 &w3) {
+    const float2 *t = tws + (span - 1) + k;
+    w1 = t[0];
+    w2 = t[span];
+    w3 = t[2 * span];
+}
 template <int SB, int SA>
-__device__ __forceinline__ void r16_dit(float2 (&v)[16], const float2 *__restrict__ tws, int kb, int ka0, int kas) {
+__device__ __forceinline__ void r16_dit(float2 (&v)[16], const float2 *tws, int kb, int ka0, int kas) {
     float2 w1, w2, w3;
-    load_tw(tws, SB, kb, w1, w2, w3);
+    load_tw_s(tws, SB, kb, w1, w2, w3);
 #pragma unroll
     for (int blk = 0; blk < 4; ++blk) dit4_inv(v[4 * blk], v[4 * blk + 1], v[4 * blk + 2], v[4 * blk + 3], w1, w2, w3);
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-        load_tw(tws, SA, ka0 + kas * m, w1, w2, w3);
+        load_tw_s(tws, SA, ka0 + kas * m, w1, w2, w3);
         dit4_inv(v[m], v[m + 4], v[m + 8], v[m + 12], w1, w2, w3);
     }
 }
@@ -488,10 +495,21 @@ __device__ __forceinline__ void inv16_store(const FftInvArgs &a, const float2 (&
 // served by L2 because neighbouring row blocks run at the same time.  The filtered spectra stay in shared memory,
 // where phase 2 runs the radix-16 inverse transforms (4 rows per pass) and the epilogue; they never go to HBM.
 // grid (ceil(D / FT), nseg, B*C), block 256 threads, smem FT * XB float2
+#ifdef B200CA_FFT_TRACE
+__device__ long long g_fft_trace[8 * 4096];
+#define FFT_TRACE(slot)                                                                                         \
+    do {                                                                                                        \
+        const int cta_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);                        \
+        if (threadIdx.x == 0 && cta_ < 4096) g_fft_trace[cta_ * 8 + (slot)] = clock64();                        \
+    } while (0)
+#else
+#define FFT_TRACE(slot)
+#endif
+
 template <int FT, bool MULTI, int MINB>
 __global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftInvArgs a) {
     extern __shared__ __align__(16) float2 fism[];
-    constexpr int N = 1024, NP = FT / 4;
+    constexpr int N = 1024, NP = (FT + 3) / 4;  // FT = 2: one pass in which only the first two row groups work
     const int tid = threadIdx.x, t = tid & 63, rw = tid >> 6;
     const int seg = blockIdx.y;
     const int b = blockIdx.z / a.C, j = blockIdx.z % a.C;
@@ -507,7 +525,21 @@ __global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftIn
     }
     const size_t plane_off = (size_t)(b * a.C + j) * (a.H + 2 * F) * a.pitch;
     const size_t zstride = (size_t)a.g.nseg * N;
+    // everything that does not depend on the row-FFT kernel is fetched before the dependency wait, so that under
+    // programmatic dependent launch it overlaps the previous kernel: the twiddle tables (copied to shared memory:
+    // the inverse stages then never wait on L2) and the taps of the first chunk
+    FFT_TRACE(0);
+    float2 *tw_s = fism + FT * XB;
+    for (int e = tid; e < N; e += 256) tw_s[e] = __ldg(a.tws + e);
+    float2 kt[KROWS];
+    {
+        const float *kf = a.kfft + (size_t)((b * a.NS) * a.C + j) * KROWS * N + 2 * tid;
+#pragma unroll
+        for (int dy = 0; dy < KROWS; ++dy) kt[dy] = __ldg(reinterpret_cast<const float2 *>(kf + dy * N));
+    }
+    FFT_TRACE(1);
     pdl_wait_then_release();  // the spectra come from the row-FFT kernel
+    FFT_TRACE(2);
     for (int i = 0; i < a.NS; ++i) {
         const int pidx = (b * a.NS + i) * a.C + j;
         const int src_plane = b * a.C + i / a.k_mult;
@@ -516,8 +548,7 @@ __global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftIn
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
             const int p0 = 2 * tid + 512 * c;
-            float2 kt[KROWS];
-            {
+            if (i > 0 || c > 0) {
                 const float *kf = a.kfft + (size_t)pidx * KROWS * N + p0;
 #pragma unroll
                 for (int dy = 0; dy < KROWS; ++dy) kt[dy] = __ldg(reinterpret_cast<const float2 *>(kf + dy * N));
@@ -546,12 +577,15 @@ __global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftIn
 #pragma unroll
             for (int y = 0; y < FT; ++y) fo[y * (XB / 2)] = make_float4(are[y].x, are[y].y, aim[y].x, aim[y].y);
         }
+        FFT_TRACE(3);
         __syncthreads();
+        FFT_TRACE(4);
         // phase 2: inverse transforms, 4 rows per pass; a row belongs to 64 threads (2 warps) with their own named barrier
         const float mu = __ldg(a.mu + pidx), sg = __ldg(a.sigma + pidx), wt = __ldg(a.weights + pidx);
         const float c2 = 1.4426950408889634f / (2.f * sg * sg);
 #pragma unroll
         for (int ps = 0; ps < NP; ++ps) {
+            if (FT < 4 && rw >= FT) break;
             float2 *buf = fism + (ps * 4 + rw) * XB;
             const int yy = y0 + ps * 4 + rw;
             float2 v[16];
@@ -577,7 +611,7 @@ __global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftIn
             row_sync(rw);
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] = buf[68 * B4 + k3 + 4 * q + (q >> 2)];
-            r16_dit<4, 16>(v, a.tws, k3, k3, 4);
+            r16_dit<4, 16>(v, tw_s, k3, k3, 4);
             row_sync(rw);
 #pragma unroll
             for (int q = 0; q < 16; ++q) buf[64 * B4 + k3 + 4 * (q ^ (B4 & 3))] = v[q];
@@ -591,7 +625,7 @@ __global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftIn
                 row_sync(rw);
                 inv16_stage_state(a, buf, plane_off, min(yy, a.g.D - 1), seg, t);
             }
-            r16_dit<64, 256>(v, a.tws, t, t, 64);
+            r16_dit<64, 256>(v, tw_s, t, t, 64);
             // growth + weighted source sum (lenia.py:423-426, :444-446): 2*exp(-(u-mu)^2/(2 sigma^2)) - 1
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
@@ -604,7 +638,9 @@ __global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftIn
                     v[q] = make_float2(g0 * wt, g1 * wt);
                 }
             }
+            FFT_TRACE(5);
             if (stage) cp_async_commit_wait_all();  // own slots only: no barrier needed before reading them back
+            FFT_TRACE(6);
             if (!MULTI && yy < a.g.D) {
                 const bool rows_edge = a.row_wrap && (yy < F || yy >= a.g.D - F);
                 const bool edge = rows_edge || a.g.periodic || seg == 0 || seg == a.g.nseg - 1;
@@ -613,11 +649,12 @@ __global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftIn
             }
         }
     }
+    FFT_TRACE(7);
     if (MULTI) {
 #pragma unroll
         for (int ps = 0; ps < NP; ++ps) {
             const int yy = y0 + ps * 4 + rw;
-            if (yy >= a.g.D) continue;
+            if (yy >= a.g.D || (FT < 4 && rw >= FT)) continue;
             const float2 *buf = fism + (ps * 4 + rw) * XB;
             const bool rows_edge = a.row_wrap && (yy < F || yy >= a.g.D - F);
             const bool edge = rows_edge || a.g.periodic || seg == 0 || seg == a.g.nseg - 1;
@@ -720,6 +757,12 @@ static int get_twiddles(int N, const float2 **out, cudaStream_t st) {
 }  // namespace b200ca
 
 using namespace b200ca;
+
+#ifdef B200CA_FFT_TRACE
+extern "C" int b200ca_debug_fft_trace(long long *out, int n) {
+    return (int)cudaMemcpyFromSymbol(out, g_fft_trace, sizeof(long long) * n);
+}
+#endif
 
 extern "C" int b200ca_lenia_fft_length(int H, int W) {
     FftGeom g;
@@ -858,19 +901,23 @@ extern "C" int b200ca_lenia_step_fft_phase(const float *state_in, float *state_o
         static int minb = 0;
         if (!minb) minb = getenv("B200CA_FFT_MINB") ? atoi(getenv("B200CA_FFT_MINB")) : 2;
         // 8 row pairs per CTA when that still gives every SM its resident CTAs, else 4 (more, smaller CTAs)
-        const int ft = fused == 4 || fused == 8 ? fused : ((long long)ceil_div(g.D, 8) * g.nseg * B * C >= 2LL * num_sms() ? 8 : 4);
-        const size_t smem = (size_t)ft * XB * sizeof(float2);
+        const long long per_row = (long long)g.nseg * B * C;
+        const int ft = fused == 2 || fused == 4 || fused == 8 ? fused
+                       : (ceil_div(g.D, 8) * per_row >= 2LL * num_sms() ? 8 : (ceil_div(g.D, 4) * per_row >= 2LL * num_sms() ? 4 : 2));
+        const size_t smem = ((size_t)ft * XB + 1024) * sizeof(float2);  // row buffers + twiddle tables
         static bool attr_done = false;
         if (!attr_done) {
-            const int big = (int)(8 * XB * sizeof(float2));
+            const int big = (int)((8 * XB + 1024) * sizeof(float2));
             B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_firinv_kernel<8, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
             B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_firinv_kernel<8, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
             B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_firinv_kernel<8, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
             attr_done = true;
         }
         dim3 grid(ceil_div(g.D, ft), g.nseg, B * C);
-        if (NS > 1) B200CA_CUDA(ft == 8 ? launch_pdl(lenia_fft_firinv_kernel<8, true, 2>, grid, dim3(256), smem, st, a)
-                                        : launch_pdl(lenia_fft_firinv_kernel<4, true, 2>, grid, dim3(256), smem, st, a));
+        if (ft == 2) B200CA_CUDA(NS > 1 ? launch_pdl(lenia_fft_firinv_kernel<2, true, 2>, grid, dim3(256), smem, st, a)
+                                        : launch_pdl(lenia_fft_firinv_kernel<2, false, 2>, grid, dim3(256), smem, st, a));
+        else if (NS > 1) B200CA_CUDA(ft == 8 ? launch_pdl(lenia_fft_firinv_kernel<8, true, 2>, grid, dim3(256), smem, st, a)
+                                             : launch_pdl(lenia_fft_firinv_kernel<4, true, 2>, grid, dim3(256), smem, st, a));
         else if (minb != 3) B200CA_CUDA(ft == 8 ? launch_pdl(lenia_fft_firinv_kernel<8, false, 2>, grid, dim3(256), smem, st, a)
                                                 : launch_pdl(lenia_fft_firinv_kernel<4, false, 2>, grid, dim3(256), smem, st, a));
         else B200CA_CUDA(ft == 8 ? launch_pdl(lenia_fft_firinv_kernel<8, false, 3>, grid, dim3(256), smem, st, a)
