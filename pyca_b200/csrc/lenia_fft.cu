@@ -509,7 +509,7 @@ __device__ long long g_fft_trace[8 * 4096];
 template <int FT, bool MULTI, int MINB>
 __global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftInvArgs a) {
     extern __shared__ __align__(16) float2 fism[];
-    constexpr int N = 1024, NP = (FT + 3) / 4;  // FT = 2: one pass in which only the first two row groups work
+    constexpr int N = 1024, NP = FT / 4;
     const int tid = threadIdx.x, t = tid & 63, rw = tid >> 6;
     const int seg = blockIdx.y;
     const int b = blockIdx.z / a.C, j = blockIdx.z % a.C;
@@ -585,7 +585,6 @@ __global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftIn
         const float c2 = 1.4426950408889634f / (2.f * sg * sg);
 #pragma unroll
         for (int ps = 0; ps < NP; ++ps) {
-            if (FT < 4 && rw >= FT) break;
             float2 *buf = fism + (ps * 4 + rw) * XB;
             const int yy = y0 + ps * 4 + rw;
             float2 v[16];
@@ -654,7 +653,7 @@ __global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftIn
 #pragma unroll
         for (int ps = 0; ps < NP; ++ps) {
             const int yy = y0 + ps * 4 + rw;
-            if (yy >= a.g.D || (FT < 4 && rw >= FT)) continue;
+            if (yy >= a.g.D) continue;
             const float2 *buf = fism + (ps * 4 + rw) * XB;
             const bool rows_edge = a.row_wrap && (yy < F || yy >= a.g.D - F);
             const bool edge = rows_edge || a.g.periodic || seg == 0 || seg == a.g.nseg - 1;
@@ -901,9 +900,7 @@ extern "C" int b200ca_lenia_step_fft_phase(const float *state_in, float *state_o
         static int minb = 0;
         if (!minb) minb = getenv("B200CA_FFT_MINB") ? atoi(getenv("B200CA_FFT_MINB")) : 2;
         // 8 row pairs per CTA when that still gives every SM its resident CTAs, else 4 (more, smaller CTAs)
-        const long long per_row = (long long)g.nseg * B * C;
-        const int ft = fused == 2 || fused == 4 || fused == 8 ? fused
-                       : (ceil_div(g.D, 8) * per_row >= 2LL * num_sms() ? 8 : (ceil_div(g.D, 4) * per_row >= 2LL * num_sms() ? 4 : 2));
+        const int ft = fused == 4 || fused == 8 ? fused : ((long long)ceil_div(g.D, 8) * g.nseg * B * C >= 2LL * num_sms() ? 8 : 4);
         const size_t smem = ((size_t)ft * XB + 1024) * sizeof(float2);  // row buffers + twiddle tables
         static bool attr_done = false;
         if (!attr_done) {
@@ -914,9 +911,7 @@ extern "C" int b200ca_lenia_step_fft_phase(const float *state_in, float *state_o
             attr_done = true;
         }
         dim3 grid(ceil_div(g.D, ft), g.nseg, B * C);
-        if (ft == 2) B200CA_CUDA(NS > 1 ? launch_pdl(lenia_fft_firinv_kernel<2, true, 2>, grid, dim3(256), smem, st, a)
-                                        : launch_pdl(lenia_fft_firinv_kernel<2, false, 2>, grid, dim3(256), smem, st, a));
-        else if (NS > 1) B200CA_CUDA(ft == 8 ? launch_pdl(lenia_fft_firinv_kernel<8, true, 2>, grid, dim3(256), smem, st, a)
+        if (NS > 1) B200CA_CUDA(ft == 8 ? launch_pdl(lenia_fft_firinv_kernel<8, true, 2>, grid, dim3(256), smem, st, a)
                                              : launch_pdl(lenia_fft_firinv_kernel<4, true, 2>, grid, dim3(256), smem, st, a));
         else if (minb != 3) B200CA_CUDA(ft == 8 ? launch_pdl(lenia_fft_firinv_kernel<8, false, 2>, grid, dim3(256), smem, st, a)
                                                 : launch_pdl(lenia_fft_firinv_kernel<4, false, 2>, grid, dim3(256), smem, st, a));

@@ -268,7 +268,10 @@ class LeniaSlabCUDA(LeniaSlab):
             self.overlap = overlap and world > 1 and self.n_tile_rows > 2 * self.n_boundary
         self.comm_stream = torch.cuda.Stream(device=self.device) if world > 1 else None
         self._pending_exchange = False  # FFT path: the ghost rows of `buf` are still in flight on comm_stream
-        self.launches_per_step = (4 if self.overlap else 3) if self.use_fft else (3 if self.overlap else 1)
+        # FFT path: row FFTs (twice when the halo exchange is overlapped: interior rows, then the rows touching ghost rows)
+        # + column FIR and inverse FFT, fused into one kernel for N = 1024 transforms
+        nfft = 2 if self.use_fft and _lib.lib().b200ca_lenia_fft_length(self.hl, self.W) == 1024 else 3
+        self.launches_per_step = (nfft + (1 if self.overlap else 0)) if self.use_fft else (3 if self.overlap else 1)
 
     def set_interior(self, dense: torch.Tensor, group=None):
         """dense: (B,C,hl,W) rows [r0,r1) of the global state."""
