@@ -155,6 +155,19 @@ int b200ca_lenia_run_host(const float *h_state_in, float *h_state_out, const flo
                           const float *sigma, const float *weights, int B, int C, int k_mult, int H, int W, float dt,
                           int family, float beta, float alpha, int nsteps);
 
+/* Pipelined host entry point: a stream of HOST-resident worlds (pinned buffers) through the same step.  The reference's
+ * headless loop on host data is `auto.state = t; auto.step(); t = auto.state` per world (lenia.py:79, :430-451), every
+ * copy serialised with the step; independent worlds can overlap instead.  A pipe owns `depth` lanes (stream, staging,
+ * framed buffers, FFT workspace); submit() queues H2D -> nsteps steps -> D2H on the next lane (round-robin) and returns
+ * at once -- it only blocks while that lane's previous world is still in flight; drain() waits for everything queued.
+ * K/mu/sigma/weights: the reference's `k`, `mu`, `sigma`, `weights` tensors (host or device pointers; copied at create).
+ * family: 0 Lenia, 1 MaCE, 2 MaCE-XChan.  Uses the FFT path when the shape supports it, else the direct path. */
+int b200ca_lenia_pipe_create(void **pipe, const float *K, const float *mu, const float *sigma, const float *weights, int B,
+                             int C, int k_mult, int ks, int H, int W, float dt, int family, float beta, float alpha, int depth);
+int b200ca_lenia_pipe_submit(void *pipe, const float *h_state_in, float *h_state_out, int nsteps);
+int b200ca_lenia_pipe_drain(void *pipe);
+int b200ca_lenia_pipe_destroy(void *pipe);
+
 /* ------------------------------------------------------------------------------------
  * Neural CA inference.  Replaces NCAModule.forward for one step (models/nca.py:239-263):
  * SobelConv perception (:328-344), Linear-ReLU-Linear (:205-208), sigmoid * update mask,

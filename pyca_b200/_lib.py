@@ -49,6 +49,11 @@ SIGNATURES = {
     "b200ca_frame_mass": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200ca_lenia_run_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                       c_int, c_float, c_int, c_float, c_float, c_int]),
+    "b200ca_lenia_pipe_create": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                         c_int, c_int, c_int, c_float, c_int, c_float, c_float, c_int]),
+    "b200ca_lenia_pipe_submit": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
+    "b200ca_lenia_pipe_drain": (c_int, [c_void_p]),
+    "b200ca_lenia_pipe_destroy": (c_int, [c_void_p]),
     "b200ca_nca_wprep_bytes": (c_int64, [c_int, c_int]),
     "b200ca_nca_prepare_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "b200ca_nca_scratch_bytes": (c_int64, [c_int, c_int, c_int]),

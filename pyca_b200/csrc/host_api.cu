@@ -40,3 +40,170 @@ extern "C" int b200ca_lenia_run_host(const float *h_state_in, float *h_state_out
     } while (0);
     return rc;
 }
+
+// ---- pipelined host entry point --------------------------------------------------------------------------------
+// A stream of HOST-resident worlds through the Lenia-family step.  Independent worlds only depend on their own state,
+// so while world i steps on the SMs, world i+1 rides up the PCIe link and world i-1 rides down (separate copy engines
+// per direction).  A pipe owns `depth` lanes -- stream, dense staging buffer, two framed buffers, affinity plane, FFT
+// workspace, completion event; submit() deals worlds to lanes round-robin and returns as soon as the work is queued.
+namespace {
+
+struct Lane {
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    float *dense = nullptr, *a = nullptr, *b = nullptr, *aff = nullptr, *ws = nullptr;
+    bool busy = false;
+};
+
+struct Pipe {
+    int dev = 0, B = 0, C = 0, km = 0, H = 0, W = 0, family = 0, depth = 0, next = 0;
+    float dt = 0.f, beta = 0.f, alpha = 0.f;
+    bool fft = false;
+    size_t dbytes = 0;
+    float *kprep = nullptr, *kfft = nullptr, *mu = nullptr, *sigma = nullptr, *weights = nullptr;
+    Lane *lanes = nullptr;
+};
+
+void pipe_free(Pipe *p) {
+    if (!p) return;
+    if (p->lanes) {
+        for (int i = 0; i < p->depth; ++i) {
+            Lane &l = p->lanes[i];
+            if (l.st) cudaStreamSynchronize(l.st);
+            cudaFree(l.dense);
+            cudaFree(l.a);
+            cudaFree(l.b);
+            cudaFree(l.aff);
+            cudaFree(l.ws);
+            if (l.done) cudaEventDestroy(l.done);
+            if (l.st) cudaStreamDestroy(l.st);
+        }
+        delete[] p->lanes;
+    }
+    cudaFree(p->kprep);
+    cudaFree(p->kfft);
+    cudaFree(p->mu);
+    cudaFree(p->sigma);
+    cudaFree(p->weights);
+    delete p;
+    (void)cudaGetLastError();
+}
+
+int pipe_build(Pipe *p, const float *K, const float *mu, const float *sigma, const float *weights, int ks) {
+    const int B = p->B, C = p->C, km = p->km, H = p->H, W = p->W;
+    const size_t np = (size_t)B * C * km * C * sizeof(float);
+    const size_t fbytes = (size_t)b200ca_frame_elems(B, C, H, W) * sizeof(float);
+    B200CA_CUDA(cudaMalloc(&p->mu, np));
+    B200CA_CUDA(cudaMalloc(&p->sigma, np));
+    B200CA_CUDA(cudaMalloc(&p->weights, np));
+    B200CA_CUDA(cudaMemcpy(p->mu, mu, np, cudaMemcpyDefault));
+    B200CA_CUDA(cudaMemcpy(p->sigma, sigma, np, cudaMemcpyDefault));
+    B200CA_CUDA(cudaMemcpy(p->weights, weights, np, cudaMemcpyDefault));
+    // the reference's kernel tensor `k` may live on either side; the prepare kernels want it on the device
+    const size_t kbytes = (size_t)B * C * km * C * ks * ks * sizeof(float);
+    float *dK = nullptr;
+    B200CA_CUDA(cudaMalloc(&dK, kbytes));
+    int rc = check_cuda(cudaMemcpy(dK, K, kbytes, cudaMemcpyDefault), "K upload");
+    if (!rc) {
+        if (p->fft) {
+            rc = check_cuda(cudaMalloc(&p->kfft, (size_t)b200ca_lenia_fft_kernel_elems(B, C, km, H, W) * sizeof(float)), "cudaMalloc");
+            if (!rc) rc = b200ca_lenia_fft_prepare_kernel(dK, p->kfft, B, C, km, ks, H, W, nullptr);
+        } else {
+            rc = check_cuda(cudaMalloc(&p->kprep, (size_t)b200ca_lenia_kprep_elems(B, C, km) * sizeof(float)), "cudaMalloc");
+            if (!rc) rc = b200ca_lenia_prepare_kernel(dK, p->kprep, B, C, km, ks, nullptr);
+        }
+    }
+    if (!rc) rc = check_cuda(cudaDeviceSynchronize(), "kernel preparation");
+    cudaFree(dK);
+    if (rc) return rc;
+    p->lanes = new Lane[p->depth];
+    for (int i = 0; i < p->depth; ++i) {
+        Lane &l = p->lanes[i];
+        B200CA_CUDA(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
+        B200CA_CUDA(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+        B200CA_CUDA(cudaMalloc(&l.dense, p->dbytes));
+        B200CA_CUDA(cudaMalloc(&l.a, fbytes));
+        B200CA_CUDA(cudaMalloc(&l.b, fbytes));
+        B200CA_CUDA(cudaMemset(l.a, 0, fbytes));
+        B200CA_CUDA(cudaMemset(l.b, 0, fbytes));
+        if (p->family > 0) {
+            B200CA_CUDA(cudaMalloc(&l.aff, fbytes));
+            B200CA_CUDA(cudaMemset(l.aff, 0, fbytes));
+        }
+        if (p->fft) B200CA_CUDA(cudaMalloc(&l.ws, (size_t)b200ca_lenia_fft_workspace_elems(B, C, km, H, W) * sizeof(float)));
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int b200ca_lenia_pipe_create(void **pipe, const float *K, const float *mu, const float *sigma, const float *weights,
+                                        int B, int C, int k_mult, int ks, int H, int W, float dt, int family, float beta,
+                                        float alpha, int depth) {
+    B200CA_REQUIRE(pipe && K && mu && sigma && weights, "lenia_pipe_create: null pointer");
+    B200CA_REQUIRE(family >= 0 && family <= 2, "lenia_pipe_create: family must be 0 (Lenia), 1 (MaCE) or 2 (MaCE-XChan)");
+    B200CA_REQUIRE(depth >= 1 && depth <= 16, "lenia_pipe_create: depth must be in [1,16] (got %d)", depth);
+    B200CA_REQUIRE(B >= 1 && C >= 1 && k_mult >= 1 && ks >= 1 && (ks & 1) && ks <= 31 && H >= B200CA_FRAME && W >= B200CA_FRAME,
+                   "lenia_pipe_create: bad shape B=%d C=%d k_mult=%d ks=%d H=%d W=%d", B, C, k_mult, ks, H, W);
+    *pipe = nullptr;
+    int dev = 0;
+    B200CA_CUDA(cudaGetDevice(&dev));
+    Pipe *p = new Pipe();
+    p->dev = dev;
+    p->B = B, p->C = C, p->km = k_mult, p->H = H, p->W = W, p->family = family, p->depth = depth;
+    p->dt = dt, p->beta = beta, p->alpha = alpha;
+    p->fft = b200ca_lenia_fft_length(H, W) > 0;
+    p->dbytes = (size_t)B * C * H * W * sizeof(float);
+    const int rc = pipe_build(p, K, mu, sigma, weights, ks);
+    if (rc) {
+        pipe_free(p);
+        return rc;
+    }
+    *pipe = p;
+    return 0;
+}
+
+extern "C" int b200ca_lenia_pipe_submit(void *pipe, const float *h_state_in, float *h_state_out, int nsteps) {
+    Pipe *p = static_cast<Pipe *>(pipe);
+    B200CA_REQUIRE(p && h_state_in && h_state_out && nsteps >= 0, "lenia_pipe_submit: bad arguments");
+    Lane &l = p->lanes[p->next];
+    p->next = (p->next + 1) % p->depth;
+    if (l.busy) B200CA_CUDA(cudaEventSynchronize(l.done));  // the lane's previous world has landed in its host buffer
+    const int B = p->B, C = p->C, km = p->km, H = p->H, W = p->W;
+    B200CA_CUDA(cudaMemcpyAsync(l.dense, h_state_in, p->dbytes, cudaMemcpyHostToDevice, l.st));
+    int rc = b200ca_frame_load(l.dense, l.a, B, C, H, W, 1, l.st);
+    float *src = l.a, *dst = l.b;
+    for (int i = 0; i < nsteps && !rc; ++i) {
+        float *conv_out = p->family == 0 ? dst : l.aff;
+        const int mode = p->family == 0 ? B200CA_MODE_LENIA : B200CA_MODE_AFF;
+        rc = p->fft ? b200ca_lenia_step_fft(src, conv_out, p->kfft, p->mu, p->sigma, p->weights, l.ws, B, C, km, H, W, p->dt, mode, 1, l.st)
+                    : b200ca_lenia_step(src, conv_out, p->kprep, p->mu, p->sigma, p->weights, B, C, km, H, W, p->dt, mode, 1, 0, 0, l.st);
+        if (!rc && p->family > 0)
+            rc = b200ca_mace_redistribute(src, l.aff, dst, B, C, H, W, p->beta, p->family == 2, p->alpha, 1, l.st);
+        float *t = src;
+        src = dst;
+        dst = t;
+    }
+    if (rc) return rc;
+    if ((rc = b200ca_frame_store(src, l.dense, B, C, H, W, l.st))) return rc;
+    B200CA_CUDA(cudaMemcpyAsync(h_state_out, l.dense, p->dbytes, cudaMemcpyDeviceToHost, l.st));
+    B200CA_CUDA(cudaEventRecord(l.done, l.st));
+    l.busy = true;
+    return 0;
+}
+
+extern "C" int b200ca_lenia_pipe_drain(void *pipe) {
+    Pipe *p = static_cast<Pipe *>(pipe);
+    B200CA_REQUIRE(p, "lenia_pipe_drain: null pipe");
+    for (int i = 0; i < p->depth; ++i)
+        if (p->lanes[i].busy) {
+            B200CA_CUDA(cudaEventSynchronize(p->lanes[i].done));
+            p->lanes[i].busy = false;
+        }
+    return 0;
+}
+
+extern "C" int b200ca_lenia_pipe_destroy(void *pipe) {
+    pipe_free(static_cast<Pipe *>(pipe));
+    return 0;
+}
