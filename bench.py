@@ -858,6 +858,39 @@ def main():
             except Exception as e:  # keep the headline line even if an extra fails
                 extras[other] = {"error": repr(e)[:200]}
 
+        # draw() + Automaton.worldmap of a 1024^2 3-channel Lenia world, fused kernel + 3 B/cell D2H against
+        # the reference's expression on the same GPU (torch clamp, float permute, 12 B/cell D2H, host-side uint8 cast)
+        try:
+            dw = make_workload("lenia3_1k", 0, 1, device)
+            dw.setup()
+            a = dw.auto
+
+            def fused():
+                a.draw()
+                return a.worldmap
+
+            def torch_way():
+                wm = torch.clamp(a.state[0][:3].clone(), 0.0, 1.0)
+                return (255 * wm.permute(2, 1, 0)).detach().cpu().numpy().astype(dtype=np.uint8)
+
+            res = {}
+            for nm, fn in (("fused_ms", fused), ("torch_reference_expression_ms", torch_way)):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(20):
+                    fn()
+                torch.cuda.synchronize()
+                res[nm] = (time.perf_counter() - t0) / 20 * 1e3
+            res["identical"] = bool(np.array_equal(fused(), torch_way()))
+            res["workload"] = "draw() + worldmap, Lenia 1x3x1024x1024 -> (1024,1024,3) uint8 on the host"
+            extras["draw_lenia3_1k"] = res
+            del dw
+            torch.cuda.empty_cache()
+        except Exception as e:
+            extras["draw_lenia3_1k"] = {"error": repr(e)[:200]}
+
     sharded = None
     if world > 1 and not args.no_extras:
         # BASELINE configs[4]: one big torus in row slabs with NVLink halo exchange; raw values at N GPUs and, for

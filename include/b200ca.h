@@ -193,6 +193,26 @@ int b200ca_nca_step(const float *state_in, float *state_out, const void *Wprep, 
 int b200ca_nca_run_host(const float *h_state_in, float *h_state_out, const void *Wprep, const uint8_t *h_update_mask,
                         uint64_t seed, int B, int n, int hid, int H, int W, int impl, int nsteps);
 
+/* ------------------------------------------------------------------------------------
+ * Fused draw(): state -> RGB frame on the device (the step either side of the hot path).
+ * Replaces the torch elementwise ops of draw() (ca2d.py:117-124, lenia.py:481-500, macelenia.py:365-385,
+ * nca.py:74-87) and the float permute + D2H + host uint8 cast of Automaton.worldmap (automaton.py:209-216).
+ *   worldmap: float (3,H,W) device tensor = the reference's `_worldmap` (NULL = not wanted, except CA2D where it is the
+ *             echo state read and rewritten every frame);
+ *   frame:    uint8 (W,H,3) device buffer = what `worldmap` returns after its host-side cast:
+ *             frame[x][y][c] = (uint8)(255.f * worldmap[c][y][x]) (truncation); NULL = not wanted.
+ * ---------------------------------------------------------------------------------- */
+int b200ca_draw_gol(const uint32_t *bits, float *worldmap, uint8_t *frame, int H, int W, int stride_words, float decay_r,
+                    float decay_g, float decay_b, void *stream);
+/* state: framed (B,C,H,W); C==1 grey, C==2 (c0,c1,0), C>=3 first three channels; food: dense (H,W) plane added to all
+ * three colours before the clamp (macelenia.py:379-380) or NULL. */
+int b200ca_draw_lenia(const float *state, const float *food, float *worldmap, uint8_t *frame, int batch_index, int C, int H,
+                      int W, void *stream);
+/* state: dense (B,n,H,W), channels 0..3 = RGBA; rgb = clamp(rgb,0,1) * clamp(a,0,1) (brush overlay is GUI, not drawn). */
+int b200ca_draw_nca(const float *state, float *worldmap, uint8_t *frame, int batch_index, int n, int H, int W, void *stream);
+/* Automaton.worldmap alone (automaton.py:216) for a float (3,H,W) `_worldmap` produced by any draw(): -> (W,H,3) uint8. */
+int b200ca_frame_pack_rgb(const float *worldmap, uint8_t *frame, int H, int W, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,10 @@ Reference lines followed (relative to the PyCA tree):
   nca_perception        pyca/automata/models/nca.py:306-344
   nca_live_mask         pyca/automata/models/nca.py:226-237
   nca_step              pyca/automata/models/nca.py:239-263
+  frame_u8              pyca/automata/automaton.py:209-216 (Automaton.worldmap)
+  gol_draw              pyca/automata/models/ca2d.py:117-124
+  lenia_draw            pyca/automata/models/lenia/lenia.py:481-500, macelenia.py:365-385 (single-world view)
+  nca_draw              pyca/automata/models/nca.py:74-87 (blend; brush overlay is GUI)
 """
 from __future__ import annotations
 
@@ -236,3 +240,40 @@ def nca_draw_mask(B, H, W, seed):
     ``forward`` (nca.py:256): one ``torch.rand(B,1,H,W)`` call on the CPU generator."""
     g = torch.Generator().manual_seed(seed)
     return torch.rand(B, 1, H, W, generator=g) <= 0.5
+
+
+# --------------------------------------------------------------------------- #
+# draw() / worldmap (SURVEY.md 8 f-2)
+# --------------------------------------------------------------------------- #
+def frame_u8(worldmap: torch.Tensor) -> np.ndarray:
+    """automaton.py:216: (3,H,W) float -> (W,H,3) uint8 (fp32 product, truncating cast)."""
+    return (255 * worldmap.permute(2, 1, 0)).detach().cpu().numpy().astype(dtype=np.uint8)
+
+
+def gol_draw(world, worldmap, decay_speed, highlight_color):
+    """ca2d.py:121-124: echo of the previous frame fading by decay_speed * highlight_color, plus the live cells."""
+    echo = torch.clamp(worldmap - decay_speed * highlight_color[:, None, None], min=0, max=1)
+    w = torch.as_tensor(world)
+    return torch.clamp(w[None, :, :].expand(3, -1, -1).to(dtype=torch.float) + echo, min=0, max=1)
+
+
+def lenia_draw(state, batch_index=0, food=None):
+    """lenia.py:487-500 / macelenia.py:371-385.  C == 2 shows (c0, c1, 0) (the reference concatenates a 2-plane zero
+    tensor there, which yields 4 planes; the three-plane reading of its own comment is used)."""
+    toshow = state[batch_index].clone()
+    C = toshow.shape[0]
+    if C == 1:
+        toshow = toshow.expand(3, -1, -1).clone()
+    elif C == 2:
+        toshow = torch.cat([toshow, torch.zeros_like(toshow[:1])], dim=0)
+    else:
+        toshow = toshow[:3]
+    if food is not None:
+        toshow = toshow + food[batch_index]
+    return torch.clamp(toshow, 0.0, 1.0)
+
+
+def nca_draw(state):
+    """nca.py:79-82: clamp(ARGB = state[:, :4]) then RGB * A (black background)."""
+    pic = torch.clamp(state[:, :4].squeeze(0), 0, 1)
+    return pic[:3] * pic[3:]

@@ -61,6 +61,10 @@ SIGNATURES = {
                                 c_int, c_int, c_int, c_void_p]),
     "b200ca_nca_run_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_int, c_int, c_int, c_int, c_int,
                                     c_int, c_int]),
+    "b200ca_draw_gol": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
+    "b200ca_draw_lenia": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200ca_frame_pack_rgb": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "b200ca_draw_nca": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 FRAME = 16

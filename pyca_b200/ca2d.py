@@ -167,9 +167,19 @@ class CA2D(Automaton):
         self._world = None
 
     def draw(self):
-        """ca2d.py:117-124."""
-        echo = torch.clamp(self._worldmap - self.decay_speed * self.highlight_color[:, None, None], min=0, max=1)
-        self._worldmap = torch.clamp(self.world[None, :, :].expand(3, -1, -1).to(dtype=torch.float) + echo, min=0, max=1)
+        """ca2d.py:117-124, fused: one kernel reads the packed bits and the previous `_worldmap` (the echo), rewrites
+        `_worldmap` in place and emits the (W,H,3) uint8 frame that `worldmap` returns."""
+        self._sync_to_device()
+        wm = self._worldmap
+        if not (wm.is_cuda and wm.dtype == torch.float32 and wm.is_contiguous() and tuple(wm.shape) == (3, self.h, self.w)):
+            wm = self._worldmap = wm.to(self.device, torch.float32).contiguous()
+        d = (self.decay_speed * self.highlight_color).tolist()  # fp32 product, as in the reference expression
+        fb = self._frame()
+        pw = self._packed
+        with _lib.device_guard(pw.device):
+            _lib.call("b200ca_draw_gol", _lib.ptr(pw.bits), _lib.ptr(wm), _lib.ptr(fb.dev), self.h, self.w, pw.stride,
+                      d[0], d[1], d[2], _lib.current_stream(pw.device))
+        fb.mark(wm)
 
     def name(self):
         return "2D Cellular Automaton"

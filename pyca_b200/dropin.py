@@ -35,6 +35,25 @@ class _Tracked:
         self.tensor, self.version = t, t._version
 
 
+def _fast_worldmap(base):
+    """`worldmap` (automaton.py:209-216) for a reference subclass: the float (3,H,W) `_worldmap` its own draw() left on the
+    GPU is turned into the (W,H,3) uint8 frame there and copied as bytes (3 B/cell instead of 12 + a host-side cast)."""
+    from .automaton import FrameBuffer
+
+    def worldmap(self):
+        wm = self._worldmap
+        if not (torch.is_tensor(wm) and wm.is_cuda and wm.ndim == 3 and wm.shape[0] == 3):
+            return base.worldmap.fget(self)
+        fb = getattr(self, "_b200_fb", None)
+        if fb is None or (fb.H, fb.W) != tuple(wm.shape[1:]) or fb.dev.device != wm.device:
+            fb = FrameBuffer(wm.shape[1], wm.shape[2], wm.device)
+            object.__setattr__(self, "_b200_fb", fb)
+        fb.pack(wm)
+        return fb.numpy()
+
+    return property(worldmap)
+
+
 def make_ca2d(base):
     class CA2D(base):
         __doc__ = base.__doc__
@@ -52,6 +71,8 @@ def make_ca2d(base):
             self._b200_trk.set(self.world)
 
     CA2D.__name__ = CA2D.__qualname__ = "CA2D"
+    if isinstance(getattr(base, "worldmap", None), property):
+        CA2D.worldmap = _fast_worldmap(base)
     return CA2D
 
 
@@ -141,6 +162,8 @@ def make_lenia(base):
             self.frames += 1
 
     Lenia.__name__ = Lenia.__qualname__ = "Lenia"
+    if isinstance(getattr(base, "worldmap", None), property):
+        Lenia.worldmap = _fast_worldmap(base)
     return Lenia
 
 
@@ -170,6 +193,8 @@ def make_mace(base):
             self.frames += 1
 
     MaCELenia.__name__ = MaCELenia.__qualname__ = "MaCELenia"
+    if isinstance(getattr(base, "worldmap", None), property):
+        MaCELenia.worldmap = _fast_worldmap(base)
     return MaCELenia
 
 
@@ -185,6 +210,8 @@ def make_xchan(base):
             _mace_step(self, True, float(self.alpha))
 
     MaCELeniaXChan.__name__ = MaCELeniaXChan.__qualname__ = "MaCELeniaXChan"
+    if isinstance(getattr(base, "worldmap", None), property):
+        MaCELeniaXChan.worldmap = _fast_worldmap(base)
     return MaCELeniaXChan
 
 
@@ -207,6 +234,8 @@ def make_nca(base):
             self.state = nca_step(st, self._b200_w, update_mask=mask, impl=impl)
 
     NeuralCA.__name__ = NeuralCA.__qualname__ = "NeuralCA"
+    if isinstance(getattr(base, "worldmap", None), property):
+        NeuralCA.worldmap = _fast_worldmap(base)
     return NeuralCA
 
 

@@ -240,18 +240,24 @@ class Lenia(Automaton):
         self._sync_state()
         return (self._fs.mass() / (self.h * self.w)).float()
 
+    def _draw_fused(self, batch_index=0, food=None):
+        """One kernel: framed state -> float `_worldmap` (3,H,W) + the (W,H,3) uint8 frame `worldmap` returns."""
+        self._sync_state()
+        fs = self._fs
+        wm = self._worldmap
+        if not (wm.is_cuda and wm.dtype == torch.float32 and wm.is_contiguous() and tuple(wm.shape) == (3, self.h, self.w)):
+            wm = self._worldmap = torch.empty((3, self.h, self.w), dtype=torch.float32, device=fs.device)
+        fb = self._frame()
+        with _lib.device_guard(fs.device):
+            _lib.call("b200ca_draw_lenia", _lib.ptr(fs.buf), _lib.ptr(food), _lib.ptr(wm), _lib.ptr(fb.dev), int(batch_index),
+                      fs.C, fs.H, fs.W, _lib.current_stream(fs.device))
+        fb.mark(wm)
+
     @torch.no_grad()
     def draw(self):
-        """lenia.py:481-500."""
-        assert self.state.shape[0] == 1, "Batch size must be 1 to draw"
-        toshow = self.state[0].clone()
-        if self.C == 1:
-            toshow = toshow.expand(3, -1, -1)
-        elif self.C == 2:
-            toshow = torch.cat([toshow, torch.zeros_like(toshow[:1])], dim=0)
-        else:
-            toshow = toshow[:3, :, :]
-        self._worldmap = torch.clamp(toshow, 0.0, 1.0)
+        """lenia.py:481-500 (C == 2 shows (c0, c1, 0); the kernel overlay of `display_kernel` is GUI and not drawn)."""
+        assert self._fs.B == 1, "Batch size must be 1 to draw"
+        self._draw_fused(0)
 
 
 class MaCELenia(Lenia):
@@ -313,10 +319,10 @@ class MaCELenia(Lenia):
         self._sync_state()
         return self._fs.mass().sum(dim=1)
 
+    @torch.no_grad()
     def draw(self):
-        st = self.state[self.show_batch]
-        toshow = st[:3] if self.C >= 3 else torch.cat([st, torch.zeros((3 - self.C,) + tuple(st.shape[1:]), device=st.device)], 0)
-        self._worldmap = torch.clamp(toshow, 0.0, 1.0)
+        """macelenia.py:365-385 (single-world view `show_batch`; the gridified `show_all` view is GUI)."""
+        self._draw_fused(self.show_batch)
 
 
 class MaCELeniaXChan(MaCELenia):

@@ -116,10 +116,21 @@ class NeuralCA(Automaton):
         self.state = new
         self.frames += 1
 
+    @torch.no_grad()
     def draw(self):
-        """nca.py:74-87 (without the brush overlay)."""
-        pic = torch.clamp(self.state[0, :4], 0, 1)
-        self._worldmap = pic[:3] * pic[3:]
+        """nca.py:74-87 (without the brush overlay, which needs the GUI's mouse position): RGB = clamp(rgb) * clamp(alpha),
+        one kernel writing the float `_worldmap` and the (W,H,3) uint8 frame `worldmap` returns."""
+        st = self.state
+        if not (st.is_contiguous() and st.dtype == torch.float32):
+            st = self.state = st.float().contiguous()
+        B, n, H, W = st.shape
+        wm = self._worldmap
+        if not (wm.is_cuda and wm.dtype == torch.float32 and wm.is_contiguous() and tuple(wm.shape) == (3, H, W)):
+            wm = self._worldmap = torch.empty((3, H, W), dtype=torch.float32, device=st.device)
+        fb = self._frame()
+        with _lib.device_guard(st.device):
+            _lib.call("b200ca_draw_nca", _lib.ptr(st), _lib.ptr(wm), _lib.ptr(fb.dev), 0, n, H, W, _lib.current_stream(st.device))
+        fb.mark(wm)
 
     def insert_seed(self, h, w):
         """nca.py:151-162."""

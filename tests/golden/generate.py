@@ -216,8 +216,55 @@ def gen_nca():
              state_out=out, seed=np.array(seed))
 
 
+
+
+# ------------------------------------------------------------------ draw() / worldmap
+def gen_draw():
+    """The reference's own draw() + Automaton.worldmap on seeded states: float (3,H,W) `_worldmap` and the (W,H,3) uint8
+    frame.  CA2D: three frames with two steps in between (the echo trail depends on the previous frame)."""
+    out = {}
+    H, W = 37, 70
+    torch.manual_seed(21)
+    a = REF.CA2D((H, W))
+    a.world = (torch.rand(H, W) < 0.4).to(torch.int)
+    out["gol_w0"] = a.world.to(torch.uint8)
+    out["gol_color"] = a.highlight_color
+    out["gol_decay"] = np.array(a.decay_speed, dtype=np.float64)
+    for i in range(3):
+        a.draw()
+        out[f"gol_wm{i}"] = a._worldmap.clone()
+        out[f"gol_frame{i}"] = a.worldmap
+        a.step()
+    # Lenia C=3 / C=1 and MaCE (values above 1 get clamped)
+    f = "abominable_mongolic.pt"
+    d = torch.load(os.path.join(DEMO, "demo_lenia", f), weights_only=True, map_location="cpu")
+    g = torch.Generator().manual_seed(31)
+    s3 = torch.rand(1, 3, 40, 52, generator=g) * 1.3 - 0.1
+    au = REF.Lenia((40, 52), params=REF.LeniaParams(from_file=os.path.join(DEMO, "demo_lenia", f)), state_init=s3.clone())
+    au.draw()
+    out["lenia3_state"], out["lenia3_wm"], out["lenia3_frame"] = s3, au._worldmap.clone(), au.worldmap
+    d1 = {k: (v[:, :1, :1] if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+    a1 = REF.Lenia((40, 52), num_channels=1, params=REF.LeniaParams(param_dict=d1, channels=1), state_init=s3[:, :1].clone())
+    a1.draw()
+    out["lenia1_wm"], out["lenia1_frame"] = a1._worldmap.clone(), a1.worldmap
+    fm = pick("demo_macelenia", 1)[0]
+    sm = torch.rand(1, 3, 40, 52, generator=g) * 3.0
+    am = REF.MaCELenia((40, 52), params=REF.LeniaParams(from_file=os.path.join(DEMO, "demo_macelenia", fm)), state_init=sm.clone())
+    am.draw()
+    out["mace_state"], out["mace_wm"], out["mace_frame"] = sm, am._worldmap.clone(), am.worldmap
+    # NCA: draw() = clamp(argb) blend + a brush overlay at the GUI mouse position; the mouse is parked far outside the
+    # world so the overlay is empty and `_worldmap` is the blend alone
+    an = REF.NeuralCA((24, 40), os.path.join(DEMO, "NCA_models"))
+    an.state = torch.rand(1, 16, 24, 40, generator=g) * 1.4 - 0.2
+    an.m_pos = type("P", (), {"x": -1000, "y": -1000})()
+    an.draw()
+    out["nca_state"], out["nca_wm"], out["nca_frame"] = an.state, an._worldmap.clone(), an.worldmap
+    save("draw.npz", **out)
+
+
 if __name__ == "__main__":
-    gen_gol()
-    gen_lenia_family()
-    gen_kmult()
-    gen_nca()
+    only = [a[2:] for a in sys.argv[1:] if a.startswith("--")]   # e.g. --draw regenerates draw.npz alone
+    gens = {"gol": gen_gol, "family": gen_lenia_family, "kmult": gen_kmult, "nca": gen_nca, "draw": gen_draw}
+    for name, fn in gens.items():
+        if not only or name in only:
+            fn()

@@ -105,3 +105,24 @@ def test_lenia_k_mult_2():
     assert torch.allclose(K, t(fx["K"]), atol=1e-9, rtol=0) and torch.equal(q["weights"], t(fx["weights_s"]))
     out = orc.lenia_step(t(fx["state_in"]), K, q["mu"], q["sigma"], q["weights"], float(fx["dt"]))
     assert (out - t(fx["state_out"])).abs().max().item() <= TOL
+
+
+def test_draw_oracle_matches_reference_fixture():
+    """draw() + Automaton.worldmap restatements against the reference's own frames (tests/golden/draw.npz)."""
+    fx = load_npz("draw.npz")
+    wm = torch.zeros(3, *fx["gol_w0"].shape)
+    w = fx["gol_w0"].astype(np.int32)
+    color, decay = t(fx["gol_color"]), float(fx["gol_decay"])
+    for i in range(3):
+        wm = orc.gol_draw(w, wm, decay, color)
+        assert torch.equal(wm, t(fx[f"gol_wm{i}"]))
+        assert np.array_equal(orc.frame_u8(wm), fx[f"gol_frame{i}"])
+        w = orc.gol_step(w)
+    s3 = t(fx["lenia3_state"])
+    assert torch.equal(orc.lenia_draw(s3), t(fx["lenia3_wm"]))
+    assert np.array_equal(orc.frame_u8(orc.lenia_draw(s3)), fx["lenia3_frame"])
+    assert torch.equal(orc.lenia_draw(s3[:, :1]), t(fx["lenia1_wm"]))
+    assert np.array_equal(orc.frame_u8(orc.lenia_draw(s3[:, :1])), fx["lenia1_frame"])
+    assert torch.equal(orc.lenia_draw(t(fx["mace_state"])), t(fx["mace_wm"]))
+    assert torch.equal(orc.nca_draw(t(fx["nca_state"])), t(fx["nca_wm"]))
+    assert np.array_equal(orc.frame_u8(orc.nca_draw(t(fx["nca_state"]))), fx["nca_frame"])
