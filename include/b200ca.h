@@ -115,6 +115,17 @@ int b200ca_lenia_step(const float *state_in, float *state_out, const float *Kpre
                       const float *weights, int B, int C, int k_mult, int H, int W, float dt, int mode, int row_wrap,
                       int tile_row_begin, int tile_row_end, void *stream);
 
+/* The same step with `g_arbi` growth functions (lenia.py:390-418 -> ArbitraryFunction.forward, funcgen.py:79-129): the growth of
+ * kernel pair p is the Fourier series  sum_h g_cos[p,h] cos(g_freq[p,h] u) + g_sin[p,h] sin(g_freq[p,h] u)  with
+ * g_freq = fp32(2 pi / period) * harmonic (period 2 for growth functions); rescale_on: followed by the reference's global
+ * rescale (v - min) / (max - min + 1e-8) * (hi - lo) + lo with min/max over the whole (H,W) plane of each pair (costs a
+ * second pass of the convolution; g_stats = 2 floats per pair of device scratch); clip_on: then max(v, clip_min).
+ * g_cos/g_sin/g_freq: (B, C*k_mult, C, n_harmonics) fp32 device.  Direct path only. */
+int b200ca_lenia_step_garbi(const float *state_in, float *state_out, const float *Kprep, const float *weights, const float *g_cos,
+                            const float *g_sin, const float *g_freq, int n_harmonics, int rescale_on, float rescale_lo,
+                            float rescale_hi, int clip_on, float clip_min, float *g_stats, int B, int C, int k_mult, int H, int W,
+                            float dt, int mode, int row_wrap, void *stream);
+
 /* FFT path of the same operator (row FFT x column-direct hybrid, see pyca_b200/csrc/lenia_fft.cu): identical
  * arguments and semantics to b200ca_lenia_step; supported when H is even (>= 32) and W >= 64.  The x direction is an
  * exact periodic transform when W is 256, 1024 or 4096, overlap-save segments otherwise.

@@ -22,6 +22,7 @@ Reference lines followed (relative to the PyCA tree):
   kernel_fft            pyca/automata/models/lenia/lenia.py:364-380
   fft_conv              pyca/automata/models/lenia/lenia.py:453-469
   growth                pyca/automata/models/lenia/lenia.py:419-428
+  growth_arbi           pyca/automata/models/lenia/lenia.py:390-418 + lenia/funcgen.py:79-129 (g_arbi Fourier growth)
   lenia_step            pyca/automata/models/lenia/lenia.py:430-451
   mace_affinity         pyca/automata/models/lenia/macelenia.py:122-159 (food off)
   mace_step             pyca/automata/models/lenia/macelenia.py:89-120
@@ -138,19 +139,44 @@ def growth(U, mu, sigma):
     return 2 * torch.exp(-((U - m) ** 2 / s**2) / 2) - 1
 
 
-def lenia_affinity(state, K, mu, sigma, weights, Kf=None):
-    """Weighted source-sum of growths: (B,C,H,W) (lenia.py:436-446 / macelenia.py:144-150)."""
+def growth_arbi(U, g_coeffs, g_harmonics, g_rescale=None, g_clip=None):
+    """g_arbi growth (lenia.py:390-418): ArbitraryFunction.forward (funcgen.py:79-129) on the range (0, 2), one function
+    per (b, i*k_mult+m, j) plane; `g_rescale` = global min/max rescale over each plane, `g_clip` = lower clip.
+    U (B,CK,C,H,W); g_coeffs (B,CK,C,2*nh) as (cos,sin) pairs; g_harmonics (B,CK,C,nh)."""
+    B, CK, C, H, W = U.shape
+    n = B * CK * C
+    co = g_coeffs.reshape(n, -1, 2)
+    harm = g_harmonics.reshape(n, -1)
+    ranges = torch.tensor([0.0, 2.0])[None, :].expand(n, -1)
+    shifts, period = ranges[:, 0], ranges[:, 1] - ranges[:, 0]
+    x = U.reshape(n, 1, -1)
+    interior = 2 * torch.pi / period[:, None, None] * harm[..., None] * (x - shifts[:, None, None])
+    values = torch.sum(co[:, :, 0][..., None] * torch.cos(interior) + co[:, :, 1][..., None] * torch.sin(interior), dim=1)
+    if g_rescale is not None:
+        mn, _ = values.min(dim=-1, keepdim=True)
+        mx, _ = values.max(dim=-1, keepdim=True)
+        values = (values - mn) / (mx - mn + 1e-8)
+        values = values * (g_rescale[1] - g_rescale[0]) + g_rescale[0]
+    if g_clip is not None:
+        values[values < g_clip] = g_clip
+    return values.reshape(B, CK, C, H, W)
+
+
+def lenia_affinity(state, K, mu, sigma, weights, Kf=None, garbi=None):
+    """Weighted source-sum of growths: (B,C,H,W) (lenia.py:436-446 / macelenia.py:144-150).
+    garbi = (g_coeffs, g_harmonics, g_rescale, g_clip) replaces the Gaussian growth by the Fourier one."""
     B, C, H, W = state.shape
     k_mult = K.shape[1] // C
     if Kf is None:
         Kf = kernel_fft(K, H, W)
     U = fft_conv(state, Kf, k_mult)
-    return (growth(U, mu, sigma) * weights[..., None, None]).sum(dim=1)
+    G = growth(U, mu, sigma) if garbi is None else growth_arbi(U, *garbi)
+    return (G * weights[..., None, None]).sum(dim=1)
 
 
-def lenia_step(state, K, mu, sigma, weights, dt=0.1, Kf=None):
+def lenia_step(state, K, mu, sigma, weights, dt=0.1, Kf=None, garbi=None):
     """lenia.py:430-451."""
-    dx = lenia_affinity(state, K, mu, sigma, weights, Kf)
+    dx = lenia_affinity(state, K, mu, sigma, weights, Kf, garbi)
     return torch.clamp(state + dt * dx, 0, 1)
 
 
@@ -170,9 +196,9 @@ def mace_redistribute(state, aff, b):
     return (E[:, :, None] * give).sum(dim=2)
 
 
-def mace_step(state, K, mu, sigma, weights, b=8.0, Kf=None):
+def mace_step(state, K, mu, sigma, weights, b=8.0, Kf=None, garbi=None):
     """macelenia.py:72-120 with food off.  Returns (new_state, Aff)."""
-    aff = lenia_affinity(state, K, mu, sigma, weights, Kf)
+    aff = lenia_affinity(state, K, mu, sigma, weights, Kf, garbi)
     return mace_redistribute(state, aff, b), aff
 
 
@@ -185,9 +211,9 @@ def xchan_mix(state, aff, b, alpha):
     return state - (state - target) * alpha
 
 
-def xchan_step(state, K, mu, sigma, weights, b=6.0, alpha=0.03, Kf=None):
+def xchan_step(state, K, mu, sigma, weights, b=6.0, alpha=0.03, Kf=None, garbi=None):
     """mace_lenia_xchan.py:59-66 with food off."""
-    new, aff = mace_step(state, K, mu, sigma, weights, b, Kf)
+    new, aff = mace_step(state, K, mu, sigma, weights, b, Kf, garbi)
     return xchan_mix(new, aff, b, alpha)
 
 

@@ -36,6 +36,9 @@ SIGNATURES = {
     "b200ca_lenia_tile_rows": (c_int, [c_int, c_int, c_int, c_int]),
     "b200ca_lenia_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                   c_int, c_float, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200ca_lenia_step_garbi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
+                                        c_float, c_int, c_float, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+                                        c_int, c_void_p]),
     "b200ca_lenia_fft_length": (c_int, [c_int, c_int]),
     "b200ca_lenia_fft_kernel_elems": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
     "b200ca_lenia_fft_workspace_elems": (c_int64, [c_int, c_int, c_int, c_int, c_int]),

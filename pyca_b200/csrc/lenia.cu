@@ -44,7 +44,25 @@ struct LeniaArgs {
     float dt;
     int mode, row_wrap;
     int tile_row0;  // first tile row of this launch
+    // g_arbi growth (lenia.py:390-418, funcgen.py:79-129): a Fourier series of u per kernel pair instead of the Gaussian
+    int gmode;                        // G_GAUSS, or (GARBI kernels) G_SERIES / G_RESCALE / G_STATS
+    int nh;                           // harmonics per function
+    const float *gcos, *gsin, *gfreq; // (B*NS*C, nh): cos / sin coefficients, fp32(2 pi / period) * harmonic
+    float *gstats;                    // (B*NS*C, 2): min, max of the raw series over the plane (global rescale)
+    float gr0, gspan;                 // rescale target: value * (r1 - r0) + r0
+    float gclip;
+    int gclip_on;
 };
+enum { G_GAUSS = 0, G_SERIES = 1, G_RESCALE = 2, G_STATS = 3 };
+
+__device__ __forceinline__ void atomic_min_f32(float *p, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int *>(p), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned *>(p), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f32(float *p, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int *>(p), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned *>(p), __float_as_uint(v));
+}
 
 // writes v at interior cell (y, x) of a framed plane and at its periodic images inside the frame
 __device__ __forceinline__ void store_mirrors(float *__restrict__ plane, int H, int W, int pitch, int y, int x, float v,
@@ -66,7 +84,9 @@ __device__ __forceinline__ void store_mirrors(float *__restrict__ plane, int H, 
         }
 }
 
-template <int NW>
+// GARBI = true: the growth of a pair is its Fourier series (g_arbi); kept out of the Gaussian instantiation, whose register
+// allocation and code are what the direct path was tuned with.
+template <int NW, bool GARBI>
 __global__ void __launch_bounds__(32 * NW) lenia_conv_kernel(const CUtensorMap *__restrict__ tmap, const LeniaArgs a) {
     constexpr int TH = 8 * NW;
     constexpr int TROWS = TH + 2 * R;
@@ -164,19 +184,65 @@ __global__ void __launch_bounds__(32 * NW) lenia_conv_kernel(const CUtensorMap *
 
         // growth + weighted source sum (lenia.py:423-426, :444-446)
         const int pidx = (b * a.NS + i) * a.C + j;
-        const float mu = __ldg(a.mu + pidx), sg = __ldg(a.sigma + pidx), wt = __ldg(a.weights + pidx);
-        const float sg2 = sg * sg;
+        if (!GARBI) {
+            const float mu = __ldg(a.mu + pidx), sg = __ldg(a.sigma + pidx), wt = __ldg(a.weights + pidx);
+            const float sg2 = sg * sg;
 #pragma unroll
-        for (int k = 0; k < STRIP; ++k) {
-            float d = acc[k] - mu;
-            float z = __fdiv_rn(d * d, sg2) * 0.5f;
-            float g = 2.f * expf(-z) - 1.f;
-            dxs[k] += g * wt;
+            for (int k = 0; k < STRIP; ++k) {
+                float d = acc[k] - mu;
+                float z = __fdiv_rn(d * d, sg2) * 0.5f;
+                float g = 2.f * expf(-z) - 1.f;
+                dxs[k] += g * wt;
+            }
+        } else {
+            // values = sum_h cos_h cos(f_h u) + sin_h sin(f_h u);  optional (v - min) / (max - min + 1e-8) * (r1 - r0) + r0 with
+            // the plane-wide min / max of the raw series (funcgen.py:99-117), optional clip from below
+            const float wt = __ldg(a.weights + pidx);
+            const float *gc = a.gcos + (size_t)pidx * a.nh, *gs = a.gsin + (size_t)pidx * a.nh, *gf = a.gfreq + (size_t)pidx * a.nh;
+            float lo = 0.f, den = 1.f;
+            if (a.gmode == G_RESCALE) {
+                lo = a.gstats[2 * pidx];
+                den = a.gstats[2 * pidx + 1] - lo + 1e-8f;
+            }
+            float vmin = __int_as_float(0x7f800000), vmax = __int_as_float(0xff800000);
+            const bool row_ok = (y0 + yl) < a.H;
+#pragma unroll 1
+            for (int k = 0; k < STRIP; ++k) {
+                const float u = acc[k];
+                float v = 0.f;
+                for (int h = 0; h < a.nh; ++h) {
+                    float sn, cs;
+                    sincosf(__ldg(gf + h) * u, &sn, &cs);
+                    v += __ldg(gc + h) * cs + __ldg(gs + h) * sn;
+                }
+                if (a.gmode == G_STATS) {
+                    if (row_ok && x0 + tx * STRIP + k < a.W) {
+                        vmin = fminf(vmin, v);
+                        vmax = fmaxf(vmax, v);
+                    }
+                    continue;
+                }
+                if (a.gmode == G_RESCALE) v = __fdiv_rn(v - lo, den) * a.gspan + a.gr0;
+                if (a.gclip_on) v = fmaxf(v, a.gclip);
+                dxs[k] += v * wt;
+            }
+            if (a.gmode == G_STATS) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+                    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+                }
+                if (lane == 0 && vmin <= vmax) {
+                    atomic_min_f32(a.gstats + 2 * pidx, vmin);
+                    atomic_max_f32(a.gstats + 2 * pidx + 1, vmax);
+                }
+            }
         }
         __syncthreads();  // everyone is done with tile[s] / taps[s] before they are refilled
     }
 
     // epilogue
+    if (GARBI && a.gmode == G_STATS) return;  // statistics pass: nothing is stored
     const int y = y0 + yl;
     if (y >= a.H) return;
     const int xb = x0 + tx * STRIP;
@@ -239,7 +305,15 @@ __global__ void lenia_prepare_kernel_kernel(const float *__restrict__ K, float *
     }
 }
 
-template <int NW>
+__global__ void garbi_stats_init_kernel(float *stats, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        stats[2 * i] = __int_as_float(0x7f800000);      // +inf
+        stats[2 * i + 1] = __int_as_float(0xff800000);  // -inf
+    }
+}
+
+template <int NW, bool GARBI>
 static int launch_conv(const CUtensorMap *tm, const LeniaArgs &a, int tiles_y, cudaStream_t st) {
     constexpr int TH = 8 * NW;
     constexpr size_t smem = (size_t)2 * (((TH + 2 * R) * SROW + 31) / 32 * 32) * 4 + 2 * KPREP * 4 + 64;
@@ -247,11 +321,11 @@ static int launch_conv(const CUtensorMap *tm, const LeniaArgs &a, int tiles_y, c
     int dev = 0;
     B200CA_CUDA(cudaGetDevice(&dev));
     if (!attr_set[dev & 63]) {
-        B200CA_CUDA(cudaFuncSetAttribute(lenia_conv_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200CA_CUDA(cudaFuncSetAttribute(lenia_conv_kernel<NW, GARBI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[dev & 63] = true;
     }
     dim3 grid(ceil_div(a.W, TW), tiles_y, a.B * a.C);
-    lenia_conv_kernel<NW><<<grid, 32 * NW, smem, st>>>(tm, a);
+    lenia_conv_kernel<NW, GARBI><<<grid, 32 * NW, smem, st>>>(tm, a);
     B200CA_LAUNCH_CHECK("lenia_conv_kernel");
     return 0;
 }
@@ -313,14 +387,13 @@ extern "C" int b200ca_lenia_prepare_kernel(const float *K, float *Kprep, int B, 
 
 extern "C" int b200ca_lenia_tile_rows(int H, int W, int B, int C) { return 8 * choose_nw(H, W, B, C); }
 
-extern "C" int b200ca_lenia_step(const float *state_in, float *state_out, const float *Kprep, const float *mu, const float *sigma,
-                                 const float *weights, int B, int C, int k_mult, int H, int W, float dt, int mode, int row_wrap,
-                                 int tile_row_begin, int tile_row_end, void *stream) {
-    B200CA_REQUIRE(state_in && state_out && Kprep && mu && sigma && weights, "lenia_step: null pointer");
-    B200CA_REQUIRE(state_in != state_out, "lenia_step: in-place update is not supported");
+static int lenia_step_impl(LeniaArgs a, int B, int C, int k_mult, int H, int W, int tile_row_begin, int tile_row_end,
+                           void *stream) {
+    B200CA_REQUIRE(a.state_in && a.out && a.kprep && a.weights, "lenia_step: null pointer");
+    B200CA_REQUIRE(a.state_in != a.out, "lenia_step: in-place update is not supported");
     B200CA_REQUIRE(B >= 1 && C >= 1 && k_mult >= 1 && H >= F && W >= F, "lenia_step: need H,W >= %d (got %dx%d)", F, H, W);
     B200CA_REQUIRE((long long)B * C <= 65535, "lenia_step: B*C too large");
-    B200CA_REQUIRE(mode == B200CA_MODE_LENIA || mode == B200CA_MODE_AFF, "lenia_step: bad mode %d", mode);
+    B200CA_REQUIRE(a.mode == B200CA_MODE_LENIA || a.mode == B200CA_MODE_AFF, "lenia_step: bad mode %d", a.mode);
     const int nw = choose_nw(H, W, B, C);
     const int TH = 8 * nw;
     const int tiles_y_all = ceil_div(H, TH);
@@ -328,13 +401,6 @@ extern "C" int b200ca_lenia_step(const float *state_in, float *state_out, const 
     B200CA_REQUIRE(tile_row_begin >= 0 && tile_row_end <= tiles_y_all && tile_row_begin <= tile_row_end,
                    "lenia_step: tile row range [%d,%d) outside [0,%d)", tile_row_begin, tile_row_end, tiles_y_all);
     if (tile_row_begin == tile_row_end) return 0;
-    LeniaArgs a;
-    a.state_in = state_in;
-    a.out = state_out;
-    a.kprep = Kprep;
-    a.mu = mu;
-    a.sigma = sigma;
-    a.weights = weights;
     a.B = B;
     a.C = C;
     a.NS = C * k_mult;
@@ -342,20 +408,79 @@ extern "C" int b200ca_lenia_step(const float *state_in, float *state_out, const 
     a.H = H;
     a.W = W;
     a.pitch = b200ca_frame_pitch(W);
-    a.dt = dt;
-    a.mode = mode;
-    a.row_wrap = row_wrap;
     a.tile_row0 = tile_row_begin;
     const CUtensorMap *tm = nullptr;
     const uint64_t rows = (uint64_t)H + 2 * F;
-    int rc = get_tensor_map_3d(&tm, state_in, (uint64_t)a.pitch, rows, (uint64_t)B * C, (uint64_t)a.pitch, (uint64_t)a.pitch * rows,
+    int rc = get_tensor_map_3d(&tm, a.state_in, (uint64_t)a.pitch, rows, (uint64_t)B * C, (uint64_t)a.pitch, (uint64_t)a.pitch * rows,
                                SROW, (uint32_t)(TH + 2 * R));
     if (rc) return rc;
     const int ty = tile_row_end - tile_row_begin;
     cudaStream_t st = as_stream(stream);
-    switch (nw) {
-        case 2: return launch_conv<2>(tm, a, ty, st);
-        case 4: return launch_conv<4>(tm, a, ty, st);
-        default: return launch_conv<8>(tm, a, ty, st);
+    if (a.gmode == G_GAUSS) {
+        switch (nw) {
+            case 2: return launch_conv<2, false>(tm, a, ty, st);
+            case 4: return launch_conv<4, false>(tm, a, ty, st);
+            default: return launch_conv<8, false>(tm, a, ty, st);
+        }
     }
+    switch (nw) {
+        case 2: return launch_conv<2, true>(tm, a, ty, st);
+        case 4: return launch_conv<4, true>(tm, a, ty, st);
+        default: return launch_conv<8, true>(tm, a, ty, st);
+    }
+}
+
+extern "C" int b200ca_lenia_step(const float *state_in, float *state_out, const float *Kprep, const float *mu, const float *sigma,
+                                 const float *weights, int B, int C, int k_mult, int H, int W, float dt, int mode, int row_wrap,
+                                 int tile_row_begin, int tile_row_end, void *stream) {
+    B200CA_REQUIRE(mu && sigma, "lenia_step: null pointer");
+    LeniaArgs a = {};
+    a.state_in = state_in;
+    a.out = state_out;
+    a.kprep = Kprep;
+    a.mu = mu;
+    a.sigma = sigma;
+    a.weights = weights;
+    a.dt = dt;
+    a.mode = mode;
+    a.row_wrap = row_wrap;
+    a.gmode = G_GAUSS;
+    return lenia_step_impl(a, B, C, k_mult, H, W, tile_row_begin, tile_row_end, stream);
+}
+
+extern "C" int b200ca_lenia_step_garbi(const float *state_in, float *state_out, const float *Kprep, const float *weights,
+                                       const float *g_cos, const float *g_sin, const float *g_freq, int n_harmonics, int rescale_on,
+                                       float rescale_lo, float rescale_hi, int clip_on, float clip_min, float *g_stats, int B, int C,
+                                       int k_mult, int H, int W, float dt, int mode, int row_wrap, void *stream) {
+    B200CA_REQUIRE(g_cos && g_sin && g_freq && n_harmonics >= 1 && n_harmonics <= 64, "lenia_step_garbi: bad growth series");
+    B200CA_REQUIRE(!rescale_on || g_stats, "lenia_step_garbi: the global rescale needs the g_stats scratch (2 floats per kernel pair)");
+    LeniaArgs a = {};
+    a.state_in = state_in;
+    a.out = state_out;
+    a.kprep = Kprep;
+    a.weights = weights;
+    a.dt = dt;
+    a.mode = mode;
+    a.row_wrap = row_wrap;
+    a.nh = n_harmonics;
+    a.gcos = g_cos;
+    a.gsin = g_sin;
+    a.gfreq = g_freq;
+    a.gstats = g_stats;
+    a.gr0 = rescale_lo;
+    a.gspan = rescale_hi - rescale_lo;
+    a.gclip = clip_min;
+    a.gclip_on = clip_on;
+    if (rescale_on) {
+        // pass 1: the same convolution, reduced to the min / max of every pair's raw series over its plane; pass 2 recomputes
+        // the (bit-identical) values and rescales them
+        const int npairs = B * C * k_mult * C;
+        garbi_stats_init_kernel<<<ceil_div(npairs, 128), 128, 0, as_stream(stream)>>>(g_stats, npairs);
+        B200CA_LAUNCH_CHECK("garbi_stats_init_kernel");
+        a.gmode = G_STATS;
+        const int rc = lenia_step_impl(a, B, C, k_mult, H, W, 0, 0, stream);
+        if (rc) return rc;
+    }
+    a.gmode = rescale_on ? G_RESCALE : G_SERIES;
+    return lenia_step_impl(a, B, C, k_mult, H, W, 0, 0, stream);
 }

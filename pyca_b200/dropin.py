@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from .ca2d import PackedWorld
-from .lenia import FramedState
+from .lenia import FramedState, conv_garbi, garbi_tables
 from .nca import NCAWeights, nca_step
 
 F = _lib.FRAME
@@ -90,14 +90,17 @@ class _LeniaEngine:
         self.L = _lib.lib()
 
     def prepare(self, owner):
-        key = (id(owner.k), owner.k._version, id(owner.mu), id(owner.sigma), id(owner.weights))
+        key = (id(owner.k), owner.k._version, id(getattr(owner, "mu", None)), id(getattr(owner, "sigma", None)), id(owner.weights),
+               id(getattr(owner, "params", None)))
         if key == self.key:
             return
         fs = self.fs
         dev = fs.device
         self.k_mult = int(getattr(owner, "k_mult", 1))
+        self.garbi = None
         if getattr(owner, "g_arbi", False):
-            raise _lib.B200CAError("g_arbi growth functions are not built yet (SURVEY.md 8f-3)")
+            pd = {k: (v.detach().to(dev) if torch.is_tensor(v) else v) for k, v in owner.params.param_dict.items()}
+            self.garbi = garbi_tables(pd, fs.B, fs.C, self.k_mult)
         self.K = owner.k.detach().to(dev, torch.float32).contiguous()
         self.mu = owner.mu.detach().to(dev, torch.float32).contiguous()
         self.sigma = owner.sigma.detach().to(dev, torch.float32).contiguous()
@@ -107,7 +110,7 @@ class _LeniaEngine:
             self.kprep = torch.empty(self.L.b200ca_lenia_kprep_elems(fs.B, fs.C, self.k_mult), dtype=torch.float32, device=dev)
             _lib.call("b200ca_lenia_prepare_kernel", _lib.ptr(self.K), _lib.ptr(self.kprep), fs.B, fs.C, self.k_mult, ks,
                       _lib.current_stream(dev))
-            self.use_fft = self.L.b200ca_lenia_fft_length(fs.H, fs.W) > 0
+            self.use_fft = self.L.b200ca_lenia_fft_length(fs.H, fs.W) > 0 and self.garbi is None
             if self.use_fft:
                 self.kfft = torch.empty(self.L.b200ca_lenia_fft_kernel_elems(fs.B, fs.C, self.k_mult, fs.H, fs.W), dtype=torch.float32,
                                         device=dev)
@@ -125,7 +128,9 @@ class _LeniaEngine:
         fs = self.fs
         with torch.cuda.device(fs.device):
             st = _lib.current_stream(fs.device)
-            if self.use_fft:
+            if self.garbi is not None:
+                conv_garbi(fs, dst, self.kprep, self.weights, self.garbi, self.k_mult, dt, mode)
+            elif self.use_fft:
                 _lib.call("b200ca_lenia_step_fft", _lib.ptr(fs.buf), _lib.ptr(dst), _lib.ptr(self.kfft), _lib.ptr(self.mu),
                           _lib.ptr(self.sigma), _lib.ptr(self.weights), _lib.ptr(self.ws), fs.B, fs.C, self.k_mult, fs.H, fs.W,
                           float(dt), mode, 1, st)

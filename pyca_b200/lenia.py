@@ -29,6 +29,37 @@ from .lenia_params import LeniaParams, compute_kernel
 F = _lib.FRAME
 
 
+def garbi_tables(p, B, C, k_mult):
+    """Growth functions as Fourier series (lenia.py:390-418): coefficient tables for b200ca_lenia_step_garbi.  The argument
+    of harmonic h is  (2 pi / period) * h * (u - 0)  on the period (0, 2), built in fp32 in the reference's order of
+    operations (funcgen.py:99-104).  `p`: parameter dict with g_coeffs (B,C*k_mult,C,2*nh) [, g_harmonics, g_rescale, g_clip]."""
+    if "g_coeffs" not in p:
+        raise _lib.B200CAError("g_coeffs not in params, but g_arbi is True")
+    n = B * C * k_mult * C
+    co = p["g_coeffs"].float().reshape(n, -1, 2)
+    nh = co.shape[1]
+    if "g_harmonics" in p and p["g_harmonics"] is not None:
+        harm = p["g_harmonics"].float().reshape(n, nh)
+    else:
+        harm = torch.arange(nh, device=co.device).float()[None].expand(n, -1)
+    period = torch.full((n, 1), 2.0, device=co.device)
+    freq = (2 * torch.pi / period * harm).contiguous()
+    rescale, clip = p.get("g_rescale"), p.get("g_clip")
+    return {"cos": co[:, :, 0].contiguous(), "sin": co[:, :, 1].contiguous(), "freq": freq, "nh": nh,
+            "rescale": None if rescale is None else (float(rescale[0]), float(rescale[1])),
+            "clip": None if clip is None else float(clip),
+            "stats": torch.zeros((n, 2), dtype=torch.float32, device=co.device)}
+
+
+def conv_garbi(fs, dst, kprep, weights, g, k_mult, dt, mode):
+    """b200ca_lenia_step_garbi on a FramedState (direct path; two passes when the growth is globally rescaled)."""
+    rs, cl = g["rescale"], g["clip"]
+    _lib.call("b200ca_lenia_step_garbi", _lib.ptr(fs.buf), _lib.ptr(dst), _lib.ptr(kprep), _lib.ptr(weights), _lib.ptr(g["cos"]),
+              _lib.ptr(g["sin"]), _lib.ptr(g["freq"]), g["nh"], 0 if rs is None else 1, 0.0 if rs is None else rs[0],
+              0.0 if rs is None else rs[1], 0 if cl is None else 1, 0.0 if cl is None else cl, _lib.ptr(g["stats"]), fs.B, fs.C,
+              k_mult, fs.H, fs.W, float(dt), mode, 1, _lib.current_stream(fs.device))
+
+
 class FramedState:
     """Two framed (B,C,H,W) fp32 device buffers with ping-pong and an interior view."""
 
@@ -181,17 +212,21 @@ class Lenia(Automaton):
         self.k_mult = p.get("k_mult", 1)
         self.g_arbi = bool(p.get("g_arbi", False))
         self.k_arbi = bool(p.get("k_arbi", False))
-        if self.g_arbi:
-            raise _lib.B200CAError("g_arbi (Fourier growth functions) is not built yet (SURVEY.md 8f-3)")
-        self.mu = p["mu"].float().contiguous()
-        self.sigma = p["sigma"].float().contiguous()
         self.weights = p["weights"].float().contiguous()
+        exp_shape = (self.batch, self.C * self.k_mult, self.C)
+        if tuple(self.weights.shape) != exp_shape:
+            raise _lib.B200CAError(f"weights shape {tuple(self.weights.shape)} != {exp_shape}")
+        # files with Fourier growth functions may carry no mu / sigma at all
+        self.mu = p["mu"].float().contiguous() if "mu" in p else torch.zeros(exp_shape, device=self.device)
+        self.sigma = p["sigma"].float().contiguous() if "sigma" in p else torch.ones(exp_shape, device=self.device)
         for key in ("beta", "mu_k", "sigma_k"):
             if key in p:
                 setattr(self, key, p[key])
-        exp_shape = (self.batch, self.C * self.k_mult, self.C)
         if tuple(self.mu.shape) != exp_shape:
             raise _lib.B200CAError(f"mu shape {tuple(self.mu.shape)} != {exp_shape}")
+        self._garbi = None
+        if self.g_arbi:
+            self._garbi = garbi_tables(p, self.batch, self.C, self.k_mult)
         self.k = compute_kernel(self.params, self.C).float().contiguous()  # (B, C*k_mult, C, ks, ks)
         L = _lib.lib()
         n = L.b200ca_lenia_kprep_elems(self.batch, self.C, self.k_mult)
@@ -204,7 +239,7 @@ class Lenia(Automaton):
         fft_ok = L.b200ca_lenia_fft_length(self.h, self.w) > 0
         if self.conv_path == "fft" and not fft_ok:
             raise _lib.B200CAError(f"conv_path='fft' is not supported for a {self.h}x{self.w} world (H even >= 32, W >= 64)")
-        self.use_fft = fft_ok and self.conv_path in ("fft", "auto")
+        self.use_fft = fft_ok and self.conv_path in ("fft", "auto") and not self.g_arbi  # Fourier growth: direct path only
         if self.use_fft:
             self._kfft = torch.empty(L.b200ca_lenia_fft_kernel_elems(self.batch, self.C, self.k_mult, self.h, self.w),
                                      dtype=torch.float32, device=self.device)
@@ -218,7 +253,9 @@ class Lenia(Automaton):
     def _conv(self, dst: torch.Tensor, mode: int):
         fs = self._fs
         with _lib.device_guard(fs.device):
-            if self.use_fft:
+            if self._garbi is not None:
+                conv_garbi(fs, dst, self._kprep, self.weights, self._garbi, self.k_mult, self.dt, mode)
+            elif self.use_fft:
                 _lib.call("b200ca_lenia_step_fft", _lib.ptr(fs.buf), _lib.ptr(dst), _lib.ptr(self._kfft), _lib.ptr(self.mu),
                           _lib.ptr(self.sigma), _lib.ptr(self.weights), _lib.ptr(self._fft_ws), fs.B, fs.C, self.k_mult, fs.H, fs.W,
                           float(self.dt), mode, 1, _lib.current_stream(fs.device))

@@ -262,9 +262,66 @@ def gen_draw():
     save("draw.npz", **out)
 
 
+# ------------------------------------------------------------------ g_arbi growth functions
+def _raw_dict(d):
+    """every entry of a parameter file as numpy under the key p_<name> (tuples -> arrays, None -> nan)."""
+    out = {}
+    for k, v in d.items():
+        if k == "state":
+            continue
+        if v is None:
+            v = np.nan
+        out["p_" + k] = np_(v) if isinstance(v, torch.Tensor) else np.asarray(v, dtype=np.float64)
+    return out
+
+
+def gen_garbi():
+    """Fourier-series growth functions (lenia.py:390-418, funcgen.py:79-129): the three demo_data files that use them
+    (global min/max rescale on two of them, a k_arbi kernel on one) + a synthetic Lenia case with a clip."""
+    H, W = 48, 64
+    cases = [("demo_macelenia", "underweight_skagway", REF.MaCELenia, 1),
+             ("demo_macelenia_xchan", "inaesthetic_maupassant", REF.MaCELeniaXChan, 2),
+             ("demo_macelenia_xchan", "unsuspected_lanthanotidae", REF.MaCELeniaXChan, 2)]
+    for ci, (folder, name, cls, family) in enumerate(cases):
+        path = os.path.join(DEMO, folder, name + ".pt")
+        d = torch.load(path, weights_only=True, map_location="cpu")
+        g = torch.Generator().manual_seed(2000 + ci)
+        s0 = torch.rand(1, 3, H, W, generator=g) * (torch.rand(1, 3, H, W, generator=g) < 0.6)
+        auto = cls((H, W), params=REF.LeniaParams(from_file=path), state_init=s0.clone())
+        if family == 2 and "alpha" in d:
+            auto.alpha = float(d["alpha"])
+        assert auto.g_arbi
+        aff = auto._compute_affinity()
+        K, w_s = auto.k.clone(), auto.weights.clone()
+        auto.step()
+        rs = d.get("g_rescale")
+        save(f"garbi_{name}.npz", state_in=s0, state_out=auto.state, aff=aff, K=K, weights_s=w_s, g_coeffs=d["g_coeffs"],
+             g_harmonics=d["g_harmonics"], g_rescale=np.array(rs if rs is not None else [np.nan, np.nan], dtype=np.float64),
+             g_clip=np.array(np.nan if d.get("g_clip") is None else d["g_clip"], dtype=np.float64), family=np.array(family),
+             b=np.array(float(auto.b)), alpha_used=np.array(float(getattr(auto, "alpha", 0.0))), k_size=np.array(d["k_size"]),
+             **_raw_dict(d))
+    # plain Lenia, C = 2, ring kernels + Fourier growth with rescale and clip
+    torch.manual_seed(9)
+    C = 2
+    d = {"beta": torch.rand(1, C, C, 3), "mu_k": torch.rand(1, C, C, 3), "sigma_k": 0.05 + 0.2 * torch.rand(1, C, C, 3),
+         "weights": torch.rand(1, C, C), "k_size": 31, "k_mult": 1, "num_channels": C, "g_arbi": True, "k_arbi": False,
+         "g_coeffs": torch.randn(1, C, C, 8), "g_harmonics": torch.tensor([0.0, 1.0, 2.0, 3.0]).expand(1, C, C, 4).clone(),
+         "g_rescale": (-1.0, 1.0), "g_clip": -0.5}
+    g = torch.Generator().manual_seed(3)
+    s0 = torch.rand(1, C, 40, 72, generator=g)
+    raw = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+    a = REF.Lenia((40, 72), num_channels=C, params=REF.LeniaParams(param_dict=dict(d), channels=C), state_init=s0.clone())
+    assert a.g_arbi
+    K, w_s = a.k.clone(), a.weights.clone()
+    a.step()
+    save("garbi_lenia_synth.npz", state_in=s0, state_out=a.state, aff=np.zeros(0, np.float32), K=K, weights_s=w_s,
+         g_coeffs=raw["g_coeffs"], g_harmonics=raw["g_harmonics"], g_rescale=np.array([-1.0, 1.0]), g_clip=np.array(-0.5),
+         family=np.array(0), b=np.array(0.0), alpha_used=np.array(0.0), k_size=np.array(31), dt=np.array(a.dt), **_raw_dict(raw))
+
+
 if __name__ == "__main__":
     only = [a[2:] for a in sys.argv[1:] if a.startswith("--")]   # e.g. --draw regenerates draw.npz alone
-    gens = {"gol": gen_gol, "family": gen_lenia_family, "kmult": gen_kmult, "nca": gen_nca, "draw": gen_draw}
+    gens = {"gol": gen_gol, "family": gen_lenia_family, "kmult": gen_kmult, "nca": gen_nca, "draw": gen_draw, "garbi": gen_garbi}
     for name, fn in gens.items():
         if not only or name in only:
             fn()

@@ -293,3 +293,64 @@ def test_k_mult_2_vs_oracle(path):
     m.step()
     refm = orc.xchan_step(s0, K, q["mu"], q["sigma"], q["weights"], 6.0, 0.03)
     assert (m.state.cpu() - refm).abs().max().item() <= TOL
+
+
+@pytest.mark.parametrize("name", ["underweight_skagway", "inaesthetic_maupassant", "unsuspected_lanthanotidae", "lenia_synth"])
+def test_garbi_growth_golden(name):
+    """g_arbi Fourier growth functions: the three demo_data files that use them + a synthetic Lenia case,
+    against the reference's own step (tests/golden/garbi_*.npz).  Built from the raw parameter file, so the k_arbi kernel
+    construction, the coefficient tables and the two-pass global rescale are all on the tested path."""
+    import pyca_b200
+    from tests.util import garbi_case, raw_param_dict
+
+    fx, garbi = garbi_case(name)
+    s0 = t(fx["state_in"])
+    C, H, W = s0.shape[1:]
+    fam = int(fx["family"])
+    params = pyca_b200.LeniaParams(param_dict=raw_param_dict(fx), channels=C)
+    cls = [pyca_b200.Lenia, pyca_b200.MaCELenia, pyca_b200.MaCELeniaXChan][fam]
+    kw = {"num_channels": C, "params": params, "state_init": s0, "device": "cuda"}
+    a = cls((H, W), **kw)
+    assert a.g_arbi and not a.use_fft
+    assert (a.k.cpu() - t(fx["K"])).abs().max().item() <= 1e-6
+    if fam == 2:
+        a.alpha = float(fx["alpha_used"])
+    a.step()
+    # Steep Fourier growth functions amplify fp32 rounding of U (and MaCE's exp(b*Aff) amplifies it again): on
+    # underweight_skagway the REFERENCE's own fp32 step is 2.3e-5 away from the same step in float64.  The bound is
+    # therefore 1e-5 or 2.5x the reference's own distance to float64 on this input, whichever is larger.
+    K64, w64 = t(fx["K"]).double(), t(fx["weights_s"]).double()
+    g64 = (garbi[0].double(), garbi[1].double(), garbi[2], garbi[3])
+    if fam == 0:
+        o64 = orc.lenia_step(s0.double(), K64, None, None, w64, 0.1, garbi=g64)
+    elif fam == 1:
+        o64 = orc.mace_step(s0.double(), K64, None, None, w64, float(fx["b"]), garbi=g64)[0]
+    else:
+        o64 = orc.xchan_step(s0.double(), K64, None, None, w64, float(fx["b"]), float(fx["alpha_used"]), garbi=g64)
+    ref = t(fx["state_out"])
+    noise = (ref.double() - o64).abs().max().item()
+    tol = max(1e-5 * max(1.0, float(ref.abs().max())), 2.5 * noise)
+    assert (a.state.cpu() - ref).abs().max().item() <= tol
+    assert (a.state.cpu().double() - o64).abs().max().item() <= tol
+    if fam > 0:
+        a64 = orc.lenia_affinity(s0.double(), K64, None, None, w64, garbi=g64)
+        noise_a = (t(fx["aff"]).double() - a64).abs().max().item()
+        assert (a.Aff.cpu() - t(fx["aff"])).abs().max().item() <= max(1e-5, 2.5 * noise_a)
+        m0, m1 = float(s0.double().sum()), float(a.state.double().sum())
+        assert abs(m1 - m0) <= 1e-6 * m0   # MaCE stays mass conserving whatever the growth function
+
+
+def test_garbi_odd_shape_vs_oracle():
+    """Global rescale statistics must ignore the overhang of edge tiles (world not a multiple of the 64-wide tiles)."""
+    import pyca_b200
+    from tests.util import garbi_case, raw_param_dict
+
+    fx, garbi = garbi_case("lenia_synth")
+    C = 2
+    g = torch.Generator().manual_seed(12)
+    s0 = torch.rand(1, C, 37, 83, generator=g)
+    a = pyca_b200.Lenia((37, 83), num_channels=C, params=pyca_b200.LeniaParams(param_dict=raw_param_dict(fx), channels=C),
+                        state_init=s0, device="cuda")
+    a.step()
+    ref = orc.lenia_step(s0, t(fx["K"]), None, None, t(fx["weights_s"]), 0.1, garbi=garbi)
+    assert (a.state.cpu() - ref).abs().max().item() <= 1e-5

@@ -126,3 +126,21 @@ def test_draw_oracle_matches_reference_fixture():
     assert torch.equal(orc.lenia_draw(t(fx["mace_state"])), t(fx["mace_wm"]))
     assert torch.equal(orc.nca_draw(t(fx["nca_state"])), t(fx["nca_wm"]))
     assert np.array_equal(orc.frame_u8(orc.nca_draw(t(fx["nca_state"]))), fx["nca_frame"])
+
+
+@pytest.mark.parametrize("name", ["underweight_skagway", "inaesthetic_maupassant", "unsuspected_lanthanotidae", "lenia_synth"])
+def test_garbi_oracle_matches_reference_fixture(name):
+    """g_arbi Fourier growth (incl. the global min/max rescale) against the reference's own step on the demo_data files."""
+    from tests.util import garbi_case
+
+    fx, garbi = garbi_case(name)
+    s0, K, w = t(fx["state_in"]), t(fx["K"]), t(fx["weights_s"])
+    fam = int(fx["family"])
+    if fam == 0:
+        out = orc.lenia_step(s0, K, None, None, w, float(fx["dt"]), garbi=garbi)
+    elif fam == 1:
+        out, aff = orc.mace_step(s0, K, None, None, w, float(fx["b"]), garbi=garbi)
+        assert (aff - t(fx["aff"])).abs().max().item() <= TOL
+    else:
+        out = orc.xchan_step(s0, K, None, None, w, float(fx["b"]), float(fx["alpha_used"]), garbi=garbi)
+    assert (out - t(fx["state_out"])).abs().max().item() <= TOL

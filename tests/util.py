@@ -35,3 +35,40 @@ def family_case(tag, name):
     if name == "realstate":
         return fx, fx
     return fx, load_npz(f"params_{tag}_{name}.npz")
+
+
+GARBI_CASES = ["underweight_skagway", "inaesthetic_maupassant", "unsuspected_lanthanotidae", "lenia_synth"]
+
+
+def garbi_case(name):
+    """g_arbi fixture -> (fixture, oracle `garbi` tuple, param dict for pyca_b200.LeniaParams)."""
+    fx = load_npz(f"garbi_{name}.npz")
+    rs = None if np.isnan(fx["g_rescale"]).any() else (float(fx["g_rescale"][0]), float(fx["g_rescale"][1]))
+    cl = None if np.isnan(fx["g_clip"]) else float(fx["g_clip"])
+    garbi = (t(fx["g_coeffs"]), t(fx["g_harmonics"]), rs, cl)
+    return fx, garbi
+
+
+INT_KEYS = ("k_size", "k_mult", "num_channels")
+BOOL_KEYS = ("g_arbi", "k_arbi")
+TUPLE_KEYS = ("g_rescale", "k_rescale")
+
+
+def raw_param_dict(fx):
+    """The parameter-file dict stored under p_* keys of a fixture, back in the reference's types."""
+    d = {}
+    for key, v in fx.items():
+        if not key.startswith("p_"):
+            continue
+        k = key[2:]
+        if k in INT_KEYS:
+            d[k] = int(v)
+        elif k in BOOL_KEYS:
+            d[k] = bool(v)
+        elif k in TUPLE_KEYS:
+            d[k] = None if np.isnan(v).any() else (float(v[0]), float(v[1]))
+        elif v.ndim == 0:
+            d[k] = None if np.isnan(v) else float(v)
+        else:
+            d[k] = t(v.astype(np.float32))
+    return d
