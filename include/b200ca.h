@@ -156,6 +156,24 @@ int b200ca_lenia_step_fft_phase(const float *state_in, float *state_out, const f
 int b200ca_mace_redistribute(const float *state_in, const float *aff, float *state_out, int B, int C, int H, int W,
                              float beta, int alpha_on, float alpha, int row_wrap, void *stream);
 
+/* MaCE food subsystem (macelenia.py:122-226; off by default in the reference).
+ *   b200ca_lenia_conv_sum    out[b,j] = sum_{i,m} K[b,i*k_mult+m,j] (*) planes_in[b,i]   (framed in/out, direct path): the
+ *                            `kernel_fftconv(food_aff).sum(dim=1)` of food sensing (:152-154) with planes_in = the food mask
+ *                            replicated over the C channels.
+ *   b200ca_mace_food_sense   aff += (food > 0) + food_conv over the whole framed extent (:149-157); food dense (B,1,H,W).
+ *   b200ca_mace_food_decay   state -= (state > threshold ? decay : 0) on the interior, in place; loss[b] += mass removed
+ *                            (double, device) (:171-185).  The frame of `state` is stale afterwards.
+ *   b200ca_mace_food_consume transfer = min(food, rate * [food > 0 and sum_c state >= min_density]); state_out = state_in +
+ *                            transfer / 3 (framed, periodic frame written); food -= transfer (in place) (:194-226, death off);
+ *                            alpha_on: followed by the cross-channel mixing with softmax_c(beta * aff) that
+ *                            MaCELeniaXChan.step applies after the food step (mace_lenia_xchan.py:59-76). */
+int b200ca_lenia_conv_sum(const float *planes_in, float *out, const float *Kprep, int B, int C, int k_mult, int H, int W,
+                          void *stream);
+int b200ca_mace_food_sense(float *aff, const float *food_conv, const float *food, int B, int C, int H, int W, void *stream);
+int b200ca_mace_food_decay(float *state, double *loss, int B, int C, int H, int W, float threshold, float decay, void *stream);
+int b200ca_mace_food_consume(const float *state_in, float *state_out, float *food, const float *aff, int B, int C, int H, int W,
+                             float min_density, float transfer_rate, int alpha_on, float beta, float alpha, void *stream);
+
 /* sum over H*W of every (b,c) plane of a framed tensor into mass[b*C+c] (double, device): total_mass()
  * (macelenia.py:421-428). */
 int b200ca_frame_mass(const float *framed, double *mass, int B, int C, int H, int W, void *stream);

@@ -27,6 +27,10 @@ Reference lines followed (relative to the PyCA tree):
   mace_affinity         pyca/automata/models/lenia/macelenia.py:122-159 (food off)
   mace_step             pyca/automata/models/lenia/macelenia.py:89-120
   xchan_step            pyca/automata/models/lenia/mace_lenia_xchan.py:59-76
+  food_affinity         pyca/automata/models/lenia/macelenia.py:149-157 (sense_food)
+  food_decay            pyca/automata/models/lenia/macelenia.py:171-185
+  food_consume          pyca/automata/models/lenia/macelenia.py:194-226 (death_enabled=False)
+  mace_food_step        pyca/automata/models/lenia/macelenia.py:72-87, :161-192; mace_lenia_xchan.py:59-66 (has_food)
   nca_perception        pyca/automata/models/nca.py:306-344
   nca_live_mask         pyca/automata/models/nca.py:226-237
   nca_step              pyca/automata/models/nca.py:239-263
@@ -215,6 +219,55 @@ def xchan_step(state, K, mu, sigma, weights, b=6.0, alpha=0.03, Kf=None, garbi=N
     """mace_lenia_xchan.py:59-66 with food off."""
     new, aff = mace_step(state, K, mu, sigma, weights, b, Kf, garbi)
     return xchan_mix(new, aff, b, alpha)
+
+
+# ---- MaCE food subsystem (off by default in the reference) ------------------------------------------------------
+def food_affinity(aff, food, K, Kf=None):
+    """macelenia.py:149-157: Aff + mask + sum over sources of K (*) mask, mask = (food > 0) on every channel."""
+    B, C, H, W = aff.shape
+    k_mult = K.shape[1] // C
+    if Kf is None:
+        Kf = kernel_fft(K, H, W)
+    food_aff = (food > 0).float().expand(-1, C, -1, -1)
+    food_aff = food_aff + fft_conv(food_aff, Kf, k_mult).sum(dim=1)
+    return aff + food_aff
+
+
+def food_decay(state):
+    """macelenia.py:171-185 (decay variant 3): returns (state - decay, per-world mass lost)."""
+    decay = torch.where(state > 0.02, 0.0003, torch.zeros_like(state))
+    return state - decay, decay.view(state.shape[0], -1).sum(dim=1)
+
+
+def food_consume(state, food, min_density=0.1, transfer_rate=0.1):
+    """macelenia.py:194-226 with death_enabled=False: returns (state + transfer/3, food - transfer)."""
+    where_food = food > 0
+    where_contact = state.sum(dim=1, keepdim=True) >= min_density
+    overlap = where_food & where_contact
+    transfer = torch.minimum(food, torch.ones_like(where_food) * overlap * transfer_rate)
+    return state + transfer / 3, food - transfer
+
+
+def mace_food_step(state, food, cum_loss, K, mu, sigma, weights, b, sense_food=False, alpha=None, respawn=None, Kf=None,
+                   garbi=None):
+    """One MaCELenia.step (alpha None) or MaCELeniaXChan.step (alpha given) with has_food=True.
+    `respawn(food, batches) -> food` stands in for random_food_chan(200, 5, 7, add_to_exisitng=True) (host RNG).
+    Returns (state, food, cum_loss, Aff)."""
+    aff = lenia_affinity(state, K, mu, sigma, weights, Kf, garbi)
+    if sense_food:
+        aff = food_affinity(aff, food, K, Kf)
+    state = mace_redistribute(state, aff, b)
+    state, lost = food_decay(state)
+    cum_loss = cum_loss + lost
+    idx = [p[0] for p in torch.argwhere(cum_loss >= 200).tolist()]
+    if idx:
+        cum_loss = cum_loss.clone()
+        cum_loss[idx] = cum_loss[idx] - 200
+        food = respawn(food, idx)
+    state, food = food_consume(state, food, 0.3 if sense_food else 0.1, 0.1)
+    if alpha is not None:
+        state = xchan_mix(state, aff, b, alpha)
+    return state, food, cum_loss, aff
 
 
 # float64 direct evaluation, for noise-floor reporting (not a restatement of reference lines)

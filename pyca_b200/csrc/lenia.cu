@@ -53,7 +53,7 @@ struct LeniaArgs {
     float gclip;
     int gclip_on;
 };
-enum { G_GAUSS = 0, G_SERIES = 1, G_RESCALE = 2, G_STATS = 3 };
+enum { G_GAUSS = 0, G_SERIES = 1, G_RESCALE = 2, G_STATS = 3, G_LINEAR = 4 };
 
 __device__ __forceinline__ void atomic_min_f32(float *p, float v) {
     if (v >= 0.f) atomicMin(reinterpret_cast<int *>(p), __float_as_int(v));
@@ -197,6 +197,12 @@ __global__ void __launch_bounds__(32 * NW) lenia_conv_kernel(const CUtensorMap *
         } else {
             // values = sum_h cos_h cos(f_h u) + sin_h sin(f_h u);  optional (v - min) / (max - min + 1e-8) * (r1 - r0) + r0 with
             // the plane-wide min / max of the raw series (funcgen.py:99-117), optional clip from below
+            if (a.gmode == G_LINEAR) {  // plain sum of the convolutions (food sensing, macelenia.py:152-154)
+#pragma unroll
+                for (int k = 0; k < STRIP; ++k) dxs[k] += acc[k];
+                __syncthreads();
+                continue;
+            }
             const float wt = __ldg(a.weights + pidx);
             const float *gc = a.gcos + (size_t)pidx * a.nh, *gs = a.gsin + (size_t)pidx * a.nh, *gf = a.gfreq + (size_t)pidx * a.nh;
             float lo = 0.f, den = 1.f;
@@ -482,5 +488,18 @@ extern "C" int b200ca_lenia_step_garbi(const float *state_in, float *state_out, 
         if (rc) return rc;
     }
     a.gmode = rescale_on ? G_RESCALE : G_SERIES;
+    return lenia_step_impl(a, B, C, k_mult, H, W, 0, 0, stream);
+}
+
+extern "C" int b200ca_lenia_conv_sum(const float *planes_in, float *out, const float *Kprep, int B, int C, int k_mult, int H, int W,
+                                     void *stream) {
+    LeniaArgs a = {};
+    a.state_in = planes_in;
+    a.out = out;
+    a.kprep = Kprep;
+    a.weights = Kprep;  // unused in this mode
+    a.mode = B200CA_MODE_AFF;
+    a.row_wrap = 1;
+    a.gmode = G_LINEAR;
     return lenia_step_impl(a, B, C, k_mult, H, W, 0, 0, stream);
 }

@@ -304,18 +304,24 @@ class MaCELenia(Lenia):
 
     def __init__(self, size, num_channels=3, params=None, state_init=None, device="cuda", has_food=False, sense_food=False,
                  interest_files=None, save_dir=".", conv_path="auto"):
-        if has_food or sense_food:
-            raise _lib.B200CAError("the MaCE food subsystem is not built yet (SURVEY.md 8f-3)")
-        self.has_food = False
-        self.sense_food = False
+        if len(size) == 2:
+            size = (1,) + tuple(size)
+        self.has_food = has_food
+        self.initial_food = 0.1 * size[1] * size[2]   # macelenia.py:37
+        self.sense_food = sense_food
         self._beta = 8
         super().__init__(size, dt=0.1, num_channels=num_channels, params=params, state_init=state_init, device=device,
                          interest_files=interest_files, save_dir=save_dir, conv_path=conv_path)
         self.show_batch = 0
+        self.cum_loss_mass = torch.zeros(self.batch, device=device)
+        self.food_channel = torch.zeros((self.batch, 1, self.h, self.w), device=device)
+        if self.has_food:
+            self.food_channel = self.random_food_chan(food_amount=self.initial_food)
 
     def _init_family_buffers(self):
         fs = self._fs
         self._aff = torch.zeros((fs.B, fs.C, fs.rows, fs.pitch), dtype=torch.float32, device=fs.device)
+        self._food_bufs = None  # framed mask planes, framed food convolution, per-world loss (allocated on first use)
 
     @property
     def b(self):
@@ -330,36 +336,120 @@ class MaCELenia(Lenia):
         """Affinity of the last step, (B,C,H,W) view (macelenia.py:52)."""
         return self._aff[:, :, F:F + self.h, F:F + self.w]
 
-    def _compute_affinity(self) -> torch.Tensor:
-        """macelenia.py:122-159 (food off)."""
+    # ---- food subsystem (macelenia.py:161-226, :301-345; off by default) -----------------------------------------
+    def _food_scratch(self):
+        if self._food_bufs is None:
+            fs = self._fs
+            self._food_bufs = {"mask": torch.zeros_like(self._aff), "conv": torch.zeros_like(self._aff),
+                               "loss": torch.zeros(fs.B, dtype=torch.float64, device=fs.device)}
+        return self._food_bufs
+
+    def _food_dense(self) -> torch.Tensor:
+        f = self.food_channel
+        if not (f.is_cuda and f.dtype == torch.float32 and f.is_contiguous()):
+            f = self.food_channel = f.to(self._fs.device, torch.float32).contiguous()
+        return f
+
+    def random_food_chan(self, food_amount, num_spots=300, food_size=5, add_to_exisitng=False, batches=[]):
+        """macelenia.py:301-345: `num_spots` squares of side `food_size` at positions drawn from Python's `random`."""
+        import random
+
+        food_density = food_amount / (num_spots * food_size * food_size)
+        places = [[random.randint(food_size, self.h - food_size), random.randint(food_size, self.w - food_size)]
+                  for _ in range(num_spots)]
+        if add_to_exisitng:
+            food_chan = self.food_channel.clone()
+        else:
+            food_chan = torch.zeros((self.batch, 1, self.h, self.w), device=self.device)
+        for y, x in places:
+            ys, xs = slice(y - food_size // 2, y + food_size // 2 + 1), slice(x - food_size // 2, x + food_size // 2 + 1)
+            if add_to_exisitng:
+                food_chan[batches, :, ys, xs] = food_density
+            else:
+                food_chan[:, :, ys, xs] = food_density
+        return food_chan
+
+    def set_food(self, has_food: bool):
+        """macelenia.py:246-258."""
+        self.has_food = has_food
+        if self.has_food:
+            self.food_channel = self.random_food_chan(food_amount=self.initial_food)
+        else:
+            self.food_channel = torch.zeros_like(self.food_channel)
+
+    def _compute_affinity(self, sense_food=False) -> torch.Tensor:
+        """macelenia.py:122-159."""
         self._sync_state()
         self._conv(self._aff, _lib.MODE_AFF)
+        if self.has_food and sense_food:
+            # Aff += mask + sum_src K_src,j (*) mask, mask = (food > 0) on every channel (:149-157)
+            fs, sc = self._fs, self._food_scratch()
+            food = self._food_dense()
+            mask = (food > 0).float().expand(-1, fs.C, -1, -1).contiguous()
+            with _lib.device_guard(fs.device):
+                st = _lib.current_stream(fs.device)
+                _lib.call("b200ca_frame_load", _lib.ptr(mask), _lib.ptr(sc["mask"]), fs.B, fs.C, fs.H, fs.W, 1, st)
+                _lib.call("b200ca_lenia_conv_sum", _lib.ptr(sc["mask"]), _lib.ptr(sc["conv"]), _lib.ptr(self._kprep), fs.B, fs.C,
+                          self.k_mult, fs.H, fs.W, st)
+                _lib.call("b200ca_mace_food_sense", _lib.ptr(self._aff), _lib.ptr(sc["conv"]), _lib.ptr(food), fs.B, fs.C, fs.H, fs.W, st)
         return self.Aff
 
-    def _mace_step(self, alpha_on=False, alpha=0.0):
+    def _mace_step(self, alpha_on=False, alpha=0.0, sense_food=None):
+        """_mace_step (+ _food_step, + the cross-channel step of the XChan variant): macelenia.py:72-120, :161-226."""
         fs = self._fs
-        self._compute_affinity()
+        sense = self.sense_food if sense_food is None else sense_food
+        self._compute_affinity(sense_food=sense)
         with _lib.device_guard(fs.device):
-            _lib.call("b200ca_mace_redistribute", _lib.ptr(fs.buf), _lib.ptr(self._aff), _lib.ptr(fs.other), fs.B, fs.C, fs.H,
-                      fs.W, float(self.b), 1 if alpha_on else 0, float(alpha), 1, _lib.current_stream(fs.device))
-        fs.swap()
+            st = _lib.current_stream(fs.device)
+            if not self.has_food:
+                _lib.call("b200ca_mace_redistribute", _lib.ptr(fs.buf), _lib.ptr(self._aff), _lib.ptr(fs.other), fs.B, fs.C, fs.H,
+                          fs.W, float(self.b), 1 if alpha_on else 0, float(alpha), 1, st)
+                fs.swap()
+                return self.Aff
+            # with food the reference runs redistribution -> decay (+ respawn) -> consume -> cross-channel step, so the
+            # mixing moves from the redistribution kernel's epilogue into the consume kernel's
+            sc = self._food_scratch()
+            food = self._food_dense()
+            _lib.call("b200ca_mace_redistribute", _lib.ptr(fs.buf), _lib.ptr(self._aff), _lib.ptr(fs.other), fs.B, fs.C, fs.H, fs.W,
+                      float(self.b), 0, 0.0, 1, st)
+            sc["loss"].zero_()
+            _lib.call("b200ca_mace_food_decay", _lib.ptr(fs.other), _lib.ptr(sc["loss"]), fs.B, fs.C, fs.H, fs.W, 0.02, 0.0003, st)
+            self._respawn_food(sc["loss"])
+            food = self._food_dense()
+            _lib.call("b200ca_mace_food_consume", _lib.ptr(fs.other), _lib.ptr(fs.buf), _lib.ptr(food), _lib.ptr(self._aff), fs.B, fs.C,
+                      fs.H, fs.W, 0.3 if self.sense_food else 0.1, 0.1, 1 if alpha_on else 0, float(self.b), float(alpha), st)
+        fs._view = None  # same buffer, new contents: hand out a fresh view object
         return self.Aff
+
+    def _respawn_food(self, loss64):
+        """macelenia.py:183-192: a world that has lost 200 units of mass since the last respawn gets them back as food."""
+        food_amount = 200
+        self.cum_loss_mass = self.cum_loss_mass.to(loss64.device) + loss64.float()
+        update_idxs = [p[0] for p in torch.argwhere(self.cum_loss_mass >= food_amount).tolist()]
+        if update_idxs:
+            self.cum_loss_mass[update_idxs] = self.cum_loss_mass[update_idxs] - food_amount
+            self.food_channel = self.random_food_chan(food_amount=food_amount, num_spots=5, food_size=7, add_to_exisitng=True,
+                                                      batches=update_idxs)
 
     @torch.no_grad()
-    def step(self):
+    def step(self, sense_food=None):
         """macelenia.py:72-87."""
-        self._mace_step()
+        self._mace_step(sense_food=sense_food)
         self.frames += 1
 
     def total_mass(self):
-        """(B,) total mass (macelenia.py:421-428)."""
+        """(B,) total mass (macelenia.py:421-428; the reference returns world 0's scalar when food is on)."""
         self._sync_state()
-        return self._fs.mass().sum(dim=1)
+        m = self._fs.mass().sum(dim=1)
+        if self.has_food:
+            return (m + self.food_channel.double().sum(dim=(1, 2, 3)))[0]
+        return m
 
     @torch.no_grad()
     def draw(self):
         """macelenia.py:365-385 (single-world view `show_batch`; the gridified `show_all` view is GUI)."""
-        self._draw_fused(self.show_batch)
+        food = self._food_dense()[self.show_batch] if self.has_food else None
+        self._draw_fused(self.show_batch, food=food)
 
 
 class MaCELeniaXChan(MaCELenia):
@@ -383,5 +473,5 @@ class MaCELeniaXChan(MaCELenia):
 
     @torch.no_grad()
     def step(self):
-        """mace_lenia_xchan.py:59-66 (note: the reference does not advance `frames` here)."""
+        """mace_lenia_xchan.py:59-66: MaCE step, food step, cross-channel step (the reference does not advance `frames`)."""
         self._mace_step(alpha_on=True, alpha=self.alpha)

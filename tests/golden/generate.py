@@ -319,9 +319,44 @@ def gen_garbi():
          family=np.array(0), b=np.array(0.0), alpha_used=np.array(0.0), k_size=np.array(31), dt=np.array(a.dt), **_raw_dict(raw))
 
 
+# ------------------------------------------------------------------ MaCE food subsystem
+def gen_food():
+    """has_food=True steps of the reference (macelenia.py:72-87, :161-226): plain MaCE with a forced respawn (the world's
+    cum_loss_mass starts just under the 200 threshold; spot positions come from Python's `random`, seeded), and the
+    cross-channel variant with food sensing over two steps."""
+    import random
+
+    H, W = 48, 64
+    out = {}
+    for tag, folder, cls, sense, nsteps, loss0 in [("mace", "demo_macelenia", REF.MaCELenia, False, 1, 199.95),
+                                                    ("xchan", "demo_macelenia_xchan", REF.MaCELeniaXChan, True, 2, 0.0)]:
+        f = pick(folder, 1)[0]
+        g = torch.Generator().manual_seed(4000 + len(out))
+        s0 = torch.rand(1, 3, H, W, generator=g) * (torch.rand(1, 3, H, W, generator=g) < 0.6)
+        auto = cls((H, W), params=REF.LeniaParams(from_file=os.path.join(DEMO, folder, f)), state_init=s0.clone())
+        random.seed(1234)
+        auto.set_food(True)
+        auto.sense_food = sense
+        auto.cum_loss_mass = torch.full((1,), loss0)
+        out[f"{tag}_file"] = np.array(f[:-3])
+        out[f"{tag}_state0"], out[f"{tag}_food0"] = s0, auto.food_channel.clone()
+        out[f"{tag}_b"] = np.array(float(auto.b))
+        out[f"{tag}_alpha"] = np.array(float(getattr(auto, "alpha", 0.0)))
+        out[f"{tag}_loss0"] = np.array(loss0)
+        random.seed(99)
+        for i in range(nsteps):
+            auto.step()
+            out[f"{tag}_state{i + 1}"], out[f"{tag}_food{i + 1}"] = auto.state.clone(), auto.food_channel.clone()
+            out[f"{tag}_loss{i + 1}"] = auto.cum_loss_mass.clone()
+        out[f"{tag}_total_mass"] = np.array(float(auto.total_mass()))
+        auto.draw()
+        out[f"{tag}_wm"], out[f"{tag}_frame"] = auto._worldmap.clone(), auto.worldmap
+    save("food.npz", **out)
+
+
 if __name__ == "__main__":
     only = [a[2:] for a in sys.argv[1:] if a.startswith("--")]   # e.g. --draw regenerates draw.npz alone
-    gens = {"gol": gen_gol, "family": gen_lenia_family, "kmult": gen_kmult, "nca": gen_nca, "draw": gen_draw, "garbi": gen_garbi}
+    gens = {"gol": gen_gol, "family": gen_lenia_family, "kmult": gen_kmult, "nca": gen_nca, "draw": gen_draw, "garbi": gen_garbi, "food": gen_food}
     for name, fn in gens.items():
         if not only or name in only:
             fn()

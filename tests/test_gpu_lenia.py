@@ -354,3 +354,41 @@ def test_garbi_odd_shape_vs_oracle():
     a.step()
     ref = orc.lenia_step(s0, t(fx["K"]), None, None, t(fx["weights_s"]), 0.1, garbi=garbi)
     assert (a.state.cpu() - ref).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("tag", ["mace", "xchan"])
+def test_mace_food_subsystem_golden(tag):
+    """has_food=True steps: food sensing, decay, the respawn of food spots (host `random`, same seed as the
+    reference run), consumption and -- for the cross-channel variant -- the mixing AFTER the food step; plus total_mass()
+    and draw() with the food overlay.  Fixture: tests/golden/food.npz from the unmodified reference."""
+    import random
+
+    import pyca_b200
+
+    fx = load_npz("food.npz")
+    p = load_npz(f"params_{tag}_{str(fx[tag + '_file'])}.npz")
+    d = {k: t(p[k]) for k in ["mu", "sigma", "beta", "mu_k", "sigma_k", "weights"]}
+    d["k_size"] = int(p["k_size"])
+    s0 = t(fx[f"{tag}_state0"])
+    H, W = s0.shape[2:]
+    cls = pyca_b200.MaCELenia if tag == "mace" else pyca_b200.MaCELeniaXChan
+    a = cls((H, W), params=pyca_b200.LeniaParams(param_dict=d), state_init=s0, device="cuda")
+    random.seed(1234)
+    a.set_food(True)
+    assert torch.equal(a.food_channel.cpu(), t(fx[f"{tag}_food0"]))   # same spot positions as the reference drew
+    a.sense_food = tag == "xchan"
+    a.cum_loss_mass = torch.full((1,), float(fx[f"{tag}_loss0"]), device="cuda")
+    if tag == "xchan":
+        a.alpha = float(fx["xchan_alpha"])
+    random.seed(99)
+    i = 1
+    while f"{tag}_state{i}" in fx:
+        a.step()
+        assert (a.state.cpu() - t(fx[f"{tag}_state{i}"])).abs().max().item() <= 1e-5 * i
+        assert (a.food_channel.cpu() - t(fx[f"{tag}_food{i}"])).abs().max().item() <= 1e-6
+        assert (a.cum_loss_mass.cpu() - t(fx[f"{tag}_loss{i}"])).abs().max().item() <= 1e-4
+        i += 1
+    assert abs(float(a.total_mass()) - float(fx[f"{tag}_total_mass"])) <= 1e-5 * float(fx[f"{tag}_total_mass"])
+    a.draw()
+    assert (a._worldmap.cpu() - t(fx[f"{tag}_wm"])).abs().max().item() <= 1e-5 * i
+    assert (a.worldmap.astype(np.int32) - fx[f"{tag}_frame"].astype(np.int32)).__abs__().max() <= 1   # uint8 truncation of ~1e-5 diffs

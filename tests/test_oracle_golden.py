@@ -144,3 +144,29 @@ def test_garbi_oracle_matches_reference_fixture(name):
     else:
         out = orc.xchan_step(s0, K, None, None, w, float(fx["b"]), float(fx["alpha_used"]), garbi=garbi)
     assert (out - t(fx["state_out"])).abs().max().item() <= TOL
+
+
+@pytest.mark.parametrize("tag", ["mace", "xchan"])
+def test_food_oracle_matches_reference_fixture(tag):
+    """MaCE food subsystem (sensing, decay, respawn, consumption, cross-channel order) against the reference's own steps."""
+    import random
+
+    from tests.util import food_respawn_like_reference
+
+    fx = load_npz("food.npz")
+    p = load_npz(f"params_{tag}_{str(fx[tag + '_file'])}.npz")
+    K, mu, sg, w = t(p["K"]), t(p["mu_s"]), t(p["sigma_s"]), t(p["weights_s"])
+    state, food = t(fx[f"{tag}_state0"]), t(fx[f"{tag}_food0"])
+    H, W = state.shape[2:]
+    loss = torch.full((1,), float(fx[f"{tag}_loss0"]))
+    random.seed(99)
+    i = 1
+    while f"{tag}_state{i}" in fx:
+        state, food, loss, _ = orc.mace_food_step(state, food, loss, K, mu, sg, w, float(fx[f"{tag}_b"]), sense_food=(tag == "xchan"),
+                                                  alpha=float(fx[f"{tag}_alpha"]) if tag == "xchan" else None,
+                                                  respawn=food_respawn_like_reference(H, W))
+        assert (state - t(fx[f"{tag}_state{i}"])).abs().max().item() <= TOL
+        assert (food - t(fx[f"{tag}_food{i}"])).abs().max().item() <= TOL
+        assert (loss - t(fx[f"{tag}_loss{i}"])).abs().max().item() <= 1e-4
+        i += 1
+    assert i > 1

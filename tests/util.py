@@ -72,3 +72,19 @@ def raw_param_dict(fx):
         else:
             d[k] = t(v.astype(np.float32))
     return d
+
+
+def food_respawn_like_reference(H, W):
+    """random_food_chan(food_amount=200, num_spots=5, food_size=7, add_to_exisitng=True) of macelenia.py:301-345 as a
+    callback for oracle.mace_food_step: same `random.randint` calls in the same order."""
+    import random
+
+    def respawn(food, batches, food_amount=200, num_spots=5, food_size=7):
+        dens = food_amount / (num_spots * food_size * food_size)
+        places = [[random.randint(food_size, H - food_size), random.randint(food_size, W - food_size)] for _ in range(num_spots)]
+        food = food.clone()
+        for y, x in places:
+            food[batches, :, y - food_size // 2: y + food_size // 2 + 1, x - food_size // 2: x + food_size // 2 + 1] = dens
+        return food
+
+    return respawn
