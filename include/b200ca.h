@@ -174,6 +174,14 @@ int b200ca_mace_food_decay(float *state, double *loss, int B, int C, int H, int 
 int b200ca_mace_food_consume(const float *state_in, float *state_out, float *food, const float *aff, int B, int C, int H, int W,
                              float min_density, float transfer_rate, int alpha_on, float beta, float alpha, void *stream);
 
+/* FlowLenia step tail (flow_lenia.py:207-253): flow field F = grad(Aff)(1 - alpha) - grad(sum_c state) alpha with zero-padded
+ * Sobel stencils and alpha = clip((sum_c state / theta_x)^n, 0, 1), then reintegration tracking (ReintegrationTracker,
+ * :97-153): every cell's mass, a square of half-width sigma_rt displaced by clip(dt F, +-(dd - sigma_rt)), is collected by
+ * the cells it overlaps within +-dd.  aff: framed output of the convolution in mode AFF.  state_out gets its periodic frame.
+ * Mass conserving away from the world edge; like the reference, nothing flows across the edge. */
+int b200ca_flow_reintegrate(const float *state_in, const float *aff, float *state_out, int B, int C, int H, int W, float dt, int dd,
+                            float sigma_rt, float theta_x, int n_pow, void *stream);
+
 /* sum over H*W of every (b,c) plane of a framed tensor into mass[b*C+c] (double, device): total_mass()
  * (macelenia.py:421-428). */
 int b200ca_frame_mass(const float *framed, double *mass, int B, int C, int H, int W, void *stream);

@@ -27,6 +27,10 @@ Reference lines followed (relative to the PyCA tree):
   mace_affinity         pyca/automata/models/lenia/macelenia.py:122-159 (food off)
   mace_step             pyca/automata/models/lenia/macelenia.py:89-120
   xchan_step            pyca/automata/models/lenia/mace_lenia_xchan.py:59-76
+  flow_sobel            pyca/automata/models/lenia/flow_lenia.py:6-47 (zero-padded, unnormalised)
+  flow_field            pyca/automata/models/lenia/flow_lenia.py:207-228 (FlowLenia.compute_affinity)
+  flow_reintegrate      pyca/automata/models/lenia/flow_lenia.py:97-153 (ReintegrationTracker.step / apply_flow)
+  flow_step             pyca/automata/models/lenia/flow_lenia.py:246-253 (FlowLenia.step, food off)
   food_affinity         pyca/automata/models/lenia/macelenia.py:149-157 (sense_food)
   food_decay            pyca/automata/models/lenia/macelenia.py:171-185
   food_consume          pyca/automata/models/lenia/macelenia.py:194-226 (death_enabled=False)
@@ -268,6 +272,56 @@ def mace_food_step(state, food, cum_loss, K, mu, sigma, weights, b, sense_food=F
     if alpha is not None:
         state = xchan_mix(state, aff, b, alpha)
     return state, food, cum_loss, aff
+
+
+# ---- FlowLenia -----------------------------------------------------------------------------------
+def flow_sobel(x):
+    """flow_lenia.py:6-47: per-channel 3x3 Sobel cross-correlations with ZERO padding ("same"), no 1/8 factor.
+    x (B,C,H,W) -> (B,C,2,H,W): component 0 = derivative along the width, 1 = along the height."""
+    C = x.shape[1]
+    k_w = torch.tensor([[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]], dtype=x.dtype).tile((C, 1, 1, 1))
+    k_h = torch.tensor([[-1, -2, -1], [0, 0, 0], [1, 2, 1]], dtype=x.dtype).tile((C, 1, 1, 1))
+    sw = F.conv2d(x, k_w, groups=C, stride=1, padding="same")
+    sh = F.conv2d(x, k_h, groups=C, stride=1, padding="same")
+    return torch.stack((sw, sh), dim=2)
+
+
+def flow_field(state, aff, theta_x=2.0, n=2):
+    """flow_lenia.py:212-226: F = grad(Aff) * (1 - alpha) - grad(total mass) * alpha, alpha = clip((mass/theta_x)^n, 0, 1)."""
+    grad_u = flow_sobel(aff)
+    mass = state.sum(dim=1, keepdims=True)
+    grad_x = flow_sobel(mass)
+    alpha = ((mass / theta_x) ** n).clip(0, 1)[:, :, None]
+    return grad_u * (1 - alpha) - grad_x * alpha
+
+
+def flow_reintegrate(state, flow, dt=0.1, dd=2, sigma=0.65):
+    """flow_lenia.py:97-153: reintegration tracking.  Every cell's mass is a square of half-width sigma moved by
+    clip(dt * flow); a destination collects the overlap with the squares of its (2dd+1)^2 rolled neighbours.  Positions
+    are ABSOLUTE (x + 0.5), so a source rolled in across the world edge never overlaps: the flow is not periodic."""
+    B, C, H, W = state.shape
+    mx, my = torch.meshgrid(torch.arange(W), torch.arange(H), indexing="ij")
+    pos = (torch.dstack((mx, my)) + 0.5).to(state.dtype)             # (W,H,2), pos[x,y] = (x+.5, y+.5)
+    flow_perm = flow.permute(0, 1, 4, 3, 2)                          # (B,C,W,H,2)
+    state_perm = state.permute(0, 1, 3, 2)                           # (B,C,W,H)
+    max_flow = dd - sigma
+    mu = pos[None, None] + torch.clip(dt * flow_perm, -max_flow, max_flow)
+    parts = []
+    for dx in range(-dd, dd + 1):
+        for dy in range(-dd, dd + 1):
+            st_r = torch.roll(state_perm, shifts=(dx, dy), dims=(2, 3))
+            mu_r = torch.roll(mu, shifts=(dx, dy), dims=(2, 3))
+            dist = torch.abs(mu_r - pos[None, None])
+            amount = 0.5 + (sigma - dist)
+            area = torch.clip(amount, 0, min(2 * sigma, 1)).prod(dim=-1)
+            parts.append(st_r * (area / (4 * sigma**2)))
+    return torch.stack(parts, dim=0).sum(dim=0).permute(0, 1, 3, 2)
+
+
+def flow_step(state, K, mu, sigma, weights, dt=0.1, dd=2, sigma_rt=0.65, theta_x=2.0, n=2, Kf=None):
+    """FlowLenia.step (flow_lenia.py:246-253, food off): Lenia affinity -> flow field -> reintegration tracking."""
+    aff = lenia_affinity(state, K, mu, sigma, weights, Kf)
+    return flow_reintegrate(state, flow_field(state, aff, theta_x, n), dt, dd, sigma_rt)
 
 
 # float64 direct evaluation, for noise-floor reporting (not a restatement of reference lines)

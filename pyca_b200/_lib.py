@@ -54,6 +54,8 @@ SIGNATURES = {
     "b200ca_mace_food_decay": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "b200ca_mace_food_consume": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
                                          c_float, c_float, c_void_p]),
+    "b200ca_flow_reintegrate": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_float, c_float,
+                                        c_int, c_void_p]),
     "b200ca_frame_mass": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200ca_lenia_run_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                       c_int, c_float, c_int, c_float, c_float, c_int]),

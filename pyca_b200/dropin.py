@@ -1,5 +1,5 @@
 """Registry override for a real PyCA checkout: `import pyca_b200.dropin; pyca_b200.dropin.install()` before
-`MainWindow(...)` in `simulate.py` replaces the `step()` of CA2D / Lenia / MaCELenia / MaCELeniaXChan / NeuralCA by the
+`MainWindow(...)` in `simulate.py` replaces the `step()` of CA2D / Lenia / MaCELenia / MaCELeniaXChan / FlowLenia / NeuralCA by the
 B200 kernels and leaves everything else of the reference classes (widgets, event handlers, draw, save/load) untouched.
 
 `AUTOMATAS` is keyed by class name and the last definition wins (pyca/automata/automaton.py:104-111), so defining
@@ -220,6 +220,33 @@ def make_xchan(base):
     return MaCELeniaXChan
 
 
+def make_flow(base):
+    class FlowLenia(base):
+        __doc__ = base.__doc__
+
+        @torch.no_grad()
+        def step(self):
+            """flow_lenia.py:246-253 (food off: `has_food` automata keep the reference path)."""
+            if getattr(self, "has_food", False):
+                return base.step(self)
+            eng = _engine(self)
+            fs = eng.fs
+            if eng.aff is None:
+                eng.aff = torch.zeros_like(fs.buf)
+            eng.conv(eng.aff, _lib.MODE_AFF, 0.0)
+            with torch.cuda.device(fs.device):
+                _lib.call("b200ca_flow_reintegrate", _lib.ptr(fs.buf), _lib.ptr(eng.aff), _lib.ptr(fs.other), fs.B, fs.C, fs.H, fs.W,
+                          float(self.dt), int(self.dd), float(self.sigma_rt), float(self.theta_x), int(self.n),
+                          _lib.current_stream(fs.device))
+            eng.publish(self)
+            self.frames += 1
+
+    FlowLenia.__name__ = FlowLenia.__qualname__ = "FlowLenia"
+    if isinstance(getattr(base, "worldmap", None), property):
+        FlowLenia.worldmap = _fast_worldmap(base)
+    return FlowLenia
+
+
 def make_nca(base):
     class NeuralCA(base):
         __doc__ = base.__doc__
@@ -251,7 +278,7 @@ def install():
 
     made = {}
     for name, factory in [("CA2D", make_ca2d), ("Lenia", make_lenia), ("MaCELenia", make_mace), ("MaCELeniaXChan", make_xchan),
-                          ("NeuralCA", make_nca)]:
+                          ("FlowLenia", make_flow), ("NeuralCA", make_nca)]:
         if name in AUTOMATAS:
             made[name] = factory(AUTOMATAS[name])  # __init_subclass__ re-registers under the same key
     return made

@@ -475,3 +475,45 @@ class MaCELeniaXChan(MaCELenia):
     def step(self):
         """mace_lenia_xchan.py:59-66: MaCE step, food step, cross-channel step (the reference does not advance `frames`)."""
         self._mace_step(alpha_on=True, alpha=self.alpha)
+
+
+class FlowLenia(Lenia):
+    """Pytorch port of mass conserving FlowLenia (B200 step: Lenia affinity kernels + fused flow / reintegration kernel)."""
+
+    def __init__(self, size, dt=0.1, num_channels=3, params=None, state_init=None, device="cuda", dd=2, sigma_rt=0.65,
+                 has_food=False, interest_files=None, save_dir=".", conv_path="auto"):
+        if has_food:
+            raise _lib.B200CAError("FlowLenia's experimental food mechanics (flow_lenia.py:230-244) are not built")
+        self.dd = dd
+        self.sigma_rt = sigma_rt
+        self.theta_x = 2
+        self.n = 2
+        self.has_food = False
+        super().__init__(size, dt, num_channels, params, state_init, device=device, interest_files=interest_files,
+                         save_dir=save_dir, conv_path=conv_path)
+
+    def _init_family_buffers(self):
+        fs = self._fs
+        self._aff = torch.zeros((fs.B, fs.C, fs.rows, fs.pitch), dtype=torch.float32, device=fs.device)
+
+    @property
+    def Aff(self) -> torch.Tensor:
+        """Pre-flow affinity of the last step, (B,C,H,W) view."""
+        return self._aff[:, :, F:F + self.h, F:F + self.w]
+
+    @torch.no_grad()
+    def step(self):
+        """flow_lenia.py:246-253."""
+        fs = self._fs
+        self._sync_state()
+        self._conv(self._aff, _lib.MODE_AFF)
+        with _lib.device_guard(fs.device):
+            _lib.call("b200ca_flow_reintegrate", _lib.ptr(fs.buf), _lib.ptr(self._aff), _lib.ptr(fs.other), fs.B, fs.C, fs.H, fs.W,
+                      float(self.dt), int(self.dd), float(self.sigma_rt), float(self.theta_x), int(self.n),
+                      _lib.current_stream(fs.device))
+        fs.swap()
+        self.frames += 1
+
+    def total_mass(self):
+        self._sync_state()
+        return self._fs.mass().sum(dim=1)

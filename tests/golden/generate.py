@@ -354,9 +354,32 @@ def gen_food():
     save("food.npz", **out)
 
 
+# ------------------------------------------------------------------ FlowLenia
+def gen_flow():
+    """FlowLenia.step of the reference (flow_lenia.py:246-253) with the demo_macelenia parameters its DEFAULTS entry points
+    at (interface/defaults.py:14-17): single steps on sparse random states whose values reach above 1 (alpha clips), two
+    consecutive steps, and a non-square world."""
+    out = {}
+    files = pick("demo_macelenia", 2)
+    cases = [(files[0], 48, 64, 1, 1.6), (files[1], 40, 72, 2, 2.5)]
+    for ci, (f, H, W, nsteps, amp) in enumerate(cases):
+        g = torch.Generator().manual_seed(5000 + ci)
+        s0 = amp * torch.rand(1, 3, H, W, generator=g) * (torch.rand(1, 3, H, W, generator=g) < 0.5)
+        a = REF.FlowLenia((H, W), params=REF.LeniaParams(from_file=os.path.join(DEMO, "demo_macelenia", f)), state_init=s0.clone())
+        out[f"c{ci}_file"] = np.array(f[:-3])
+        out[f"c{ci}_state0"] = s0
+        out[f"c{ci}_flow0"] = a.compute_affinity()
+        out[f"c{ci}_meta"] = np.array([a.dt, a.dd, a.sigma_rt, a.theta_x, a.n], dtype=np.float64)
+        for i in range(nsteps):
+            a.step()
+            out[f"c{ci}_state{i + 1}"] = a.state.clone()
+    out["ncases"] = np.array(len(cases))
+    save("flow.npz", **out)
+
+
 if __name__ == "__main__":
     only = [a[2:] for a in sys.argv[1:] if a.startswith("--")]   # e.g. --draw regenerates draw.npz alone
-    gens = {"gol": gen_gol, "family": gen_lenia_family, "kmult": gen_kmult, "nca": gen_nca, "draw": gen_draw, "garbi": gen_garbi, "food": gen_food}
+    gens = {"gol": gen_gol, "family": gen_lenia_family, "kmult": gen_kmult, "nca": gen_nca, "draw": gen_draw, "garbi": gen_garbi, "food": gen_food, "flow": gen_flow}
     for name, fn in gens.items():
         if not only or name in only:
             fn()

@@ -208,6 +208,8 @@ def load_reference():
     ns.xchan = importlib.import_module("pyca.automata.models.lenia.mace_lenia_xchan")
     ns.leniaparams = importlib.import_module("pyca.automata.models.lenia.leniaparams")
     ns.nca = importlib.import_module("pyca.automata.models.nca")
+    ns.flow = importlib.import_module("pyca.automata.models.lenia.flow_lenia")
+    ns.FlowLenia = ns.flow.FlowLenia
     ns.CA2D = ns.ca2d.CA2D
     ns.Lenia = ns.lenia.Lenia
     ns.MaCELenia = ns.macelenia.MaCELenia

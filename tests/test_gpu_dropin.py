@@ -64,3 +64,21 @@ def test_lenia_family_dropin():
         a.step()
         assert (a.state.cpu() - fn(s0)).abs().max().item() <= 1e-5
         assert tuple(a.Aff.shape) == (1, 3, 64, 96)
+
+
+def test_flow_lenia_dropin():
+    from pyca_b200.dropin import make_flow
+
+    p = load_npz("params_mace_anencephalic_brakeman.npz")
+    K, mu, sg, w = t(p["K"]).cuda(), t(p["mu_s"]).cuda(), t(p["sigma_s"]).cuda(), t(p["weights_s"]).cuda()
+    g = torch.Generator().manual_seed(8)
+    s0 = 1.2 * torch.rand(1, 3, 64, 96, generator=g)
+
+    class FakeFlow(FakeLenia):
+        dd, sigma_rt, theta_x, n = 2, 0.65, 2, 2
+
+    a = make_flow(FakeFlow)(s0.cuda(), K, mu, sg, w)
+    assert type(a).__name__ == "FlowLenia"
+    a.step()
+    ref = orc.flow_step(s0, K.cpu(), mu.cpu(), sg.cpu(), w.cpu(), 0.1)
+    assert (a.state.cpu() - ref).abs().max().item() <= 2e-5 and a.frames == 1

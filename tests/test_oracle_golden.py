@@ -170,3 +170,20 @@ def test_food_oracle_matches_reference_fixture(tag):
         assert (loss - t(fx[f"{tag}_loss{i}"])).abs().max().item() <= 1e-4
         i += 1
     assert i > 1
+
+
+def test_flow_lenia_oracle_matches_reference_fixture():
+    """FlowLenia (affinity -> Sobel flow -> reintegration tracking) restatement against the reference's own steps."""
+    fx = load_npz("flow.npz")
+    for ci in range(int(fx["ncases"])):
+        p = load_npz(f"params_mace_{str(fx[f'c{ci}_file'])}.npz")
+        K, mu, sg, w = t(p["K"]), t(p["mu_s"]), t(p["sigma_s"]), t(p["weights_s"])
+        dt, dd, srt, thx, n = [float(v) for v in fx[f"c{ci}_meta"]]
+        state = t(fx[f"c{ci}_state0"])
+        aff = orc.lenia_affinity(state, K, mu, sg, w)
+        assert (orc.flow_field(state, aff, thx, int(n)) - t(fx[f"c{ci}_flow0"])).abs().max().item() <= 1e-5
+        i = 1
+        while f"c{ci}_state{i}" in fx:
+            state = orc.flow_step(state, K, mu, sg, w, dt, int(dd), srt, thx, int(n))
+            assert (state - t(fx[f"c{ci}_state{i}"])).abs().max().item() <= TOL * i
+            i += 1
