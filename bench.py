@@ -13,6 +13,7 @@ extracted from the reference's demo_data):
   gol_250         Game of Life 250x250 (simulate.py default world)
   mace_xchan_4k   MaCE-Lenia cross-channel 4096x4096 C=3, demo_macelenia_xchan/arborical_asbestosis
   nca_256         NCA inference 256 x 128x128 worlds (betta weights), batch-sharded for N>1
+  flow_lenia_4k   FlowLenia 4096x4096 C=3, demo_macelenia/anencephalic_brakeman
 `--impl reference` times the CPU implementation of the same path (the oracle port of the reference's torch
 step, all host threads) on the same workload.
 """
@@ -507,6 +508,60 @@ class MaceWL(Workload):
         return f"MaCE-XChan C=3 {self.cH}x{self.cW} oracle step (fft2 + unfold path of macelenia.py:89-159)"
 
 
+class FlowWL(MaceWL):
+    """FlowLenia with the demo_macelenia parameters its DEFAULTS entry points at."""
+
+    def setup(self):
+        import pyca_b200
+
+        d, _ = load_params("params_mace_anencephalic_brakeman.npz")
+        self.params = pyca_b200.LeniaParams(param_dict=d)
+        g = torch.Generator().manual_seed(self.rank)
+        self.h_state = (1.5 * torch.rand(1, 3, self.H, self.W, generator=g)).pin_memory()
+        self.auto = pyca_b200.FlowLenia((self.H, self.W), params=self.params, state_init=self.h_state, device=self.device)
+
+    def launches_per_step(self):
+        return 3 if self.auto.use_fft else 2
+
+    def dominant(self):
+        cells = self.H * self.W
+        return {"kernel": "affinity (lenia_fft_rows + lenia_fft_firinv) + flow_rt_kernel", "bytes": cells * 3 * 8, "fma": 0}
+
+    def config(self):
+        return {"workload": self.name, "shape": [1, 3, self.H, self.W], "params": "demo_macelenia/anencephalic_brakeman",
+                "dd": 2, "sigma_rt": 0.65, "partition": "one world per GPU",
+                "l2": "inputs larger than L2" if self.H * self.W * 12 > (126 << 20) else "flushed between timed steps"}
+
+    def e2e_setup(self):
+        import pyca_b200
+
+        self.h_out = torch.empty(1, 3, self.H, self.W).pin_memory()
+
+    def e2e_step(self):
+        return self.e2e_step_sync()
+
+    def e2e_drain(self):
+        pass
+
+    def cpu_setup(self):
+        from oracle import pyca_oracle as orc
+
+        self.orc = orc
+        p = self.params.param_dict
+        self.cH, self.cW = min(self.H, 1024), min(self.W, 1024)
+        self.cK = orc.lenia_kernel(p["beta"].cpu(), p["mu_k"].cpu(), p["sigma_k"].cpu(), 31)
+        self.cKf = orc.kernel_fft(self.cK, self.cH, self.cW)
+        g = torch.Generator().manual_seed(0)
+        self.cstate = 1.5 * torch.rand(1, 3, self.cH, self.cW, generator=g)
+        self.cmu, self.csg, self.cw = p["mu"].cpu(), p["sigma"].cpu(), p["weights"].cpu()
+
+    def cpu_step(self):
+        self.cstate = self.orc.flow_step(self.cstate, self.cK, self.cmu, self.csg, self.cw, Kf=self.cKf)
+
+    def cpu_sample(self):
+        return f"FlowLenia C=3 {self.cH}x{self.cW} oracle step (fft2 + conv2d sobel + 25 rolls, flow_lenia.py:97-253)"
+
+
 class NcaWL(Workload):
     def __init__(self, rank, world, device, B=256, H=128, W=128, name="nca_256", impl=None):
         super().__init__(rank, world, device)
@@ -618,6 +673,10 @@ def make_workload(name, rank, world, device):
         return MaceWL(rank, world, device, 1024, 1024, name)
     if name == "nca_256":
         return NcaWL(rank, world, device, 256, 128, 128, name)
+    if name == "flow_lenia_1k":
+        return FlowWL(rank, world, device, 1024, 1024, name)
+    if name == "flow_lenia_4k":
+        return FlowWL(rank, world, device, 4096, 4096, name)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -689,7 +748,7 @@ def run_reference(args, rank, world):
     elif isinstance(wl, MaceWL):
         import pyca_b200
 
-        d, _ = load_params("params_xchan_arborical_asbestosis.npz")
+        d, _ = load_params("params_mace_anencephalic_brakeman.npz" if isinstance(wl, FlowWL) else "params_xchan_arborical_asbestosis.npz")
         wl.params = pyca_b200.LeniaParams(param_dict=d)
     elif isinstance(wl, NcaWL):
         from tests.util import load_npz
@@ -763,7 +822,7 @@ def main():
     # dominant kernel: average launch duration measured live with CUDA events on the launching stream
     peaks = measured_peaks()
     kern_ms = ms_per_step  # one kernel per step for the single-kernel workloads; refined below for MaCE/NCA
-    if isinstance(wl, MaceWL) and rank == 0:
+    if isinstance(wl, MaceWL) and not isinstance(wl, FlowWL) and rank == 0:
         from pyca_b200 import _lib
 
         a = wl.auto
@@ -815,7 +874,7 @@ def main():
                 torch.distributed.all_reduce(el, op=torch.distributed.ReduceOp.MAX)
             return float(el.item()), hb, db
 
-        n_e2e = max(6, min(args.steps, 60))
+        n_e2e = max(6, min(4 * args.steps, 200))
         el, hb, db = run_e2e(wl.e2e_step, n_e2e)
         cells = wl.e2e_cells() if hasattr(wl, "e2e_cells") else wl.cells_per_step()
         piped = hasattr(wl, "pipe")
@@ -837,14 +896,14 @@ def main():
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
         extras = {}
-        for other in ["lenia3_1k", "gol_250", "gol_64k", "mace_xchan_4k", "nca_256"]:
+        for other in ["lenia3_1k", "gol_250", "gol_64k", "mace_xchan_4k", "nca_256", "flow_lenia_4k"]:
             if other == name:
                 continue
             try:
                 ow = make_workload(other, 0, 1, device)
                 ow.setup()
                 od = ow.dominant()
-                k = 3 if other in ("mace_xchan_4k",) else 10
+                k = 3 if other in ("mace_xchan_4k", "flow_lenia_4k") else 10
                 ms = time_block(ow, k, 3, 1) / k
                 ent = {"gcups": ow.cells_per_step() / (ms * 1e-3) / 1e9, "ms_per_step": ms,
                        "hbm_frac_algorithmic": od["bytes"] / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "config": ow.config()}

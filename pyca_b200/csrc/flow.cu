@@ -19,13 +19,13 @@ using namespace b200ca;
 namespace {
 
 constexpr int F = B200CA_FRAME;
-constexpr int FTX = 32, FTY = 16, FTHREADS = 256;
+constexpr int FTX = 32, FTY = 32, FTHREADS = 256, RPT = 4;  // 32x32 output tile, 4 vertically adjacent outputs per thread
 
 struct FlowArgs {
     const float *state_in, *aff;
     float *out;
     int B, C, H, W, pitch;
-    float dt, sigma, max_flow, cap, norm;  // cap = min(2 sigma, 1); norm = 4 sigma^2
+    float dt, sigma, max_flow, cap, inv_norm;  // cap = min(2 sigma, 1); inv_norm = 1 / (4 sigma^2)
     float theta_x;
     int n_pow;
 };
@@ -50,13 +50,13 @@ __device__ __forceinline__ void sobel_at(const float *t, int p, float &sw, float
     sh = (f - a) + 2.f * (g - b) + (h - c);
 }
 
-template <int DD>
-__global__ void __launch_bounds__(FTHREADS) flow_rt_kernel(const FlowArgs a) {
+// UNIT_CAP: min(2 sigma, 1) == 1 (sigma >= 0.5, the default 0.65): the clip to [0, cap] is the free .SAT modifier
+template <int DD, bool UNIT_CAP>
+__global__ void __launch_bounds__(FTHREADS, 4) flow_rt_kernel(const FlowArgs a) {
     constexpr int HA = FTY + 2 * DD + 2, WA = FTX + 2 * DD + 2;  // Aff / mass tiles: halo DD + 1
     constexpr int HS = FTY + 2 * DD, WS = FTX + 2 * DD;          // displacement / state tiles: halo DD
     __shared__ float mass[HA * WA], affs[HA * WA];
-    __shared__ float gxw[HS * WS], gxh[HS * WS], alp[HS * WS];   // grad(mass), alpha: shared by all channels
-    __shared__ float cfx[HS * WS], cfy[HS * WS], sts[HS * WS];
+    __shared__ float4 src[HS * WS];  // per source cell: (clipped displacement x, y, state, -)
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * FTX, y0 = blockIdx.y * FTY, b = blockIdx.z;
     const size_t plane = (size_t)(a.H + 2 * F) * a.pitch;
@@ -72,21 +72,9 @@ __global__ void __launch_bounds__(FTHREADS) flow_rt_kernel(const FlowArgs a) {
         }
         mass[t] = m;
     }
-    __syncthreads();
-    for (int t = tid; t < HS * WS; t += FTHREADS) {
-        const int r = t / WS, q = t % WS;
-        const float *mc = mass + (r + 1) * WA + q + 1;
-        float sw, sh;
-        sobel_at(mc, WA, sw, sh);
-        const float v = mc[0] / a.theta_x;
-        const float al = a.n_pow == 2 ? v * v : powf(v, (float)a.n_pow);
-        gxw[t] = sw;
-        gxh[t] = sh;
-        alp[t] = fminf(fmaxf(al, 0.f), 1.f);
-    }
-    const int lx = tid & 31, ly0 = tid >> 5;
+    const int lx = tid & 31, ly0 = (tid >> 5) * RPT;
     for (int c = 0; c < a.C; ++c) {
-        __syncthreads();  // previous channel's gathers are done with cfx / cfy / sts / affs
+        __syncthreads();  // previous channel's gathers are done with src / affs
         for (int t = tid; t < HA * WA; t += FTHREADS) {
             const int y = y0 - DD - 1 + t / WA, x = x0 - DD - 1 + t % WA;
             affs[t] = (y >= 0 && y < a.H && x >= 0 && x < a.W) ? ab[c * plane + (size_t)(y + F) * a.pitch + x + F] : 0.f;
@@ -95,39 +83,58 @@ __global__ void __launch_bounds__(FTHREADS) flow_rt_kernel(const FlowArgs a) {
         for (int t = tid; t < HS * WS; t += FTHREADS) {
             const int r = t / WS, q = t % WS;
             const int y = y0 - DD + r, x = x0 - DD + q;
-            float sw, sh;
+            float sw, sh, gw, gh;
             sobel_at(affs + (r + 1) * WA + q + 1, WA, sw, sh);
-            const float al = alp[t], om = 1.f - al;
+            // grad(total mass) and alpha = clip((mass / theta_x)^n, 0, 1): recomputed per channel from the mass tile (a few
+            // shared-memory reads) rather than kept in three more tiles
+            const float *mc = mass + (r + 1) * WA + q + 1;
+            sobel_at(mc, WA, gw, gh);
+            const float mv = mc[0] / a.theta_x;
+            const float al = fminf(fmaxf(a.n_pow == 2 ? mv * mv : powf(mv, (float)a.n_pow), 0.f), 1.f), om = 1.f - al;
             // F = grad_u * (1 - alpha) - grad_x * alpha, every product rounded on its own as torch does
-            const float fx = __fsub_rn(__fmul_rn(sw, om), __fmul_rn(gxw[t], al));
-            const float fy = __fsub_rn(__fmul_rn(sh, om), __fmul_rn(gxh[t], al));
-            cfx[t] = fminf(fmaxf(__fmul_rn(a.dt, fx), -a.max_flow), a.max_flow);
-            cfy[t] = fminf(fmaxf(__fmul_rn(a.dt, fy), -a.max_flow), a.max_flow);
+            const float fx = __fsub_rn(__fmul_rn(sw, om), __fmul_rn(gw, al));
+            const float fy = __fsub_rn(__fmul_rn(sh, om), __fmul_rn(gh, al));
             // a source outside the world is a rolled-in one in the reference: its absolute position never overlaps
-            sts[t] = (y >= 0 && y < a.H && x >= 0 && x < a.W) ? sb[c * plane + (size_t)(y + F) * a.pitch + x + F] : 0.f;
+            const float sv = (y >= 0 && y < a.H && x >= 0 && x < a.W) ? sb[c * plane + (size_t)(y + F) * a.pitch + x + F] : 0.f;
+            src[t] = make_float4(fminf(fmaxf(__fmul_rn(a.dt, fx), -a.max_flow), a.max_flow),
+                                 fminf(fmaxf(__fmul_rn(a.dt, fy), -a.max_flow), a.max_flow), sv, 0.f);
         }
         __syncthreads();
+        // gather: a thread owns RPT vertically adjacent outputs of one column, so a source cell is read once for all the
+        // outputs it feeds and its x-overlap (same column distance for all of them) is computed once
+        {
+            const int x = x0 + lx, yb = y0 + ly0;
+            const float px = (float)x + 0.5f, pyb = (float)yb + 0.5f;  // cell centres: small offsets from them stay exact
+            float acc[RPT];
 #pragma unroll
-        for (int k = 0; k < FTY / 8; ++k) {
-            const int ly = ly0 + 8 * k;
-            const int y = y0 + ly, x = x0 + lx;
-            if (y >= a.H || x >= a.W) continue;
-            const float px = (float)x + 0.5f, py = (float)y + 0.5f;
-            float acc = 0.f;
+            for (int k = 0; k < RPT; ++k) acc[k] = 0.f;
 #pragma unroll
             for (int dx = -DD; dx <= DD; ++dx) {
 #pragma unroll
-                for (int dy = -DD; dy <= DD; ++dy) {
-                    const int t = (ly - dy + DD) * WS + (lx - dx + DD);
-                    // mu of the source = its own centre + its displacement; overlap with this cell's unit square
-                    const float mux = __fadd_rn((float)(x - dx) + 0.5f, cfx[t]);
-                    const float muy = __fadd_rn((float)(y - dy) + 0.5f, cfy[t]);
-                    const float ox = fminf(fmaxf(0.5f + (a.sigma - fabsf(mux - px)), 0.f), a.cap);
-                    const float oy = fminf(fmaxf(0.5f + (a.sigma - fabsf(muy - py)), 0.f), a.cap);
-                    acc += sts[t] * __fdiv_rn(__fmul_rn(ox, oy), a.norm);
+                for (int sr = -DD; sr < RPT + DD; ++sr) {  // source row relative to the thread's first output row
+                    const float4 s4 = src[(ly0 + sr + DD) * WS + (lx - dx + DD)];
+                    // mu of the source = its own centre + its displacement, rounded as the reference rounds it (the centres
+                    // are exact in fp32); overlap of its sigma-square with the destination's unit square, per axis
+                    const float mux = __fadd_rn(px - (float)dx, s4.x);
+                    float ox = __saturatef(0.5f + (a.sigma - fabsf(mux - px)));
+                    if (!UNIT_CAP) ox = fminf(ox, a.cap);
+                    const float muy = __fadd_rn(pyb + (float)sr, s4.y);
+                    const float w = s4.z * ox;
+#pragma unroll
+                    for (int k = 0; k < RPT; ++k) {
+                        if (k - sr < -DD || k - sr > DD) continue;  // dy = k - sr
+                        float oy = __saturatef(0.5f + (a.sigma - fabsf(muy - (pyb + (float)k))));
+                        if (!UNIT_CAP) oy = fminf(oy, a.cap);
+                        acc[k] = fmaf(w, oy, acc[k]);
+                    }
                 }
             }
-            flow_store(a.out + (size_t)(b * a.C + c) * plane, a.H, a.W, a.pitch, y, x, acc);
+            if (x < a.W) {
+#pragma unroll
+                for (int k = 0; k < RPT; ++k)
+                    if (yb + k < a.H)
+                        flow_store(a.out + (size_t)(b * a.C + c) * plane, a.H, a.W, a.pitch, yb + k, x, acc[k] * a.inv_norm);
+            }
         }
     }
 }
@@ -135,7 +142,8 @@ __global__ void __launch_bounds__(FTHREADS) flow_rt_kernel(const FlowArgs a) {
 template <int DD>
 int launch_flow(const FlowArgs &a, cudaStream_t st) {
     dim3 grid(ceil_div(a.W, FTX), ceil_div(a.H, FTY), a.B);
-    flow_rt_kernel<DD><<<grid, FTHREADS, 0, st>>>(a);
+    if (a.cap == 1.f) flow_rt_kernel<DD, true><<<grid, FTHREADS, 0, st>>>(a);
+    else flow_rt_kernel<DD, false><<<grid, FTHREADS, 0, st>>>(a);
     B200CA_LAUNCH_CHECK("flow_rt_kernel");
     return 0;
 }
@@ -159,7 +167,7 @@ extern "C" int b200ca_flow_reintegrate(const float *state_in, const float *aff, 
     // the reference forms these in Python doubles and torch casts them to fp32 when they meet the tensors
     a.max_flow = (float)((double)dd - (double)sigma_rt);
     a.cap = (float)(2.0 * (double)sigma_rt < 1.0 ? 2.0 * (double)sigma_rt : 1.0);
-    a.norm = (float)(4.0 * (double)sigma_rt * (double)sigma_rt);
+    a.inv_norm = 1.f / (float)(4.0 * (double)sigma_rt * (double)sigma_rt);
     a.theta_x = theta_x;
     a.n_pow = n_pow;
     cudaStream_t st = as_stream(stream);
