@@ -175,6 +175,20 @@ __global__ void __launch_bounds__(128 * NG, 1) nca_update_tc_kernel(const NcaArg
         const int xc = min(x, a.W - 1), yc = min(y, a.H - 1);
         const float *sb = a.in + (size_t)b * NCA_N * plane;
 
+        // The next tile of this group is known: pull its 6 rows x 16 channels (one 128-byte line each when the tile row is
+        // line-aligned) into L2 now, so that its perception loads find them there instead of in HBM one tile later
+        {
+            const int nt = tile + gridDim.x * NG;
+            if (nt < ntiles && tid < 6 * NCA_N) {
+                const int ntx = nt % tiles_x, nty = (nt / tiles_x) % tiles_y, nb = nt / (tiles_x * tiles_y);
+                const int prow = tid % 6, pch = tid / 6;
+                int py = nty * 4 - 1 + prow;
+                py = py < 0 ? py + a.H : (py >= a.H ? py - a.H : py);
+                const float *pa = a.in + ((size_t)nb * NCA_N + pch) * plane + (size_t)py * a.W + min(ntx * 32, a.W - 1);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+            }
+        }
+
         // ---- perception straight from global memory (L1-cached; ~114 independent loads per thread keep the memory
         //      system busy, which a staged shared-memory tile + barrier did not with only 8 warps per SM)
         bool alive0 = false;
