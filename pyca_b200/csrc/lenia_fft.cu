@@ -506,10 +506,17 @@ __device__ long long g_fft_trace[8 * 4096];
 #define FFT_TRACE(slot)
 #endif
 
-template <int FT, bool MULTI, int MINB>
-__global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftInvArgs a) {
+// NT = 256 threads: two frequency chunks per thread in the FIR, 4 rows per inverse pass, 2 CTAs per SM (large worlds).
+// NT = 512 (worlds whose CTAs all fit the machine at one per SM, e.g. 1024^2: the step is then one wave and a CTA's serial
+//      chain IS the kernel time): one chunk per thread, all FT = 8 rows inverted in one pass, and the state values of the
+//      Euler step are staged into their own shared-memory region in the prologue -- before the dependency wait, they are
+//      the previous step's output -- instead of behind the last FFT stages.
+template <int FT, bool MULTI, int MINB, int NT = 256>
+__global__ void __launch_bounds__(NT, MINB) lenia_fft_firinv_kernel(const FftInvArgs a) {
     extern __shared__ __align__(16) float2 fism[];
-    constexpr int N = 1024, NP = FT / 4;
+    constexpr int N = 1024, RG = NT / 64, NP = FT / RG, NCH = N / (2 * NT);
+    constexpr bool EARLY = NT == 512;
+    static_assert(FT % RG == 0 && NP >= 1, "FT must be a multiple of the row groups per pass");
     const int tid = threadIdx.x, t = tid & 63, rw = tid >> 6;
     const int seg = blockIdx.y;
     const int b = blockIdx.z / a.C, j = blockIdx.z % a.C;
@@ -530,7 +537,14 @@ __global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftIn
     // the inverse stages then never wait on L2) and the taps of the first chunk
     FFT_TRACE(0);
     float2 *tw_s = fism + FT * XB;
-    for (int e = tid; e < N; e += 256) tw_s[e] = __ldg(a.tws + e);
+    float2 *st_s = tw_s + N;  // EARLY: FT rows of 1024 staged state pairs
+    if (EARLY && lenia) {
+#pragma unroll
+        for (int ps = 0; ps < NP; ++ps)
+            inv16_stage_state(a, st_s + (ps * RG + rw) * N, plane_off, min(y0 + ps * RG + rw, a.g.D - 1), seg, t);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int e = tid; e < N; e += NT) tw_s[e] = __ldg(a.tws + e);
     float2 kt[KROWS];
     {
         const float *kf = a.kfft + (size_t)((b * a.NS) * a.C + j) * KROWS * N + 2 * tid;
@@ -546,8 +560,8 @@ __global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftIn
         if (i > 0) __syncthreads();  // previous source done with the buffers
         // phase 1: FIR.  Out^[y][p] = sum_dy Khat[|dy|][p] * Z[y + dy][p] for p = p0, p0 + 1
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-            const int p0 = 2 * tid + 512 * c;
+        for (int c = 0; c < NCH; ++c) {
+            const int p0 = 2 * tid + 2 * NT * c;
             if (i > 0 || c > 0) {
                 const float *kf = a.kfft + (size_t)pidx * KROWS * N + p0;
 #pragma unroll
@@ -585,8 +599,8 @@ __global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftIn
         const float c2 = 1.4426950408889634f / (2.f * sg * sg);
 #pragma unroll
         for (int ps = 0; ps < NP; ++ps) {
-            float2 *buf = fism + (ps * 4 + rw) * XB;
-            const int yy = y0 + ps * 4 + rw;
+            float2 *buf = fism + (ps * RG + rw) * XB;
+            const int yy = y0 + ps * RG + rw;
             float2 v[16];
             {
                 // first DIT stage (span 1, no twiddles) on the split layout: quad m = (A, Cq) = (a.re b.re a.im b.im), (c.., d..)
@@ -619,7 +633,8 @@ __global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftIn
             for (int q = 0; q < 16; ++q) v[q] = buf[(t ^ (4 * (q & 3))) + 64 * q];
             // the row buffer is free now: the state values of the Euler step are staged into it by cp.async, their
             // latency hidden behind the last two stages + growth
-            const bool stage = lenia && i == a.NS - 1;
+            const bool stage = !EARLY && lenia && i == a.NS - 1;
+            const float2 *svb = EARLY ? st_s + (ps * RG + rw) * N : buf;
             if (stage) {
                 row_sync(rw);
                 inv16_stage_state(a, buf, plane_off, min(yy, a.g.D - 1), seg, t);
@@ -638,13 +653,13 @@ __global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftIn
                 }
             }
             FFT_TRACE(5);
-            if (stage) cp_async_commit_wait_all();  // own slots only: no barrier needed before reading them back
+            if (stage || (EARLY && lenia)) cp_async_commit_wait_all();  // own slots only: no barrier needed before reading them back
             FFT_TRACE(6);
             if (!MULTI && yy < a.g.D) {
                 const bool rows_edge = a.row_wrap && (yy < F || yy >= a.g.D - F);
                 const bool edge = rows_edge || a.g.periodic || seg == 0 || seg == a.g.nseg - 1;
-                if (edge) inv16_store<true>(a, v, buf, plane_off, yy, seg, t);
-                else inv16_store<false>(a, v, buf, plane_off, yy, seg, t);
+                if (edge) inv16_store<true>(a, v, svb, plane_off, yy, seg, t);
+                else inv16_store<false>(a, v, svb, plane_off, yy, seg, t);
             }
         }
     }
@@ -652,9 +667,9 @@ __global__ void __launch_bounds__(256, MINB) lenia_fft_firinv_kernel(const FftIn
     if (MULTI) {
 #pragma unroll
         for (int ps = 0; ps < NP; ++ps) {
-            const int yy = y0 + ps * 4 + rw;
+            const int yy = y0 + ps * RG + rw;
             if (yy >= a.g.D) continue;
-            const float2 *buf = fism + (ps * 4 + rw) * XB;
+            const float2 *buf = EARLY ? st_s + (ps * RG + rw) * N : fism + (ps * RG + rw) * XB;
             const bool rows_edge = a.row_wrap && (yy < F || yy >= a.g.D - F);
             const bool edge = rows_edge || a.g.periodic || seg == 0 || seg == a.g.nseg - 1;
             if (edge) inv16_store<true>(a, dx[ps], buf, plane_off, yy, seg, t);
@@ -839,8 +854,8 @@ extern "C" int b200ca_lenia_step_fft_phase(const float *state_in, float *state_o
     float2 *O = Z + (size_t)B * C * g.zrows * g.nseg * g.N;
     // developer switches (timing / A-B runs): B200CA_FFT_ONLY = 1|2|3 runs one kernel of the step only;
     // B200CA_FFT_FUSED = 0 unfuses FIR and inverse (N = 1024), 4|8 forces the rows per CTA of the fused kernel;
-    static int rpc_rows = 0, rpc_inv = 0, only = 0, fused = -1;
-    if (!rpc_rows) {
+    static int rpc_rows_env = 0, rpc_inv = 0, only = 0, fused = -1;
+    if (!rpc_rows_env) {
         auto env = [](const char *n, int dflt) {
             const char *e = getenv(n);
             return e ? atoi(e) : dflt;
@@ -849,8 +864,8 @@ extern "C" int b200ca_lenia_step_fft_phase(const float *state_in, float *state_o
         fused = env("B200CA_FFT_FUSED", -1);
         rpc_inv = env("B200CA_FFT_RPC_INV", 1);
         if (rpc_inv != 2 && rpc_inv != 4) rpc_inv = 1;
-        rpc_rows = env("B200CA_FFT_RPC_ROWS", 2);
-        if (rpc_rows != 1 && rpc_rows != 4) rpc_rows = 2;
+        rpc_rows_env = env("B200CA_FFT_RPC_ROWS", 2);
+        if (rpc_rows_env != 1 && rpc_rows_env != 4) rpc_rows_env = 2;
     }
     if (only == 0 || only == 1) {
         // phase 1: spectra rows made of owned rows only (zr in [R, D+R)); phase 2: the 2R rows that touch ghost rows
@@ -867,6 +882,9 @@ extern "C" int b200ca_lenia_step_fft_phase(const float *state_in, float *state_o
 #define ROWS4(RPC, NN, SP) launch_pdl(lenia_fft_rows_kernel<RPC, NN, SP>, dim3(ceil_div(gr.zr_count, RPC), g.nseg, B * C), dim3(NN / 4), \
                                   (size_t)RPC * NN * sizeof(float2), st, state_in, Z, tw, gr, H, W, pitch)
         const bool split = g.N == 1024 && fused != 0;  // the fused FIR + inverse kernel reads split spectra
+        // small worlds (every CTA resident at once): one row pair per CTA shortens the serial chain (1024^2: 19.9 -> 19.4 us/step)
+        static const bool rpc_forced = getenv("B200CA_FFT_RPC_ROWS") != nullptr;
+        const int rpc_rows = (!rpc_forced && (long long)gr.zr_count * g.nseg * B * C <= 5LL * num_sms()) ? 1 : rpc_rows_env;
         if (split) B200CA_CUDA(rpc_rows == 1 ? ROWS4(1, 1024, true) : (rpc_rows == 4 ? ROWS4(4, 1024, true) : ROWS4(2, 1024, true)));
         else if (g.N == 1024) B200CA_CUDA(rpc_rows == 1 ? ROWS4(1, 1024, false) : (rpc_rows == 4 ? ROWS4(4, 1024, false) : ROWS4(2, 1024, false)));
         else B200CA_CUDA(rpc_rows == 1 ? ROWS4(1, 256, false) : (rpc_rows == 4 ? ROWS4(4, 256, false) : ROWS4(2, 256, false)));
@@ -909,6 +927,25 @@ extern "C" int b200ca_lenia_step_fft_phase(const float *state_in, float *state_o
             B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_firinv_kernel<8, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
             B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_firinv_kernel<8, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
             attr_done = true;
+        }
+        // small worlds: when every 8-row CTA fits the machine at one per SM the step is a single wave; 512-thread CTAs halve
+        // the serial chain of a CTA (B200CA_FFT_NT512=0 disables)
+        static int nt512 = -1;
+        if (nt512 < 0) nt512 = getenv("B200CA_FFT_NT512") ? atoi(getenv("B200CA_FFT_NT512")) : 1;
+        const long long ctas8 = (long long)ceil_div(g.D, 8) * g.nseg * B * C;
+        if (nt512 && fused < 0 && ctas8 <= (long long)num_sms()) {
+            const size_t smem5 = ((size_t)8 * XB + 1024 + 8 * 1024) * sizeof(float2);  // row buffers + twiddles + staged state
+            static bool attr5 = false;
+            if (!attr5) {
+                B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_firinv_kernel<8, false, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+                B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_firinv_kernel<8, true, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+                attr5 = true;
+            }
+            dim3 grid5(ceil_div(g.D, 8), g.nseg, B * C);
+            B200CA_CUDA(NS > 1 ? launch_pdl(lenia_fft_firinv_kernel<8, true, 1, 512>, grid5, dim3(512), smem5, st, a)
+                               : launch_pdl(lenia_fft_firinv_kernel<8, false, 1, 512>, grid5, dim3(512), smem5, st, a));
+            B200CA_LAUNCH_CHECK("lenia_fft_firinv_kernel");
+            return 0;
         }
         dim3 grid(ceil_div(g.D, ft), g.nseg, B * C);
         if (NS > 1) B200CA_CUDA(ft == 8 ? launch_pdl(lenia_fft_firinv_kernel<8, true, 2>, grid, dim3(256), smem, st, a)
