@@ -227,6 +227,13 @@ class LeniaWL(Workload):
             self.rot_i = 0
             self.rotating = self.n_rot > 1
             self.slab = None
+            # small worlds: the ring's steps (one per world, twice round) are captured into a CUDA graph -- a 20 us step is
+            # otherwise paced by the Python launch path and its jitter (B200CA_BENCH_GRAPH=0 issues every step from Python)
+            self.graph = None
+            if self.rotating and os.environ.get("B200CA_BENCH_GRAPH", "1") != "0":
+                from pyca_b200.graph import StepGraph
+
+                self.graph = StepGraph(self.autos, reps=2)
         else:
             self.slab = LeniaSlabCUDA(self.params, self.C, self.H, self.W, self.rank, self.world, device=self.device)
             g = torch.Generator(device=self.device).manual_seed(1000 + self.rank)
@@ -239,6 +246,25 @@ class LeniaWL(Workload):
             self.rot_i = (self.rot_i + 1) % self.n_rot
         else:
             self.slab.step()
+
+    def align(self):
+        """(untimed, after the warm-up) finishes the current turn of the ring so that the timed steps start at world 0"""
+        while getattr(self, "graph", None) is not None and self.rot_i != 0:
+            self.step()
+
+    def run(self, k):
+        """exactly k steps of the ring (one world per step, round-robin): whole turns of the ring by graph replay, the rest
+        step by step"""
+        g = getattr(self, "graph", None)
+        if g is not None:
+            while k > 0 and self.rot_i != 0:   # finish the current turn of the ring
+                self.step()
+                k -= 1
+            while k >= g.steps_per_replay:
+                g.replay()
+                k -= g.steps_per_replay
+        for _ in range(k):
+            self.step()
 
     def cells_per_step(self):
         return self.H * self.W * (self.world if self.replicas else 1)
@@ -286,7 +312,9 @@ class LeniaWL(Workload):
     def _l2_note(self):
         if getattr(self, "rotating", False):
             return (f"inputs larger than L2: {self.n_rot} independent worlds advanced round-robin (one world per step; a world is "
-                    f"revisited after {self.n_rot} steps), no flush kernel between timed steps")
+                    f"revisited after {self.n_rot} steps), no flush kernel between timed steps"
+                    + ("; steps issued by CUDA-graph replay (2 turns of the ring per launch), remainder from Python"
+                       if getattr(self, "graph", None) is not None else ""))
         if self.H * self.W * self.C * 8 // max(1, 1 if self.replicas else self.world) > (126 << 20):
             return "inputs larger than L2"
         return f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)"
@@ -710,11 +738,16 @@ def time_block(wl, steps, warmup, world):
     """K steps back to back between one pair of events (used when the working set exceeds L2)."""
     for _ in range(warmup):
         wl.step()
+    if hasattr(wl, "align"):
+        wl.align()
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(steps):
-        wl.step()
+    if hasattr(wl, "run"):
+        wl.run(steps)
+    else:
+        for _ in range(steps):
+            wl.step()
     e1.record()
     barrier(world)
     return e0.elapsed_time(e1)

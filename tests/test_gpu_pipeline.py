@@ -98,3 +98,41 @@ def test_c_pipe_matches_sync(family, shape):
     with pytest.raises(pyca_b200.B200CAError):
         pipe.submit(torch.zeros(1, 3, H, W), outs[0])
     pipe.close()
+
+
+def test_step_graph_matches_eager_steps():
+    """pyca_b200.graph.StepGraph: captured step() loops (PDL launches included) replay to the same bits as eager stepping."""
+    import pyca_b200
+    from pyca_b200.graph import StepGraph
+
+    params, _ = _lenia_params()
+    g = torch.Generator().manual_seed(21)
+    states = [torch.rand(1, 3, 64, 1024, generator=g) for _ in range(3)]   # N = 1024 FFT path (PDL-chained kernels)
+    mk = lambda s: pyca_b200.Lenia((64, 1024), params=params, state_init=s, device="cuda")
+    eager = [mk(s) for s in states]
+    graphed = [mk(s) for s in states]
+    sg = StepGraph(graphed, reps=2)          # refresh() itself advances every automaton by 2 warm-up steps
+    for a in eager:
+        a.step()
+        a.step()
+    for _ in range(3):
+        sg.replay()
+        for a in eager:
+            a.step()
+            a.step()
+    for a, b in zip(eager, graphed):
+        assert torch.equal(a.state, b.state) and a.frames == b.frames == 8
+    graphed[1].state[:, :, :8] = 0.25        # edit between replays -> refresh() re-captures
+    eager[1].state[:, :, :8] = 0.25
+    sg.refresh()
+    sg.replay()
+    for a in eager:
+        for _ in range(4):
+            a.step()
+    for a, b in zip(eager, graphed):
+        assert torch.equal(a.state, b.state)
+    ca = pyca_b200.CA2D((96, 200), device="cuda")
+    w0 = ca.world.clone()
+    sgc = StepGraph(ca, reps=4)
+    sgc.replay()
+    assert np.array_equal(ca.world.cpu().numpy(), orc.gol_run(w0.cpu().numpy(), 6))
