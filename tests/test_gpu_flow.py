@@ -74,3 +74,19 @@ def test_flow_lenia_shapes_vs_oracle(shape, dd):
     for _ in range(3):
         b.step()
     assert abs(float(b.total_mass()) - m0) <= 1e-5 * m0
+
+
+def test_flow_lenia_batch_of_two_parameter_sets():
+    """B = 2 worlds with different parameter files (batched params, lenia.py:89-101) through the flow kernel's batch axis."""
+    import pyca_b200
+
+    pa, pb = load_npz("params_mace_anencephalic_brakeman.npz"), load_npz("params_mace_apparent_kenalog.npz")
+    d = {k: torch.cat([t(pa[k]), t(pb[k])], dim=0) for k in ["mu", "sigma", "beta", "mu_k", "sigma_k", "weights"]}
+    d["k_size"] = int(pa["k_size"])
+    g = torch.Generator().manual_seed(2)
+    s0 = 1.3 * torch.rand(2, 3, 48, 80, generator=g)
+    a = pyca_b200.FlowLenia((2, 48, 80), params=pyca_b200.LeniaParams(param_dict=d), state_init=s0, device="cuda")
+    a.step()
+    for b, p in enumerate((pa, pb)):
+        ref = orc.flow_step(s0[b:b + 1], t(p["K"]), t(p["mu_s"]), t(p["sigma_s"]), t(p["weights_s"]), 0.1)
+        assert (a.state[b:b + 1].cpu() - ref).abs().max().item() <= 2e-5, f"world {b}"
