@@ -1,0 +1,51 @@
+"""Host-side (cold path) logic of the drop-ins that runs without a GPU: parameter handling, coefficient tables, kernel
+construction against the reference's kernels stored in the golden fixtures."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import garbi_case, load_npz, raw_param_dict, t
+
+
+def test_garbi_tables_follow_the_reference_argument_order():
+    from pyca_b200.lenia import garbi_tables
+
+    fx, garbi = garbi_case("unsuspected_lanthanotidae")
+    d = raw_param_dict(fx)
+    g = garbi_tables(d, 1, 3, 1)
+    assert g["nh"] == 8 and g["rescale"] is None and g["clip"] is None
+    co = t(fx["g_coeffs"]).reshape(9, 8, 2)
+    assert torch.equal(g["cos"], co[:, :, 0]) and torch.equal(g["sin"], co[:, :, 1])
+    # funcgen.py:99-104: 2*pi / period (fp32 tensor) * harmonics, period = 2
+    ref = 2 * torch.pi / torch.full((9, 1), 2.0) * t(fx["g_harmonics"]).reshape(9, 8)
+    assert torch.equal(g["freq"], ref)
+    assert abs(float(g["freq"][0, 1]) - math.pi) < 1e-6
+    fx2, _ = garbi_case("lenia_synth")
+    g2 = garbi_tables(raw_param_dict(fx2), 1, 2, 1)
+    assert g2["rescale"] == (-1.0, 1.0) and g2["clip"] == -0.5 and tuple(g2["stats"].shape) == (4, 2)
+
+
+@pytest.mark.parametrize("name", ["underweight_skagway", "inaesthetic_maupassant"])
+def test_kernel_construction_matches_reference_kernels(name):
+    """compute_kernel (ring kernels and the k_arbi Fourier kernels with the smooth disc mask) against the reference's `k`."""
+    import pyca_b200
+
+    fx, _ = garbi_case(name)
+    p = pyca_b200.LeniaParams(param_dict=raw_param_dict(fx))
+    K = pyca_b200.compute_kernel(p, 3)
+    assert (K - t(fx["K"])).abs().max().item() <= 1e-6
+    assert torch.allclose(K.sum(dim=(-1, -2)), torch.ones(1, 3, 3), atol=1e-5)
+    assert torch.allclose(p["weights"].sum(dim=1), torch.ones(1, 3), atol=1e-6)   # _sanitize: source weights sum to 1
+
+
+def test_cuda_only_classes_refuse_other_devices():
+    import pyca_b200
+
+    with pytest.raises(pyca_b200.B200CAError):
+        pyca_b200.CA2D((32, 32), device="cpu")
+    fx, _ = garbi_case("lenia_synth")
+    with pytest.raises(pyca_b200.B200CAError):
+        pyca_b200.Lenia((32, 64), num_channels=2, params=pyca_b200.LeniaParams(param_dict=raw_param_dict(fx), channels=2),
+                        state_init=torch.rand(1, 2, 32, 64), device="cpu")
