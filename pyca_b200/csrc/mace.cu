@@ -6,8 +6,6 @@
 // and the state once (framed layouts: the periodic wrap is a plain read), keeps E = exp(beta*Aff)
 // (halo 2) and A/Z (halo 1) of a 64x16 tile in shared memory, and writes the new state with its
 // periodic frame.  Algorithmic traffic: Aff read + state read + state write = 12 B/cell/channel.
-#include <type_traits>
-
 #include "common.cuh"
 
 namespace b200ca {
@@ -177,11 +175,7 @@ __global__ void __launch_bounds__(128) mace_fast_kernel(const MaceArgs a) {
         afn[c] = __ldg(affp + (size_t)c * pstride + (size_t)(y0 - 2 + F) * a.pitch);
         stn[c] = __ldg(stp + (size_t)c * pstride + (size_t)(y0 - 3 + F) * a.pitch);
     }
-    // One input row.  PH = (r - (y0 - 2)) mod 3 is the window slot that receives row r; slot (PH+1)%3 then holds row r-2 and
-    // (PH+2)%3 row r-1.  The slots rotate at COMPILE time (the loop below is unrolled by three phases), so the sliding
-    // windows cost no register moves; sums run in age order, i.e. exactly as a shifted window would add them.
-    auto row = [&](auto ph, const int r) {
-        constexpr int PH = decltype(ph)::value, OLD = (PH + 1) % 3, MID = (PH + 2) % 3;
+    for (int r = y0 - 2; r < rend; ++r) {
         float afc[C], stc[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -203,29 +197,29 @@ __global__ void __launch_bounds__(128) mace_fast_kernel(const MaceArgs a) {
             const float st = stc[c];   // state row r-1
             const float e = exp2f(bl2 * af);
             const float re = __shfl_up_sync(0xffffffffu, e, 1) + e + __shfl_down_sync(0xffffffffu, e, 1);
-            E[c][PH] = e;
-            AF[c][PH] = af;
-            rE[c][PH] = re;
-            const float z = rE[c][OLD] + rE[c][MID] + rE[c][PH];      // Z(r-1)
+            // shift windows
+            E[c][0] = E[c][1]; E[c][1] = E[c][2]; E[c][2] = e;
+            AF[c][0] = AF[c][1]; AF[c][1] = AF[c][2]; AF[c][2] = af;
+            rE[c][0] = rE[c][1]; rE[c][1] = rE[c][2]; rE[c][2] = re;
+            const float z = rE[c][0] + rE[c][1] + rE[c][2];           // Z(r-1)
             const float gq = __fdividef(st, z);                        // G(r-1)
             const float rg = __shfl_up_sync(0xffffffffu, gq, 1) + gq + __shfl_down_sync(0xffffffffu, gq, 1);
-            const float rg3 = rG[c][OLD], rg2 = rG[c][MID];           // rG(r-3), rG(r-2): written two / one rows ago
-            rG[c][PH] = rg;                                            // rG(r-1) takes the slot of rG(r-4)
-            outv[c] = E[c][OLD] * (rg3 + rg2 + rg);                    // out(r-2)
+            rG[c][0] = rG[c][1]; rG[c][1] = rG[c][2]; rG[c][2] = rg;
+            outv[c] = E[c][0] * (rG[c][0] + rG[c][1] + rG[c][2]);      // out(r-2)
         }
         const int yo = r - 2;
-        if (yo < y0 || !out_lane) return;   // window still filling / halo lane
+        if (yo < y0 || !out_lane) continue;   // window still filling / halo lane
         if (a.alpha_on) {
-            float mx = AF[0][OLD], tot = outv[0];
+            float mx = AF[0][0], tot = outv[0];
 #pragma unroll
             for (int c = 1; c < C; ++c) {
-                mx = fmaxf(mx, AF[c][OLD]);
+                mx = fmaxf(mx, AF[c][0]);
                 tot += outv[c];
             }
             float num[C], den = 0.f;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                num[c] = exp2f(bl2 * (AF[c][OLD] - mx));
+                num[c] = exp2f(bl2 * (AF[c][0] - mx));
                 den += num[c];
             }
             const float inv = __fdividef(1.f, den);
@@ -239,11 +233,6 @@ __global__ void __launch_bounds__(128) mace_fast_kernel(const MaceArgs a) {
             pl[(size_t)(yo + F) * a.pitch + x + F] = outv[c];
             if (edge) mace_mirrors(pl, a.H, a.W, a.pitch, yo, x, outv[c], a.row_wrap != 0);
         }
-    };
-    for (int r = y0 - 2; r < rend; r += 3) {
-        row(std::integral_constant<int, 0>{}, r);
-        if (r + 1 < rend) row(std::integral_constant<int, 1>{}, r + 1);
-        if (r + 2 < rend) row(std::integral_constant<int, 2>{}, r + 2);
     }
 }
 
