@@ -561,8 +561,6 @@ class FlowWL(MaceWL):
                 "l2": "inputs larger than L2" if self.H * self.W * 12 > (126 << 20) else "flushed between timed steps"}
 
     def e2e_setup(self):
-        import pyca_b200
-
         self.h_out = torch.empty(1, 3, self.H, self.W).pin_memory()
 
     def e2e_step(self):

@@ -173,7 +173,11 @@ class CA2D(Automaton):
         wm = self._worldmap
         if not (wm.is_cuda and wm.dtype == torch.float32 and wm.is_contiguous() and tuple(wm.shape) == (3, self.h, self.w)):
             wm = self._worldmap = wm.to(self.device, torch.float32).contiguous()
-        d = (self.decay_speed * self.highlight_color).tolist()  # fp32 product, as in the reference expression
+        key = (id(self.highlight_color), self.highlight_color._version, self.decay_speed)
+        if getattr(self, "_decay_key", None) != key:   # 3 floats to the host only when the colour or the speed changed
+            self._decay = (self.decay_speed * self.highlight_color).tolist()  # fp32 product, as in the reference expression
+            self._decay_key = key
+        d = self._decay
         fb = self._frame()
         pw = self._packed
         with _lib.device_guard(pw.device):

@@ -26,7 +26,7 @@ class StepGraph:
         for a in self.autos:
             if getattr(a, "has_food", False) or getattr(a, "rng", None) == "torch":
                 raise _lib.B200CAError("StepGraph: this automaton takes host-side decisions inside step(); not capturable")
-        self.device = torch.device(self.autos[0].device if not isinstance(self.autos[0].device, str) else self.autos[0].device)
+        self.device = torch.device(self.autos[0].device)
         self.graph = None
         self.refresh()
 

@@ -76,6 +76,17 @@ def exchange_ghost_rows(blocks_up_send: List[torch.Tensor], blocks_up_recv: List
         w.wait()
 
 
+def build_exchange_ops(blocks_up_send, blocks_up_recv, blocks_down_send, blocks_down_recv, rank: int, world: int, group=None):
+    """The P2P operation list of one halo exchange (same posting order as exchange_ghost_rows), built once per buffer
+    and re-posted every step: the slab step is short enough at 8 GPUs for per-step Python object churn to show."""
+    up, down = ring_neighbours(rank, world)
+    ops = [dist.P2POp(dist.isend, s, down, group) for s in blocks_down_send]
+    ops += [dist.P2POp(dist.isend, s, up, group) for s in blocks_up_send]
+    ops += [dist.P2POp(dist.irecv, r, up, group) for r in blocks_up_recv]
+    ops += [dist.P2POp(dist.irecv, r, down, group) for r in blocks_down_recv]
+    return ops
+
+
 class GolSlab:
     """Bit-packed Game-of-Life row slab with `ghost` ghost rows per side (device-agnostic bookkeeping).
 
@@ -170,8 +181,17 @@ class LeniaSlab:
 
     def exchange(self, t=None, group=None):
         t = self.buf if t is None else t
-        us, ur, ds, dr = self.ghost_blocks(t)
-        exchange_ghost_rows(us, ur, ds, dr, self.rank, self.world, group)
+        if self.world == 1:
+            us, ur, ds, dr = self.ghost_blocks(t)
+            exchange_ghost_rows(us, ur, ds, dr, self.rank, self.world, group)
+            return
+        cache = self.__dict__.setdefault("_exchange_ops", {})
+        key = (t.data_ptr(), id(group))
+        ops = cache.get(key)
+        if ops is None:
+            ops = cache[key] = build_exchange_ops(*self.ghost_blocks(t), self.rank, self.world, group)
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -298,7 +318,9 @@ class LeniaSlabCUDA(LeniaSlab):
                   1 if self.world == 1 else 0, t0, t1, _lib.current_stream(self.device))
 
     def step(self, group=None):
-        with torch.cuda.device(self.device):
+        from . import _lib
+
+        with _lib.device_guard(self.device):
             if self.world == 1:
                 self._launch(0, 0)
             elif self.use_fft and self.overlap:
