@@ -195,34 +195,32 @@ __global__ void __launch_bounds__(128 * NG, 1) nca_update_tc_kernel(const NcaArg
         {
             const int xm = xc == 0 ? a.W - 1 : xc - 1, xp = xc == a.W - 1 ? 0 : xc + 1;
             const int ym = yc == 0 ? a.H - 1 : yc - 1, yp = yc == a.H - 1 ? 0 : yc + 1;
-            // 32-bit element offsets inside this world's (16,H,W) block: one IMAD.WIDE per load instead of 64-bit chains
-            const uint32_t uplane = (uint32_t)plane;
-            uint32_t o00 = ym * a.W + xm, o01 = ym * a.W + xc, o02 = ym * a.W + xp;
-            uint32_t o10 = yc * a.W + xm, o11 = yc * a.W + xc, o12 = yc * a.W + xp;
-            uint32_t o20 = yp * a.W + xm, o21 = yp * a.W + xc, o22 = yp * a.W + xp;
+            // Addressing: the nine neighbour offsets are per-thread 32-bit BYTE offsets inside a plane, fixed for the tile; the
+            // plane base is warp-uniform and steps by `plane` per channel.  A load is then [uniform base + 32-bit lane offset]
+            // -- one instruction, where per-channel 64-bit pointer arithmetic cost ~3 integer instructions per load.
+            const uint32_t b00 = 4u * (ym * a.W + xm), b01 = 4u * (ym * a.W + xc), b02 = 4u * (ym * a.W + xp);
+            const uint32_t b10 = 4u * (yc * a.W + xm), b11 = 4u * (yc * a.W + xc), b12 = 4u * (yc * a.W + xp);
+            const uint32_t b20 = 4u * (yp * a.W + xm), b21 = 4u * (yp * a.W + xc), b22 = 4u * (yp * a.W + xp);
+            auto ld = [](const char *base, uint32_t off) { return __ldg(reinterpret_cast<const float *>(base + off)); };
             float p[NCA_K1];
 #pragma unroll
             for (int c = 0; c < NCA_N; ++c) {
-                const float *pl = sb;
-                if (c > 0) {
-                    o00 += uplane; o01 += uplane; o02 += uplane; o10 += uplane; o11 += uplane; o12 += uplane;
-                    o20 += uplane; o21 += uplane; o22 += uplane;
-                }
-                const float ctr = __ldg(pl + o11);
+                const char *pl = reinterpret_cast<const char *>(sb + (size_t)c * plane);
+                const float ctr = ld(pl, b11);
                 p[16 + c] = ctr;
                 if (c < 8) {
-                    const float l0 = __ldg(pl + o00), r0 = __ldg(pl + o02);
-                    const float l1 = __ldg(pl + o10), r1 = __ldg(pl + o12);
-                    const float l2 = __ldg(pl + o20), r2 = __ldg(pl + o22);
+                    const float l0 = ld(pl, b00), r0 = ld(pl, b02);
+                    const float l1 = ld(pl, b10), r1 = ld(pl, b12);
+                    const float l2 = ld(pl, b20), r2 = ld(pl, b22);
                     p[c] = ((r0 - l0) + 2.f * (r1 - l1) + (r2 - l2)) * 0.125f;
                     if (c == 3) {
-                        const float t1 = __ldg(pl + o01), b1 = __ldg(pl + o21);
+                        const float t1 = ld(pl, b01), b1 = ld(pl, b21);
                         const float m = fmaxf(fmaxf(fmaxf(l0, r0), fmaxf(l1, r1)), fmaxf(fmaxf(l2, r2), fmaxf(t1, b1)));
                         alive0 = fmaxf(m, ctr) > 0.1f;
                     }
                 } else {
-                    const float t0 = __ldg(pl + o00), t1 = __ldg(pl + o01), t2 = __ldg(pl + o02);
-                    const float b0 = __ldg(pl + o20), b1 = __ldg(pl + o21), b2 = __ldg(pl + o22);
+                    const float t0 = ld(pl, b00), t1 = ld(pl, b01), t2 = ld(pl, b02);
+                    const float b0 = ld(pl, b20), b1 = ld(pl, b21), b2 = ld(pl, b22);
                     p[c] = ((b0 - t0) + 2.f * (b1 - t1) + (b2 - t2)) * 0.125f;
                 }
             }
@@ -385,6 +383,7 @@ int nca_step_tc(const NcaArgs &a, cudaStream_t st) {
         B200CA_CUDA(cudaFuncSetAttribute(nca_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
         attr_done[dev & 63] = true;
     }
+    B200CA_REQUIRE((long long)a.H * a.W <= (1LL << 30), "nca_step: a plane must stay below 2^30 cells (32-bit byte offsets)");
     const int tiles_x = ceil_div(a.W, 32), tiles_y = ceil_div(a.H, 4);
     const long long ntiles = (long long)tiles_x * tiles_y * a.B;
     const int grid = (int)std::min<long long>(ceil_div64(ntiles, NG), (long long)num_sms());
