@@ -933,7 +933,7 @@ extern "C" int b200ca_lenia_step_fft_phase(const float *state_in, float *state_o
         static int nt512 = -1;
         if (nt512 < 0) nt512 = getenv("B200CA_FFT_NT512") ? atoi(getenv("B200CA_FFT_NT512")) : 1;
         const long long ctas8 = (long long)ceil_div(g.D, 8) * g.nseg * B * C;
-        if (nt512 && fused < 0 && ctas8 <= (long long)num_sms()) {
+        if (nt512 && fused < 0 && ctas8 <= (long long)num_sms() * (nt512 >= 2 ? nt512 : 1)) {
             const size_t smem5 = ((size_t)8 * XB + 1024 + 8 * 1024) * sizeof(float2);  // row buffers + twiddles + staged state
             static bool attr5 = false;
             if (!attr5) {

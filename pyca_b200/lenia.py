@@ -145,8 +145,8 @@ class Lenia(Automaton):
         self.C = num_channels
         self.dt = dt
         if params is None:
-            raise _lib.B200CAError("random parameter generation is not part of the step path: pass params= (LeniaParams, "
-                                   "dict or a demo_data .pt path)")
+            # random parameters with the reference's prior (lenia.py:68-70 -> LeniaParams.default_gen)
+            params = LeniaParams.default_gen(batch_size=self.batch, num_channels=self.C, k_size=31)
         self.g_arbi = False
         self.k_arbi = False
         self._fs = FramedState(self.batch, self.C, self.h, self.w, device)
@@ -154,7 +154,7 @@ class Lenia(Automaton):
         self._init_family_buffers()
         self.update_params(params)
         if state_init is None:
-            state_init = torch.rand((self.batch, self.C, self.h, self.w))
+            state_init = self._init_circle()
         self.state = state_init
         self.display_kernel = False
         self.save_dir = save_dir
@@ -168,6 +168,16 @@ class Lenia(Automaton):
 
     def _init_family_buffers(self):
         pass
+
+    def _init_circle(self, radius=None) -> torch.Tensor:
+        """Initial state when none is given: noise inside a centred disc of radius 3 * k_size, zero outside -- the shape of
+        the reference's `set_init_circle` (lenia.py:254-287).  The reference fills the disc with Perlin noise from the
+        third-party `pyperlin` package (absent here, and not part of the step path); uniform noise stands in for it."""
+        radius = self.k_size * 3 if radius is None else radius
+        X, Y = torch.meshgrid(torch.linspace(-self.h // 2, self.h // 2, self.h), torch.linspace(-self.w // 2, self.w // 2, self.w),
+                              indexing="ij")
+        disc = torch.sqrt(X**2 + Y**2) < radius
+        return torch.rand((self.batch, self.C, self.h, self.w)) * disc
 
     # ---- public state tensor ------------------------------------------------------------------
     @property

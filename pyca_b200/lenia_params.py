@@ -81,6 +81,32 @@ class LeniaParams:
     def k_mult(self):
         return self.param_dict["k_mult"]
 
+    @staticmethod
+    def default_gen(batch_size, num_channels=3, k_size=31, k_mult=1, device="cpu") -> "LeniaParams":
+        """Random ring-kernel parameters with the reference's prior (leniaparams.py:309-353 + `_universal_params`
+        :619-646), drawn from torch's global generator in the reference's order -- what `Lenia(params=None)` uses
+        (lenia.py:68-70).  Same seed, same parameters."""
+        CK = num_channels * k_mult
+        if k_mult == 1:
+            weights = torch.rand(batch_size, num_channels, num_channels, device=device) * (
+                1 - 0.8 * torch.diag(torch.ones(num_channels, device=device)))
+        else:
+            weights = torch.rand(batch_size, CK, num_channels, device=device)
+        mu = 0.7 * torch.rand((batch_size, CK, num_channels), device=device)
+        sigma = mu / (math.sqrt(2 * math.log(2))) * 0.8 * torch.rand((batch_size, CK, num_channels), device=device) + 1e-4
+        d = {
+            "mu": mu,
+            "sigma": sigma,
+            "beta": torch.rand((batch_size, CK, num_channels, 3), device=device),
+            "mu_k": 0.5 + 0.2 * torch.randn((batch_size, CK, num_channels, 3), device=device),
+            "sigma_k": 0.05 * (1 + torch.clamp(0.3 * torch.randn((batch_size, CK, num_channels, 3), device=device), min=-0.9) + 1e-4),
+            "k_size": k_size, "weights": weights, "k_mult": k_mult, "num_channels": num_channels,
+        }
+        # the reference builds LeniaParams twice on this path (default_gen returns one, the constructor wraps its dict in
+        # another, leniaparams.py:47-52), so the weights are normalised twice: kept, it is a 1-ulp difference
+        once = LeniaParams(param_dict=d, channels=num_channels, device=device)
+        return LeniaParams(param_dict=once.param_dict, channels=num_channels, device=device)
+
     def slice_channels(self, c: int) -> "LeniaParams":
         """First `c` channels of every tensor (``v[:, :c*k_mult, :c]``); weights re-normalised by _sanitize."""
         km = self.k_mult

@@ -377,9 +377,22 @@ def gen_flow():
     save("flow.npz", **out)
 
 
+def gen_default_params():
+    """LeniaParams(batch_size, k_size, channels) of the reference (random parameters, leniaparams.py:309-353) under a fixed
+    torch seed, after its _sanitize: what Lenia(params=None) starts from."""
+    out = {}
+    for tag, (B, C, km) in {"b2c3": (2, 3, 1), "b1c2k2": (1, 2, 2)}.items():
+        torch.manual_seed(123)
+        p = REF.LeniaParams(batch_size=B, k_size=31, channels=C, k_mult=km)
+        for k in PARAM_KEYS:
+            out[f"{tag}_{k}"] = p[k]
+        out[f"{tag}_meta"] = np.array([B, C, km, p["k_size"]], dtype=np.int64)
+    save("default_params.npz", **out)
+
+
 if __name__ == "__main__":
     only = [a[2:] for a in sys.argv[1:] if a.startswith("--")]   # e.g. --draw regenerates draw.npz alone
-    gens = {"gol": gen_gol, "family": gen_lenia_family, "kmult": gen_kmult, "nca": gen_nca, "draw": gen_draw, "garbi": gen_garbi, "food": gen_food, "flow": gen_flow}
+    gens = {"gol": gen_gol, "family": gen_lenia_family, "kmult": gen_kmult, "nca": gen_nca, "draw": gen_draw, "garbi": gen_garbi, "food": gen_food, "flow": gen_flow, "default_params": gen_default_params}
     for name, fn in gens.items():
         if not only or name in only:
             fn()

@@ -392,3 +392,22 @@ def test_mace_food_subsystem_golden(tag):
     a.draw()
     assert (a._worldmap.cpu() - t(fx[f"{tag}_wm"])).abs().max().item() <= 1e-5 * i
     assert (a.worldmap.astype(np.int32) - fx[f"{tag}_frame"].astype(np.int32)).__abs__().max() <= 1   # uint8 truncation of ~1e-5 diffs
+
+
+def test_constructors_without_params_or_state():
+    """Lenia(size) as MainWindow builds it (no params, no state): random parameters with the reference's prior, a noise disc
+    as initial state, and steps that stay finite and inside [0, 1]."""
+    import pyca_b200
+
+    torch.manual_seed(3)
+    a = pyca_b200.Lenia((96, 128), device="cuda")
+    assert tuple(a.state.shape) == (1, 3, 96, 128) and a.k_size == 31
+    assert float(a.state[0, :, 0, 0].abs().max()) == 0.0 and float(a.state.max()) > 0.5   # disc in the centre, nothing outside
+    for _ in range(3):
+        a.step()
+    s = a.state
+    assert bool(torch.isfinite(s).all()) and float(s.min()) >= 0.0 and float(s.max()) <= 1.0
+    m = pyca_b200.MaCELeniaXChan((96, 128), device="cuda")
+    m0 = float(m.total_mass())
+    m.step()
+    assert abs(float(m.total_mass()) - m0) <= 1e-5 * m0

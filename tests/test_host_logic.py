@@ -49,3 +49,17 @@ def test_cuda_only_classes_refuse_other_devices():
     with pytest.raises(pyca_b200.B200CAError):
         pyca_b200.Lenia((32, 64), num_channels=2, params=pyca_b200.LeniaParams(param_dict=raw_param_dict(fx), channels=2),
                         state_init=torch.rand(1, 2, 32, 64), device="cpu")
+
+
+@pytest.mark.parametrize("tag", ["b2c3", "b1c2k2"])
+def test_default_gen_draws_the_reference_parameters(tag):
+    """Lenia(params=None) starts from LeniaParams.default_gen: same torch seed -> the reference's random parameters."""
+    import pyca_b200
+
+    fx = load_npz("default_params.npz")
+    B, C, km, ks = [int(v) for v in fx[f"{tag}_meta"]]
+    torch.manual_seed(123)
+    p = pyca_b200.LeniaParams.default_gen(batch_size=B, num_channels=C, k_size=ks, k_mult=km)
+    for k in ["mu", "sigma", "beta", "mu_k", "sigma_k", "weights"]:
+        assert torch.equal(p[k], t(fx[f"{tag}_{k}"])), k
+    assert p.k_size == 31 and p.k_mult == km
