@@ -786,6 +786,12 @@ def run_reference(args, rank, world):
 
         wl.fx = load_npz("nca_betta.npz")
     torch.set_num_threads(os.cpu_count() or 1)
+    if torch.cuda.is_available():
+        # Measured on the B200 box (tools/cpu_arm_probe.py): the same torch CPU step runs at 0.98 ms in a process that has
+        # created a CUDA context and a pinned allocation and at 1.9 ms in one that has not (16 threads either way).  The CPU
+        # arm gets the faster setting -- it is also the one `cpu_baseline` of the CUDA arm runs under.  No kernel is launched.
+        torch.zeros(1, device="cuda")
+        torch.empty(1 << 20).pin_memory()
     wl.cpu_setup()
     # one "step" of this arm = a bounded sample of `reps` consecutive CPU steps (>= 50 ms of work), so that K steps are not
     # dominated by thread-pool start-up; a 1 s untimed spin-up precedes the W warm-up steps

@@ -400,14 +400,14 @@ def test_constructors_without_params_or_state():
     import pyca_b200
 
     torch.manual_seed(3)
-    a = pyca_b200.Lenia((96, 128), device="cuda")
-    assert tuple(a.state.shape) == (1, 3, 96, 128) and a.k_size == 31
+    a = pyca_b200.Lenia((256, 320), device="cuda")      # disc radius 3 * 31 = 93 < distance of the corners
+    assert tuple(a.state.shape) == (1, 3, 256, 320) and a.k_size == 31
     assert float(a.state[0, :, 0, 0].abs().max()) == 0.0 and float(a.state.max()) > 0.5   # disc in the centre, nothing outside
     for _ in range(3):
         a.step()
     s = a.state
     assert bool(torch.isfinite(s).all()) and float(s.min()) >= 0.0 and float(s.max()) <= 1.0
-    m = pyca_b200.MaCELeniaXChan((96, 128), device="cuda")
+    m = pyca_b200.MaCELeniaXChan((256, 320), device="cuda")
     m0 = float(m.total_mass())
     m.step()
     assert abs(float(m.total_mass()) - m0) <= 1e-5 * m0
