@@ -405,7 +405,8 @@ class GolWL(Workload):
 
     def dominant(self):
         cells = self.H * self.W // self.world
-        return {"kernel": "gol_small_kernel" if self.steps_per_call > 1 else "gol_fast_kernel", "bytes": cells // 4 * self.steps_per_call,
+        return {"kernel": ("gol_rows_kernel" if self.W <= 256 and self.H <= 1024 else "gol_small_kernel") if self.steps_per_call > 1
+                else "gol_fast_kernel", "bytes": cells // 4 * self.steps_per_call,
                 "fma": 0}
 
     def config(self):

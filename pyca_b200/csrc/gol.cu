@@ -393,6 +393,85 @@ __global__ void __launch_bounds__(GOL_SMALL_THREADS) gol_small_kernel(const uint
         if (jj[k] >= 0) out[(size_t)(off_q[k] / g.wpr) * g.stride + jj[k]] = cur[off_q[k] + jj[k]];
 }
 
+// ---- tiny worlds (<= 256 cells wide, <= 1024 rows): one ROW per thread, held in registers for all generations ----------
+// The 250x250 world of simulate.py is 8 words by 250 rows.  A thread owns its whole row, so the horizontal neighbourhood
+// (with the periodic wrap through the partial last word) never leaves its registers; per generation it publishes the row's
+// 2-bit sums west+centre+east as 8 uint2 in shared memory, one __syncthreads() later reads the two neighbouring rows' sums,
+// and applies the rule on the 9-cell count.  The exchange buffer ping-pongs by generation parity, so one barrier per
+// generation is enough.  ~170 instructions per thread and generation instead of nine shared-memory row fetches with wrap
+// logic per WORD in gol_small_kernel.
+template <int WPR, bool LIFE>
+__global__ void __launch_bounds__(1024) gol_rows_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, GolGeom g,
+                                                        uint32_t s_mask, uint32_t b_mask, int nsteps) {
+    extern __shared__ uint2 grs[];  // [2][WPR][rows_pad]
+    const int r = threadIdx.x, rows_pad = blockDim.x;
+    const bool live = r < g.H;
+    const int nb = g.W - 32 * (WPR - 1);  // valid bits of the last word
+    RuleMasks rm;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        rm.s[k] = ((s_mask >> k) & 1u) ? 0xffffffffu : 0u;
+        rm.b[k] = ((b_mask >> k) & 1u) ? 0xffffffffu : 0u;
+    }
+    uint32_t w[WPR];
+#pragma unroll
+    for (int j = 0; j < WPR; ++j) w[j] = live ? in[(size_t)r * g.stride + j] : 0u;
+    w[WPR - 1] &= g.last_mask;
+    // rows above / below (periodic, or nothing beyond the edge of an open world)
+    const int ra = r > 0 ? r - 1 : g.H - 1, rb = r + 1 < g.H ? r + 1 : 0;
+    const uint32_t ma = (g.vert_open && r == 0) ? 0u : 0xffffffffu, mb = (g.vert_open && r == g.H - 1) ? 0u : 0xffffffffu;
+    for (int step = 0; step < nsteps; ++step) {
+        uint2 *buf = grs + (size_t)(step & 1) * WPR * rows_pad;
+        uint32_t q0[WPR], q1[WPR];
+#pragma unroll
+        for (int j = 0; j < WPR; ++j) {
+            // west: cell x-1 at bit x; the cell left of x = 0 is cell W-1 = bit nb-1 of the last word (and the other way round)
+            const uint32_t prev = j > 0 ? w[j - 1] >> 31 : (w[WPR - 1] >> (nb - 1)) & 1u;
+            const uint32_t west = (w[j] << 1) | prev;
+            uint32_t east = w[j] >> 1;
+            if (j < WPR - 1) east |= w[j + 1] << 31;
+            else east |= (w[0] & 1u) << (nb - 1);
+            q0[j] = west ^ east ^ w[j];
+            q1[j] = (west & east) | (w[j] & (west ^ east));
+            if (j == WPR - 1) {  // the shifted-in bits beyond the world stay out of the sums
+                q0[j] &= g.last_mask;
+                q1[j] &= g.last_mask;
+            }
+            buf[j * rows_pad + r] = make_uint2(q0[j], q1[j]);
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < WPR; ++j) {
+                const uint2 a = buf[j * rows_pad + ra], b = buf[j * rows_pad + rb];
+                w[j] = gol_rule9<LIFE>(a.x & ma, a.y & ma, q0[j], q1[j], b.x & mb, b.y & mb, w[j], rm);
+            }
+            w[WPR - 1] &= g.last_mask;
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < WPR; ++j) out[(size_t)r * g.stride + j] = w[j];
+    }
+}
+
+template <int WPR>
+static int launch_gol_rows(const uint32_t *a, uint32_t *dst, const GolGeom &g, uint32_t s_mask, uint32_t b_mask, int nsteps,
+                           cudaStream_t st) {
+    const int threads = (g.H + 31) / 32 * 32;
+    const size_t smem = (size_t)2 * WPR * threads * sizeof(uint2);
+    const bool life = (s_mask == 0b1100u && b_mask == 0b1000u);
+    if (life) {
+        if (smem > 48 * 1024) B200CA_CUDA(cudaFuncSetAttribute(gol_rows_kernel<WPR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gol_rows_kernel<WPR, true><<<1, threads, smem, st>>>(a, dst, g, s_mask, b_mask, nsteps);
+    } else {
+        if (smem > 48 * 1024) B200CA_CUDA(cudaFuncSetAttribute(gol_rows_kernel<WPR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gol_rows_kernel<WPR, false><<<1, threads, smem, st>>>(a, dst, g, s_mask, b_mask, nsteps);
+    }
+    B200CA_LAUNCH_CHECK("gol_rows_kernel");
+    return 0;
+}
+
 // ---- pack / unpack / population / random fill ---------------------------------------------------
 template <typename T>
 __global__ void gol_pack_kernel(const T *__restrict__ world, uint32_t *__restrict__ bits, int H, int W, int stride, int wpr) {
@@ -610,6 +689,18 @@ extern "C" int b200ca_gol_run(uint32_t *a, uint32_t *b, int H, int W, int stride
             const bool life = (s_mask == 0b1100u && b_mask == 0b1000u);
             uint32_t *dst = (nsteps & 1) ? b : a;
             cudaStream_t st = as_stream(stream);
+            if (g.wpr <= 8 && H <= 1024 && H >= 2) {  // a row per thread, in registers
+                switch (g.wpr) {
+                    case 1: return launch_gol_rows<1>(a, dst, g, s_mask, b_mask, nsteps, st);
+                    case 2: return launch_gol_rows<2>(a, dst, g, s_mask, b_mask, nsteps, st);
+                    case 3: return launch_gol_rows<3>(a, dst, g, s_mask, b_mask, nsteps, st);
+                    case 4: return launch_gol_rows<4>(a, dst, g, s_mask, b_mask, nsteps, st);
+                    case 5: return launch_gol_rows<5>(a, dst, g, s_mask, b_mask, nsteps, st);
+                    case 6: return launch_gol_rows<6>(a, dst, g, s_mask, b_mask, nsteps, st);
+                    case 7: return launch_gol_rows<7>(a, dst, g, s_mask, b_mask, nsteps, st);
+                    default: return launch_gol_rows<8>(a, dst, g, s_mask, b_mask, nsteps, st);
+                }
+            }
             if (life) {
                 if (smem > 48 * 1024) B200CA_CUDA(cudaFuncSetAttribute(gol_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 gol_small_kernel<true><<<1, GOL_SMALL_THREADS, smem, st>>>(a, dst, g, s_mask, b_mask, nsteps);

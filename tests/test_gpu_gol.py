@@ -157,7 +157,8 @@ def test_host_entry_point():
     assert np.array_equal(out, orc.gol_run(w0, 9))
 
 
-@pytest.mark.parametrize("shape", [(250, 250), (1, 1), (5, 31), (64, 64), (100, 257), (300, 1024), (37, 1000)])
+@pytest.mark.parametrize("shape", [(250, 250), (1, 1), (5, 31), (64, 64), (100, 257), (300, 1024), (37, 1000), (2, 33), (1024, 256),
+                                   (33, 224), (200, 97), (999, 1), (31, 160)])
 def test_small_world_multi_generation_kernel(shape):
     """b200ca_gol_run with nsteps >= 2 on a world that fits in shared memory: all generations in one launch."""
     import pyca_b200
