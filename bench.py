@@ -667,7 +667,7 @@ class NcaWL(Workload):
         self.cw = [t(self.fx[k]) for k in ("W1", "b1", "W2", "b2")]
 
     def cpu_step(self):
-        mask = torch.rand(self.cB, 1, self.H, self.W) <= 0.5
+        mask = torch.rand(self.cB, 1, self.H, self.W, device=self.cstate.device) <= 0.5
         self.cstate = self.orc.nca_step(self.cstate, *self.cw, mask)
 
     def cpu_cells_per_step(self):
@@ -769,6 +769,33 @@ def cpu_baseline(wl, budget_s=12.0):
             "sample": f"{n} x {wl.cpu_sample()}, {el:.1f} s", "ms_per_step": el / n * 1e3}
 
 
+def torch_gpu_baseline(wl, device, budget_s=1.5):
+    """Informative column: the same torch formulation of the step -- the oracle port of the reference's ops,
+    i.e. what `python simulate.py -d cuda` executes -- on this GPU instead of the host cores."""
+    wl.cpu_setup()
+    for k, v in list(vars(wl).items()):
+        if k.startswith("c") and isinstance(v, torch.Tensor):
+            setattr(wl, k, v.to(device))
+        elif k.startswith("c") and isinstance(v, list) and v and isinstance(v[0], torch.Tensor):
+            setattr(wl, k, [x.to(device) for x in v])
+    for _ in range(2):
+        wl.cpu_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        wl.cpu_step()
+        n += 1
+        if n % 4 == 0:
+            torch.cuda.synchronize()
+            if time.perf_counter() - t0 > budget_s or n >= 400:
+                break
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t0
+    return {"value": wl.cpu_cells_per_step() * n / el / 1e9, "unit": "GCUPS", "ms_per_step": el / n * 1e3,
+            "sample": f"{n} x {wl.cpu_sample()} with every tensor on the GPU"}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU implementation of the path (oracle port), all host threads, rank 0 only."""
     if rank != 0:
@@ -795,10 +822,11 @@ def run_reference(args, rank, world):
         torch.empty(1 << 20).pin_memory()
     wl.cpu_setup()
     # one "step" of this arm = a bounded sample of `reps` consecutive CPU steps (>= 50 ms of work), so that K steps are not
-    # dominated by thread-pool start-up; a 1 s untimed spin-up precedes the W warm-up steps
+    # dominated by start-up effects; a 4 s untimed spin-up precedes the W warm-up steps (on the box the step time keeps
+    # falling for the first ~3 s of a fresh process: 1.5, 1.1, 0.98 ms in consecutive 2 s windows)
     t0 = time.perf_counter()
     n0 = 0
-    while time.perf_counter() - t0 < 1.0 or n0 < 1:
+    while time.perf_counter() - t0 < 4.0 or n0 < 1:
         wl.cpu_step()
         n0 += 1
     t_one = (time.perf_counter() - t0) / n0
@@ -960,6 +988,11 @@ def main():
                     cb = cpu_baseline(ow, budget_s=3.0)
                     ent["cpu_gcups"] = cb["value"]
                     ent["cpu_sample"] = cb["sample"]
+                    try:
+                        ent["torch_gpu_gcups"] = torch_gpu_baseline(ow, device)["value"]
+                    except Exception as e:
+                        ent["torch_gpu_gcups"] = None
+                        ent["torch_gpu_error"] = repr(e)[:120]
                 extras[other] = ent
                 del ow
                 torch.cuda.empty_cache()
@@ -1030,15 +1063,20 @@ def main():
                 sharded[big] = {"error": repr(e)[:300]}
 
     cpu = None
+    torch_gpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(wl)
+        try:
+            torch_gpu = torch_gpu_baseline(wl, device)
+        except Exception as e:
+            torch_gpu = {"value": None, "error": repr(e)[:160]}
 
     if rank == 0:
         line = {"metric": "cell-updates/sec", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": wl.scaling, "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.config(),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": wl.launches_per_step() * args.steps, "roofline": roofline,
-                "cpu_baseline": cpu, "per_model": extras, "sharded": sharded}
+                "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu, "per_model": extras, "sharded": sharded}
         emit(line)
     if world > 1:
         torch.distributed.barrier()

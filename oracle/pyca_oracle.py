@@ -279,8 +279,8 @@ def flow_sobel(x):
     """flow_lenia.py:6-47: per-channel 3x3 Sobel cross-correlations with ZERO padding ("same"), no 1/8 factor.
     x (B,C,H,W) -> (B,C,2,H,W): component 0 = derivative along the width, 1 = along the height."""
     C = x.shape[1]
-    k_w = torch.tensor([[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]], dtype=x.dtype).tile((C, 1, 1, 1))
-    k_h = torch.tensor([[-1, -2, -1], [0, 0, 0], [1, 2, 1]], dtype=x.dtype).tile((C, 1, 1, 1))
+    k_w = torch.tensor([[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]], dtype=x.dtype, device=x.device).tile((C, 1, 1, 1))
+    k_h = torch.tensor([[-1, -2, -1], [0, 0, 0], [1, 2, 1]], dtype=x.dtype, device=x.device).tile((C, 1, 1, 1))
     sw = F.conv2d(x, k_w, groups=C, stride=1, padding="same")
     sh = F.conv2d(x, k_h, groups=C, stride=1, padding="same")
     return torch.stack((sw, sh), dim=2)
@@ -300,7 +300,7 @@ def flow_reintegrate(state, flow, dt=0.1, dd=2, sigma=0.65):
     clip(dt * flow); a destination collects the overlap with the squares of its (2dd+1)^2 rolled neighbours.  Positions
     are ABSOLUTE (x + 0.5), so a source rolled in across the world edge never overlaps: the flow is not periodic."""
     B, C, H, W = state.shape
-    mx, my = torch.meshgrid(torch.arange(W), torch.arange(H), indexing="ij")
+    mx, my = torch.meshgrid(torch.arange(W, device=state.device), torch.arange(H, device=state.device), indexing="ij")
     pos = (torch.dstack((mx, my)) + 0.5).to(state.dtype)             # (W,H,2), pos[x,y] = (x+.5, y+.5)
     flow_perm = flow.permute(0, 1, 4, 3, 2)                          # (B,C,W,H,2)
     state_perm = state.permute(0, 1, 3, 2)                           # (B,C,W,H)
@@ -345,7 +345,7 @@ def nca_perception(state):
     """(B,n,H,W) -> (B,3n,H,W): grouped circular sobel conv then the state (nca.py:328-344).
     With groups=n and 2n output channels, output o reads input channel o//2."""
     n = state.shape[1]
-    kern = sobel_kernels(n).to(state.dtype)
+    kern = sobel_kernels(n).to(device=state.device, dtype=state.dtype)
     p = F.pad(state, (1, 1, 1, 1), mode="circular")
     return torch.cat([F.conv2d(p, kern, groups=n), state], dim=1)
 
