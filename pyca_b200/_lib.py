@@ -10,7 +10,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200ca.so")
+LIB_PATH = os.environ.get("B200CA_LIB") or os.path.join(_HERE, "libb200ca.so")  # (B200CA_LIB: developer builds, e.g. -DB200CA_FFT_TRACE)
 
 # name -> (restype, argtypes); mirrors include/b200ca.h one to one
 SIGNATURES = {

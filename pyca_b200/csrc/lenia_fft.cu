@@ -544,7 +544,12 @@ __global__ void __launch_bounds__(NT, MINB) lenia_fft_firinv_kernel(const FftInv
             inv16_stage_state(a, st_s + (ps * RG + rw) * N, plane_off, min(y0 + ps * RG + rw, a.g.D - 1), seg, t);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    for (int e = tid; e < N; e += NT) tw_s[e] = __ldg(a.tws + e);
+    // twiddle tables -> shared memory by cp.async (16 bytes = two entries per copy): nothing waits for them before the
+    // inverse transforms, so their latency hides behind the FIR instead of sitting in the prologue
+    for (int e = tid; e < N / 2; e += NT)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(tw_s + 2 * e)), "l"(a.tws + 2 * e)
+                     : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
     float2 kt[KROWS];
     {
         const float *kf = a.kfft + (size_t)((b * a.NS) * a.C + j) * KROWS * N + 2 * tid;
@@ -592,6 +597,7 @@ __global__ void __launch_bounds__(NT, MINB) lenia_fft_firinv_kernel(const FftInv
             for (int y = 0; y < FT; ++y) fo[y * (XB / 2)] = make_float4(are[y].x, are[y].y, aim[y].x, aim[y].y);
         }
         FFT_TRACE(3);
+        if (i == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's twiddle copies (and staged state) have landed
         __syncthreads();
         FFT_TRACE(4);
         // phase 2: inverse transforms, 4 rows per pass; a row belongs to 64 threads (2 warps) with their own named barrier

@@ -13,7 +13,7 @@ a = pyca_b200.Lenia((H, W), num_channels=1, params=d1, state_init=torch.rand(1, 
 for _ in range(5):
     a.step()
 torch.cuda.synchronize()
-L = ctypes.CDLL(os.path.join(os.path.dirname(pyca_b200.__file__), "libb200ca.so"))
+L = ctypes.CDLL(_lib.LIB_PATH)
 n = 8 * 4096
 out = np.zeros(n, dtype=np.int64)
 rc = L.b200ca_debug_fft_trace(out.ctypes.data_as(ctypes.c_void_p), n)
