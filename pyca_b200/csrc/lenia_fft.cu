@@ -481,9 +481,20 @@ __device__ __forceinline__ void inv16_store(const FftInvArgs &a, const float2 (&
         rp0[64 * q] = v0;
         rp1[64 * q] = v1;
         if (EDGE) {
-            const bool xe = (x < F) || (x >= a.W - F);
-            if (xe || re0) fft_store_mirrors(oplane, a.H, a.W, a.pitch, row0, x, v0, a.row_wrap != 0);
-            if (xe || re1) fft_store_mirrors(oplane, a.H, a.W, a.pitch, row1, x, v1, a.row_wrap != 0);
+            if (!re0 && !re1) {
+                // the common edge case: only the x images of the two cells (right frame for x < F, left frame for x >= W - F)
+                if (x < F) {
+                    rp0[64 * q + a.W] = v0;
+                    rp1[64 * q + a.W] = v1;
+                } else if (x >= a.W - F) {
+                    rp0[64 * q - a.W] = v0;
+                    rp1[64 * q - a.W] = v1;
+                }
+            } else {
+                const bool xe = (x < F) || (x >= a.W - F);
+                if (xe || re0) fft_store_mirrors(oplane, a.H, a.W, a.pitch, row0, x, v0, a.row_wrap != 0);
+                if (xe || re1) fft_store_mirrors(oplane, a.H, a.W, a.pitch, row1, x, v1, a.row_wrap != 0);
+            }
         }
     }
 }
