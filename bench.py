@@ -622,7 +622,9 @@ class NcaWL(Workload):
     def step(self):
         import pyca_b200
 
-        pyca_b200.nca_step(self.a, self.wts, out=self.b, seed=1, step_index=self.t, scratch=self.scratch, impl=self.impl)
+        # (first_world: every rank draws its slice of the one global update mask of the 256-world batch)
+        pyca_b200.nca_step(self.a, self.wts, out=self.b, seed=1, step_index=self.t, scratch=self.scratch, impl=self.impl,
+                           first_world=self.rank * self.Bl)
         self.a, self.b = self.b, self.a
         self.t += 1
 

@@ -227,6 +227,12 @@ int64_t b200ca_nca_scratch_bytes(int B, int H, int W);
 int b200ca_nca_step(const float *state_in, float *state_out, const void *Wprep, const uint8_t *update_mask,
                     uint64_t seed, uint64_t step_index, void *scratch, int B, int n, int hid, int H, int W, int impl,
                     void *stream);
+/* The same step for a batch SHARD: worlds [first_world, first_world + B) of a larger batch.  The in-kernel Philox counter is
+ * the GLOBAL cell index, so the shards of a batch split over GPUs draw exactly the mask the unsplit batch draws
+ * ("give each shard its slice of the same global mask"). */
+int b200ca_nca_step_shard(const float *state_in, float *state_out, const void *Wprep, const uint8_t *update_mask, uint64_t seed,
+                          uint64_t step_index, uint64_t first_world, void *scratch, int B, int n, int hid, int H, int W, int impl,
+                          void *stream);
 int b200ca_nca_run_host(const float *h_state_in, float *h_state_out, const void *Wprep, const uint8_t *h_update_mask,
                         uint64_t seed, int B, int n, int hid, int H, int W, int impl, int nsteps);
 

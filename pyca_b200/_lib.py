@@ -69,6 +69,8 @@ SIGNATURES = {
     "b200ca_nca_scratch_bytes": (c_int64, [c_int, c_int, c_int]),
     "b200ca_nca_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_int, c_int, c_int,
                                 c_int, c_int, c_int, c_void_p]),
+    "b200ca_nca_step_shard": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_uint64, c_void_p, c_int, c_int,
+                                      c_int, c_int, c_int, c_int, c_void_p]),
     "b200ca_nca_run_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_int, c_int, c_int, c_int, c_int,
                                     c_int, c_int]),
     "b200ca_draw_gol": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),

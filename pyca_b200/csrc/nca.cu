@@ -206,6 +206,12 @@ extern "C" int b200ca_nca_prepare_weights(const float *W1, const float *b1, cons
 extern "C" int b200ca_nca_step(const float *state_in, float *state_out, const void *Wprep, const uint8_t *update_mask,
                                uint64_t seed, uint64_t step_index, void *scratch, int B, int n, int hid, int H, int W, int impl,
                                void *stream) {
+    return b200ca_nca_step_shard(state_in, state_out, Wprep, update_mask, seed, step_index, 0, scratch, B, n, hid, H, W, impl, stream);
+}
+
+extern "C" int b200ca_nca_step_shard(const float *state_in, float *state_out, const void *Wprep, const uint8_t *update_mask,
+                                     uint64_t seed, uint64_t step_index, uint64_t first_world, void *scratch, int B, int n, int hid,
+                                     int H, int W, int impl, void *stream) {
     int rc = nca_dims_ok(n, hid);
     if (rc) return rc;
     B200CA_REQUIRE(state_in && state_out && Wprep && scratch, "nca_step: null pointer");
@@ -225,6 +231,7 @@ extern "C" int b200ca_nca_step(const float *state_in, float *state_out, const vo
     a.nz_bits = a.alive_bits + (size_t)B * H * a.wpr;
     a.seed = seed;
     a.step = step_index;
+    a.cell0 = first_world * (uint64_t)H * (uint64_t)W;
     if (impl == B200CA_NCA_SIMT) {
         dim3 grid(a.wpr, ceil_div(H, (SIMT_THREADS / 32) * SIMT_ROWS), B);
         nca_update_simt_kernel<<<grid, SIMT_THREADS, 0, st>>>(a);

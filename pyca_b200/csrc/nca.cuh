@@ -31,6 +31,7 @@ struct NcaArgs {
     uint32_t *alive_bits;  // [B*H*wpr] post-update alpha > 0.1
     uint32_t *nz_bits;     // [B*H*wpr] cell written non-zero by the update pass
     uint64_t seed, step;
+    uint64_t cell0;        // global index of this launch's first cell (batch shards draw their slice of ONE global mask)
     int B, H, W, wpr;
 };
 
@@ -41,7 +42,7 @@ int nca_prepare_tc(const float *W1, const float *b1, const float *W2, const floa
 __device__ __forceinline__ bool nca_update_bit(const NcaArgs &a, size_t cell) {
     if (a.mask) return a.mask[cell] != 0;
     uint32_t r[4];
-    Philox::gen(a.seed, (uint64_t)cell, a.step, r);
+    Philox::gen(a.seed, (uint64_t)cell + a.cell0, a.step, r);
     return (r[0] >> 8) <= (1u << 23);  // u = (r>>8) * 2^-24 <= 0.5  (nca.py:256 `rand <= 0.5`)
 }
 

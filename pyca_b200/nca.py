@@ -48,8 +48,11 @@ class NCAWeights:
 
 
 def nca_step(state: torch.Tensor, weights: NCAWeights, out: torch.Tensor = None, update_mask: torch.Tensor = None,
-             seed: int = 0, step_index: int = 0, scratch: torch.Tensor = None, impl: int = _lib.NCA_SIMT) -> torch.Tensor:
-    """One NCA step on a dense (B,n,H,W) fp32 CUDA tensor; returns the new state (a different tensor)."""
+             seed: int = 0, step_index: int = 0, scratch: torch.Tensor = None, impl: int = _lib.NCA_SIMT,
+             first_world: int = 0) -> torch.Tensor:
+    """One NCA step on a dense (B,n,H,W) fp32 CUDA tensor; returns the new state (a different tensor).
+    `first_world`: index of state[0] in a larger batch that is split over GPUs -- the in-kernel update mask is drawn from
+    the global cell index, so the shards reproduce the unsplit batch bit for bit."""
     _lib.require_cuda(state, "state")
     B, n, H, W = state.shape
     if state.dtype != torch.float32 or not state.is_contiguous():
@@ -62,8 +65,8 @@ def nca_step(state: torch.Tensor, weights: NCAWeights, out: torch.Tensor = None,
     if update_mask is not None:
         m = update_mask.to(device=state.device).reshape(B, H, W).to(torch.uint8).contiguous()
     with _lib.device_guard(state.device):
-        _lib.call("b200ca_nca_step", _lib.ptr(state), _lib.ptr(out), _lib.ptr(weights.prep), _lib.ptr(m), seed, step_index,
-                  _lib.ptr(scratch), B, n, weights.n_hidden, H, W, impl, _lib.current_stream(state.device))
+        _lib.call("b200ca_nca_step_shard", _lib.ptr(state), _lib.ptr(out), _lib.ptr(weights.prep), _lib.ptr(m), seed, step_index,
+                  int(first_world), _lib.ptr(scratch), B, n, weights.n_hidden, H, W, impl, _lib.current_stream(state.device))
     return out
 
 

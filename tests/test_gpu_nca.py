@@ -138,3 +138,20 @@ def test_host_entry_point():
     for i in range(2):
         ref = orc.nca_step(ref, t(fx["W1"]), t(fx["b1"]), t(fx["W2"]), t(fx["b2"]), masks[i].bool()[:, None])
     assert (torch.from_numpy(h_out) - ref).abs().max().item() <= 2 * TOL
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_batch_shards_draw_the_global_mask(impl):
+    """A batch split over GPUs: shards stepped with first_world = their offset reproduce the unsplit batch
+    bit for bit, because the in-kernel Philox counter is the global cell index."""
+    import pyca_b200
+
+    _impl_or_skip(impl)
+    fx = load_npz("nca_betta.npz")
+    w = pyca_b200.NCAWeights(t(fx["W1"]), t(fx["b1"]), t(fx["W2"]), t(fx["b2"]), "cuda")
+    g = torch.Generator().manual_seed(4)
+    s = torch.rand(6, 16, 40, 72, generator=g).cuda()
+    whole = pyca_b200.nca_step(s, w, seed=9, step_index=3, impl=impl)
+    parts = [pyca_b200.nca_step(s[o:o + n].contiguous(), w, seed=9, step_index=3, impl=impl, first_world=o) for o, n in ((0, 2), (2, 3), (5, 1))]
+    assert torch.equal(whole, torch.cat(parts, dim=0))
+    assert not torch.equal(whole[2:5], pyca_b200.nca_step(s[2:5].contiguous(), w, seed=9, step_index=3, impl=impl))   # offset matters
