@@ -348,3 +348,51 @@ class LeniaSlabCUDA(LeniaSlab):
                 self._launch(nb, T - nb)
                 main.wait_stream(self.comm_stream)
         self.cur ^= 1
+
+
+class MaceSlabCUDA(LeniaSlabCUDA):
+    """MaCE-Lenia (and the cross-channel variant) on a row slab.  The redistribution reads the affinity on a
+    2-row halo and the state on a 1-row halo, so a step has TWO exchanges: affinity rows after the convolution, state rows
+    after the redistribution (the 16-row frame carries both; the alternative -- a 17-row state halo and redundant boundary
+    affinity -- does not fit the frame).  macelenia.py:72-120, mace_lenia_xchan.py:59-76 on rows [r0, r1) of the torus."""
+
+    def __init__(self, lenia_params, C, H, W, rank, world, device="cuda", beta=8.0, alpha=None, conv_path="auto"):
+        super().__init__(lenia_params, C, H, W, rank, world, device=device, dt=0.1, overlap=False, conv_path=conv_path)
+        self.beta = float(beta)
+        self.alpha = alpha  # None: MaCELenia; a float: MaCELeniaXChan mixing rate
+        self.aff = torch.zeros_like(self.bufs[0])
+        self.launches_per_step = (2 if self.use_fft else 1) + 1
+
+    def affinity_phase(self):
+        """Affinity of the owned rows into the framed `aff` tensor (its top / bottom frame rows belong to the neighbours)."""
+        from . import _lib
+
+        rw = 1 if self.world == 1 else 0
+        with _lib.device_guard(self.device):
+            st = _lib.current_stream(self.device)
+            if self.use_fft:
+                _lib.call("b200ca_lenia_step_fft", _lib.ptr(self.buf), _lib.ptr(self.aff), _lib.ptr(self._kfft), _lib.ptr(self.mu),
+                          _lib.ptr(self.sigma), _lib.ptr(self.weights), _lib.ptr(self._fft_ws), self.B, self.C, self.k_mult, self.hl,
+                          self.W, 0.1, _lib.MODE_AFF, rw, st)
+            else:
+                _lib.call("b200ca_lenia_step", _lib.ptr(self.buf), _lib.ptr(self.aff), _lib.ptr(self._kprep), _lib.ptr(self.mu),
+                          _lib.ptr(self.sigma), _lib.ptr(self.weights), self.B, self.C, self.k_mult, self.hl, self.W, 0.1,
+                          _lib.MODE_AFF, rw, 0, 0, st)
+
+    def redistribute_phase(self):
+        """New state of the owned rows into `other` (needs the neighbours' affinity rows in the frame of `aff`)."""
+        from . import _lib
+
+        with _lib.device_guard(self.device):
+            _lib.call("b200ca_mace_redistribute", _lib.ptr(self.buf), _lib.ptr(self.aff), _lib.ptr(self.other), self.B, self.C, self.hl,
+                      self.W, self.beta, 0 if self.alpha is None else 1, 0.0 if self.alpha is None else float(self.alpha),
+                      1 if self.world == 1 else 0, _lib.current_stream(self.device))
+        self.cur ^= 1
+
+    def step(self, group=None):
+        self.affinity_phase()
+        if self.world > 1:
+            self.exchange(self.aff, group)
+        self.redistribute_phase()
+        if self.world > 1:
+            self.exchange(self.buf, group)

@@ -57,6 +57,28 @@ def main():
             err = (sl.interior() - single.state[:, :, sl.r0:sl.r1]).abs().max().item()
             print(f"[rank {rank}] Lenia C={C} path={path} overlap={sl.overlap}: max |slab - torus| = {err:.2e}", flush=True)
             ok &= err <= (1e-6 if path == "direct" else 5e-6)
+    # ---- MaCE-Lenia XChan slabs (two exchanges per step: affinity rows, then state rows), 3 steps, mass conserved
+    from pyca_b200.slab import MaceSlabCUDA
+
+    px = load_npz("params_xchan_arborical_asbestosis.npz")
+    dx = {k: t(px[k]) for k in ["mu", "sigma", "beta", "mu_k", "sigma_k", "weights"]}
+    dx["k_size"] = int(px["k_size"])
+    Hh, Ww = 192 * world, 320
+    g = torch.Generator().manual_seed(11)
+    full = 1.5 * torch.rand(1, 3, Hh, Ww, generator=g)
+    single = pyca_b200.MaCELeniaXChan((Hh, Ww), params=dict(dx), state_init=full, device=dev)
+    ms = MaceSlabCUDA(pyca_b200.LeniaParams(param_dict=dict(dx)), 3, Hh, Ww, rank, world, device=dev, beta=6.0, alpha=0.03)
+    ms.set_interior(full[:, :, ms.r0:ms.r1].to(dev))
+    for _ in range(3):
+        single.step()
+        ms.step()
+    torch.cuda.synchronize()
+    err = (ms.interior() - single.state[:, :, ms.r0:ms.r1]).abs().max().item()
+    mass = ms.interior().double().sum().reshape(1)
+    dist.all_reduce(mass)
+    m0 = float(full.double().sum())
+    print(f"[rank {rank}] MaCE-XChan slab: max |slab - torus| = {err:.2e}; mass {float(mass.item()):.4f} vs {m0:.4f}", flush=True)
+    ok &= err <= 1e-5 and abs(float(mass.item()) - m0) <= 1e-5 * m0
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()
