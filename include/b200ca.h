@@ -39,6 +39,10 @@ extern "C" {
 
 int b200ca_version(void);
 const char *b200ca_last_error(void);
+/* Test hook: ';'-separated names of the kernel instantiations the compute calls of this thread launched since the
+ * last reset (e.g. "lenia_fft_rows<1,1024,split>;lenia_fft_firinv<8,single,1,512>"); reset != 0 clears the log after
+ * reading it.  The parity tests use it to assert which template instantiation a shape dispatched to. */
+const char *b200ca_debug_variants(int reset);
 /* sm count / compute capability of the current device (error if none). */
 int b200ca_device_info(int *sm_count, int *cc_major, int *cc_minor);
 /* frees cached descriptors/scratch of all devices. */

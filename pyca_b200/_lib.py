@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("B200CA_LIB") or os.path.join(_HERE, "libb200ca.so")  
 SIGNATURES = {
     "b200ca_version": (c_int, []),
     "b200ca_last_error": (c_char_p, []),
+    "b200ca_debug_variants": (c_char_p, [c_int]),
     "b200ca_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
     "b200ca_shutdown": (c_int, []),
     "b200ca_gol_words_per_row": (c_int, [c_int]),
@@ -106,6 +107,12 @@ def lib() -> ctypes.CDLL:
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+def variants(reset: bool = True) -> list:
+    """Kernel instantiations launched by this thread's compute calls since the last reset (test hook)."""
+    v = lib().b200ca_debug_variants(1 if reset else 0)
+    return [x for x in (v.decode() if v else "").split(";") if x]
 
 
 def check(rc: int, what: str = "") -> None:

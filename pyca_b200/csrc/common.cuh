@@ -12,6 +12,9 @@ namespace b200ca {
 void set_error(const char *fmt, ...);
 int check_cuda(cudaError_t e, const char *what);
 int num_sms();
+// names the kernel instantiation a dispatch just launched (thread-local, bounded log read back by b200ca_debug_variants():
+// the parity tests assert through it that they exercised the instantiation they were written for)
+void note_variant(const char *fmt, ...);
 // grow-only per-device scratch buffers for the *_host entry points (slot 0..7); freed by b200ca_shutdown()
 int scratch_get(int slot, size_t bytes, void **out);
 void scratch_free_all();

@@ -15,6 +15,20 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+static thread_local char g_variants[1024] = "";
+
+void note_variant(const char *fmt, ...) {
+    char one[128];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(one, sizeof(one), fmt, ap);
+    va_end(ap);
+    const size_t have = strlen(g_variants), add = strlen(one);
+    if (have + add + 2 >= sizeof(g_variants)) return;  // bounded: the log is only read by tests, right after a reset
+    if (have) g_variants[have] = ';';
+    memcpy(g_variants + have + (have ? 1 : 0), one, add + 1);
+}
+
 int check_cuda(cudaError_t e, const char *what) {
     if (e == cudaSuccess) return 0;
     set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
@@ -148,6 +162,12 @@ using namespace b200ca;
 
 extern "C" int b200ca_version(void) { return B200CA_VERSION; }
 extern "C" const char *b200ca_last_error(void) { return g_err; }
+extern "C" const char *b200ca_debug_variants(int reset) {
+    static thread_local char out[sizeof(g_variants)];
+    memcpy(out, g_variants, sizeof(out));
+    if (reset) g_variants[0] = 0;
+    return out;
+}
 
 extern "C" int b200ca_device_info(int *sm_count, int *cc_major, int *cc_minor) {
     int dev = 0;

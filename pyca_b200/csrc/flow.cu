@@ -145,6 +145,7 @@ int launch_flow(const FlowArgs &a, cudaStream_t st) {
     if (a.cap == 1.f) flow_rt_kernel<DD, true><<<grid, FTHREADS, 0, st>>>(a);
     else flow_rt_kernel<DD, false><<<grid, FTHREADS, 0, st>>>(a);
     B200CA_LAUNCH_CHECK("flow_rt_kernel");
+    note_variant("flow_rt<%d,%s>", DD, a.cap == 1.f ? "unit" : "cap");
     return 0;
 }
 

@@ -576,6 +576,7 @@ static int launch_fast_t(const uint32_t *in, uint32_t *out, const GolGeom &g, ui
     const int bx = units >= 128 ? 128 : ceil_div(units, 32) * 32;
     dim3 grid(ceil_div(units, bx), ceil_div(g.H, RPT));
     B200CA_CUDA(launch_pdl(gol_fast_kernel<LIFE, OPEN, RPT>, grid, dim3(bx), 0, st, in, out, g.H, g.wpr, g.stride, s, b));
+    note_variant("gol_fast<%d,%d,%d>", (int)LIFE, (int)OPEN, RPT);
     return 0;
 }
 

@@ -166,6 +166,11 @@ extern "C" int b200ca_lenia_pipe_create(void **pipe, const float *K, const float
 extern "C" int b200ca_lenia_pipe_submit(void *pipe, const float *h_state_in, float *h_state_out, int nsteps) {
     Pipe *p = static_cast<Pipe *>(pipe);
     B200CA_REQUIRE(p && h_state_in && h_state_out && nsteps >= 0, "lenia_pipe_submit: bad arguments");
+    {
+        int cur = -1;
+        B200CA_CUDA(cudaGetDevice(&cur));
+        B200CA_REQUIRE(cur == p->dev, "lenia_pipe_submit: the pipe was created on device %d, the current device is %d", p->dev, cur);
+    }
     Lane &l = p->lanes[p->next];
     p->next = (p->next + 1) % p->depth;
     if (l.busy) B200CA_CUDA(cudaEventSynchronize(l.done));  // the lane's previous world has landed in its host buffer

@@ -333,6 +333,7 @@ static int launch_conv(const CUtensorMap *tm, const LeniaArgs &a, int tiles_y, c
     dim3 grid(ceil_div(a.W, TW), tiles_y, a.B * a.C);
     lenia_conv_kernel<NW, GARBI><<<grid, 32 * NW, smem, st>>>(tm, a);
     B200CA_LAUNCH_CHECK("lenia_conv_kernel");
+    note_variant("lenia_conv<%d,%s>", NW, GARBI ? "garbi" : "gauss");
     return 0;
 }
 

@@ -869,10 +869,12 @@ extern "C" int b200ca_lenia_step_fft_phase(const float *state_in, float *state_o
     const int NS = C * k_mult;
     float2 *Z = reinterpret_cast<float2 *>(workspace);
     float2 *O = Z + (size_t)B * C * g.zrows * g.nseg * g.N;
-    // developer switches (timing / A-B runs): B200CA_FFT_ONLY = 1|2|3 runs one kernel of the step only;
-    // B200CA_FFT_FUSED = 0 unfuses FIR and inverse (N = 1024), 4|8 forces the rows per CTA of the fused kernel;
-    static int rpc_rows_env = 0, rpc_inv = 0, only = 0, fused = -1;
-    if (!rpc_rows_env) {
+    // developer switches (timing / A-B runs), compiled in only with -DB200CA_DEV: B200CA_FFT_ONLY = 1|2|3 runs one kernel of
+    // the step only; B200CA_FFT_FUSED = 0 unfuses FIR and inverse (N = 1024), 4|8 forces the rows per CTA of the fused kernel
+    int rpc_rows_env = 2, rpc_inv = 1, only = 0, fused = -1, minb = 2, nt512 = 1;
+    bool rpc_forced = false;
+#ifdef B200CA_DEV
+    {
         auto env = [](const char *n, int dflt) {
             const char *e = getenv(n);
             return e ? atoi(e) : dflt;
@@ -883,7 +885,11 @@ extern "C" int b200ca_lenia_step_fft_phase(const float *state_in, float *state_o
         if (rpc_inv != 2 && rpc_inv != 4) rpc_inv = 1;
         rpc_rows_env = env("B200CA_FFT_RPC_ROWS", 2);
         if (rpc_rows_env != 1 && rpc_rows_env != 4) rpc_rows_env = 2;
+        rpc_forced = getenv("B200CA_FFT_RPC_ROWS") != nullptr;
+        minb = env("B200CA_FFT_MINB", 2);
+        nt512 = env("B200CA_FFT_NT512", 1);
     }
+#endif
     if (only == 0 || only == 1) {
         // phase 1: spectra rows made of owned rows only (zr in [R, D+R)); phase 2: the 2R rows that touch ghost rows
         FftGeom gr = g;
@@ -900,13 +906,13 @@ extern "C" int b200ca_lenia_step_fft_phase(const float *state_in, float *state_o
                                   (size_t)RPC * NN * sizeof(float2), st, state_in, Z, tw, gr, H, W, pitch)
         const bool split = g.N == 1024 && fused != 0;  // the fused FIR + inverse kernel reads split spectra
         // small worlds (every CTA resident at once): one row pair per CTA shortens the serial chain (1024^2: 19.9 -> 19.4 us/step)
-        static const bool rpc_forced = getenv("B200CA_FFT_RPC_ROWS") != nullptr;
         const int rpc_rows = (!rpc_forced && (long long)gr.zr_count * g.nseg * B * C <= 5LL * num_sms()) ? 1 : rpc_rows_env;
         if (split) B200CA_CUDA(rpc_rows == 1 ? ROWS4(1, 1024, true) : (rpc_rows == 4 ? ROWS4(4, 1024, true) : ROWS4(2, 1024, true)));
         else if (g.N == 1024) B200CA_CUDA(rpc_rows == 1 ? ROWS4(1, 1024, false) : (rpc_rows == 4 ? ROWS4(4, 1024, false) : ROWS4(2, 1024, false)));
         else B200CA_CUDA(rpc_rows == 1 ? ROWS4(1, 256, false) : (rpc_rows == 4 ? ROWS4(4, 256, false) : ROWS4(2, 256, false)));
 #undef ROWS4
         B200CA_LAUNCH_CHECK("lenia_fft_rows_kernel");
+        note_variant("lenia_fft_rows<%d,%d,%s>", rpc_rows, g.N, split ? "split" : "plain");
     }
     if (phase == 1) return 0;
     FftInvArgs a;
@@ -932,36 +938,33 @@ extern "C" int b200ca_lenia_step_fft_phase(const float *state_in, float *state_o
     a.row_wrap = row_wrap;
     if (g.N == 1024 && fused != 0) {
         if (only != 0 && only != 3) return 0;
-        static int minb = 0;
-        if (!minb) minb = getenv("B200CA_FFT_MINB") ? atoi(getenv("B200CA_FFT_MINB")) : 2;
         // 8 row pairs per CTA when that still gives every SM its resident CTAs, else 4 (more, smaller CTAs)
         const int ft = fused == 4 || fused == 8 ? fused : ((long long)ceil_div(g.D, 8) * g.nseg * B * C >= 2LL * num_sms() ? 8 : 4);
         const size_t smem = ((size_t)ft * XB + 1024) * sizeof(float2);  // row buffers + twiddle tables
-        static bool attr_done = false;
-        if (!attr_done) {
+        // (the opt-in shared-memory size is a per-device function attribute)
+        static bool attr_done[64] = {false};
+        int dev = 0;
+        B200CA_CUDA(cudaGetDevice(&dev));
+        if (!attr_done[dev & 63]) {
             const int big = (int)((8 * XB + 1024) * sizeof(float2));
+            const int big5 = (int)(((size_t)8 * XB + 1024 + 8 * 1024) * sizeof(float2));
             B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_firinv_kernel<8, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
             B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_firinv_kernel<8, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
             B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_firinv_kernel<8, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-            attr_done = true;
+            B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_firinv_kernel<8, false, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big5));
+            B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_firinv_kernel<8, true, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big5));
+            attr_done[dev & 63] = true;
         }
         // small worlds: when every 8-row CTA fits the machine at one per SM the step is a single wave; 512-thread CTAs halve
         // the serial chain of a CTA (B200CA_FFT_NT512=0 disables)
-        static int nt512 = -1;
-        if (nt512 < 0) nt512 = getenv("B200CA_FFT_NT512") ? atoi(getenv("B200CA_FFT_NT512")) : 1;
         const long long ctas8 = (long long)ceil_div(g.D, 8) * g.nseg * B * C;
         if (nt512 && fused < 0 && ctas8 <= (long long)num_sms() * (nt512 >= 2 ? nt512 : 1)) {
             const size_t smem5 = ((size_t)8 * XB + 1024 + 8 * 1024) * sizeof(float2);  // row buffers + twiddles + staged state
-            static bool attr5 = false;
-            if (!attr5) {
-                B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_firinv_kernel<8, false, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
-                B200CA_CUDA(cudaFuncSetAttribute(lenia_fft_firinv_kernel<8, true, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
-                attr5 = true;
-            }
             dim3 grid5(ceil_div(g.D, 8), g.nseg, B * C);
             B200CA_CUDA(NS > 1 ? launch_pdl(lenia_fft_firinv_kernel<8, true, 1, 512>, grid5, dim3(512), smem5, st, a)
                                : launch_pdl(lenia_fft_firinv_kernel<8, false, 1, 512>, grid5, dim3(512), smem5, st, a));
             B200CA_LAUNCH_CHECK("lenia_fft_firinv_kernel");
+            note_variant("lenia_fft_firinv<8,%s,1,512>", NS > 1 ? "multi" : "single");
             return 0;
         }
         dim3 grid(ceil_div(g.D, ft), g.nseg, B * C);
@@ -972,6 +975,7 @@ extern "C" int b200ca_lenia_step_fft_phase(const float *state_in, float *state_o
         else B200CA_CUDA(ft == 8 ? launch_pdl(lenia_fft_firinv_kernel<8, false, 3>, grid, dim3(256), smem, st, a)
                                  : launch_pdl(lenia_fft_firinv_kernel<4, false, 3>, grid, dim3(256), smem, st, a));
         B200CA_LAUNCH_CHECK("lenia_fft_firinv_kernel");
+        note_variant("lenia_fft_firinv<%d,%s,%d,256>", ft, NS > 1 ? "multi" : "single", NS > 1 ? 2 : minb);
         return 0;
     }
     if (only == 0 || only == 2) {
@@ -994,6 +998,7 @@ extern "C" int b200ca_lenia_step_fft_phase(const float *state_in, float *state_o
             B200CA_CUDA(launch_pdl(lenia_fft_fir_kernel<8>, grid, dim3(FIR_THREADS), 0, st, f));
         }
         B200CA_LAUNCH_CHECK("lenia_fft_fir_kernel");
+        note_variant("lenia_fft_fir<%d>", ctas32 >= (long long)num_sms() * 16 ? 32 : 8);
     }
     if (only == 0 || only == 3) {
 #define INV4(RPC, NN) launch_pdl(lenia_fft_inv_kernel<RPC, NN>, dim3(ceil_div(g.D, RPC), g.nseg, B * C), dim3(NN / 4), \
@@ -1002,6 +1007,7 @@ extern "C" int b200ca_lenia_step_fft_phase(const float *state_in, float *state_o
         else B200CA_CUDA(rpc_inv == 1 ? INV4(1, 256) : (rpc_inv == 4 ? INV4(4, 256) : INV4(2, 256)));
 #undef INV4
         B200CA_LAUNCH_CHECK("lenia_fft_inv_kernel");
+        note_variant("lenia_fft_inv<%d,%d>", rpc_inv, g.N);
     }
     return 0;
 }

@@ -243,9 +243,11 @@ static int launch_mace_fast(const MaceArgs &a, cudaStream_t st) {
     if (blocks32 >= (long long)num_sms() * 8) {
         dim3 grid(ceil_div(ceil_div(a.W, MCOLS), 4), ceil_div(a.H, 32), a.B);
         mace_fast_kernel<C, 32><<<grid, 128, 0, st>>>(a);
+        note_variant("mace_fast<%d,32>", C);
     } else {
         dim3 grid(ceil_div(ceil_div(a.W, MCOLS), 4), ceil_div(a.H, 8), a.B);
         mace_fast_kernel<C, 8><<<grid, 128, 0, st>>>(a);
+        note_variant("mace_fast<%d,8>", C);
     }
     B200CA_LAUNCH_CHECK("mace_fast_kernel");
     return 0;

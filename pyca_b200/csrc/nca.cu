@@ -236,6 +236,7 @@ extern "C" int b200ca_nca_step_shard(const float *state_in, float *state_out, co
         dim3 grid(a.wpr, ceil_div(H, (SIMT_THREADS / 32) * SIMT_ROWS), B);
         nca_update_simt_kernel<<<grid, SIMT_THREADS, 0, st>>>(a);
         B200CA_LAUNCH_CHECK("nca_update_simt_kernel");
+        note_variant("nca_update_simt");
     } else if (impl == B200CA_NCA_TC) {
         rc = nca_step_tc(a, st);
         if (rc) return rc;

@@ -389,6 +389,7 @@ int nca_step_tc(const NcaArgs &a, cudaStream_t st) {
     const int grid = (int)std::min<long long>(ceil_div64(ntiles, NG), (long long)num_sms());
     nca_update_tc_kernel<<<grid, 128 * NG, SM_TOTAL, st>>>(a, tiles_x, tiles_y);
     B200CA_LAUNCH_CHECK("nca_update_tc_kernel");
+    note_variant("nca_update_tc<grid=%d>", grid);
     return 0;
 }
 

@@ -8,7 +8,13 @@ started (an even number for the Lenia family and `CA2D`), so that a replay start
 
 Only device-resident, steady-state stepping is captured: host-side decisions of a step (pending state assignments, in-place
 edit detection, MaCE food respawn, torch-drawn NCA masks) are not part of a graph -- assign / edit between replays and call
-`refresh()`; automata with `has_food` or `rng='torch'` are refused.
+`refresh()`; automata with `has_food` are refused, and so is `NeuralCA`: its stochastic update mask is keyed by the step
+index, which `step()` passes to the kernel BY VALUE -- a capture would freeze it and every replay would redraw the same
+`reps` masks instead of the reference's fresh mask per step (nca.py:256).
+
+`refresh()` runs two warm-up steps outside the capture (lazy allocations, per-device function attributes); the state and
+the frame counter are snapshotted before and restored after them, so constructing or refreshing a StepGraph does not advance
+the automata.
 """
 from __future__ import annotations
 
@@ -24,8 +30,11 @@ class StepGraph:
             raise _lib.B200CAError("StepGraph: reps must be even (ping-pong buffers return to their start)")
         self.reps = reps
         for a in self.autos:
-            if getattr(a, "has_food", False) or getattr(a, "rng", None) == "torch":
+            if getattr(a, "has_food", False):
                 raise _lib.B200CAError("StepGraph: this automaton takes host-side decisions inside step(); not capturable")
+            if hasattr(a, "rng"):
+                raise _lib.B200CAError("StepGraph: NeuralCA draws its update mask from the step index, passed by value at "
+                                       "launch; a graph would replay the same masks forever -- step it from Python")
         self.device = torch.device(self.autos[0].device)
         self.graph = None
         self.refresh()
@@ -40,8 +49,14 @@ class StepGraph:
         """(Re)captures the graph; call after assigning or editing a state between replays."""
         for a in self.autos:
             self._prepare(a)
+            attr = "world" if hasattr(a, "world") else "state"
+            saved, frames0 = getattr(a, attr).clone(), getattr(a, "frames", 0)
             a.step()                 # warm-up outside the capture: lazy allocations, function attributes
             a.step()
+            setattr(a, attr, saved)  # ... and back to where the caller left the automaton
+            if hasattr(a, "frames"):
+                a.frames = frames0
+            self._prepare(a)
         torch.cuda.synchronize(self.device)
         frames = [getattr(a, "frames", 0) for a in self.autos]
         g = torch.cuda.CUDAGraph()

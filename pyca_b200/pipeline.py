@@ -86,6 +86,14 @@ class LeniaHostPipe:
 
         from .lenia import MaCELenia, MaCELeniaXChan
 
+        # the pipe implements Lenia / MaCE / MaCE-XChan steps with Gaussian growth only; anything else would silently run
+        # as plain Lenia (FlowLenia subclasses Lenia) or with placeholder mu / sigma (g_arbi)
+        if type(auto).__name__ == "FlowLenia" or hasattr(auto, "_flow_args") or hasattr(auto, "dd"):
+            raise _lib.B200CAError("LeniaHostPipe: FlowLenia is not supported by the host pipe")
+        if getattr(auto, "g_arbi", False):
+            raise _lib.B200CAError("LeniaHostPipe: Fourier growth functions (g_arbi) are not supported by the host pipe")
+        if getattr(auto, "has_food", False):
+            raise _lib.B200CAError("LeniaHostPipe: MaCE food (has_food=True) is not supported by the host pipe")
         if family is None:
             family = 2 if isinstance(auto, MaCELeniaXChan) else 1 if isinstance(auto, MaCELenia) else 0
         k = auto.k.float().contiguous()

@@ -281,11 +281,16 @@ class LeniaSlabCUDA(LeniaSlab):
                                        device=device)
         self.tile_rows = L.b200ca_lenia_tile_rows(self.hl, W, B, C)
         self.n_tile_rows = (self.hl + self.tile_rows - 1) // self.tile_rows
-        self.n_boundary = (self.F + self.tile_rows - 1) // self.tile_rows  # tile rows covering F owned rows
+        # tile rows that cover the F owned rows next to each edge.  The LAST tile row is clipped to hl - (T-1)*TH rows
+        # (lenia.cu clips the tile at row hl), so the bottom count comes from real row coverage: the smallest nb with
+        # hl - (T - nb) * TH >= F  (a remainder tile of fewer than F rows needs one more tile row below it)
+        self.n_boundary = (self.F + self.tile_rows - 1) // self.tile_rows
+        T, TH = self.n_tile_rows, self.tile_rows
+        self.n_boundary_bot = next((nb for nb in range(1, T + 1) if self.hl - (T - nb) * TH >= self.F), T)
         if self.use_fft:
             self.overlap = overlap and world > 1
         else:
-            self.overlap = overlap and world > 1 and self.n_tile_rows > 2 * self.n_boundary
+            self.overlap = overlap and world > 1 and self.n_tile_rows > self.n_boundary + self.n_boundary_bot
         self.comm_stream = torch.cuda.Stream(device=self.device) if world > 1 else None
         self._pending_exchange = False  # FFT path: the ghost rows of `buf` are still in flight on comm_stream
         # FFT path: row FFTs (twice when the halo exchange is overlapped: interior rows, then the rows touching ghost rows)
@@ -338,14 +343,14 @@ class LeniaSlabCUDA(LeniaSlab):
                 self._launch(0, 0)
                 self.exchange(self.other, group)
             else:
-                nb, T = self.n_boundary, self.n_tile_rows
+                nb, nbb, T = self.n_boundary, self.n_boundary_bot, self.n_tile_rows
                 main = torch.cuda.current_stream(self.device)
                 self._launch(0, nb)
-                self._launch(T - nb, T)
+                self._launch(T - nbb, T)
                 self.comm_stream.wait_stream(main)
                 with torch.cuda.stream(self.comm_stream):
                     self.exchange(self.other, group)
-                self._launch(nb, T - nb)
+                self._launch(nb, T - nbb)
                 main.wait_stream(self.comm_stream)
         self.cur ^= 1
 

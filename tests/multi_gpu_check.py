@@ -57,6 +57,25 @@ def main():
             err = (sl.interior() - single.state[:, :, sl.r0:sl.r1]).abs().max().item()
             print(f"[rank {rank}] Lenia C={C} path={path} overlap={sl.overlap}: max |slab - torus| = {err:.2e}", flush=True)
             ok &= err <= (1e-6 if path == "direct" else 5e-6)
+    # ---- direct path, slab height NOT a multiple of the tile height (the clipped last tile row must still count as boundary:
+    #      its rows are sent to the neighbour while the interior launch runs)
+    dd = {k: (v[:, :1, :1].clone() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+    for hl in (104, 90):
+        Hh, Ww = hl * world, 320
+        g = torch.Generator().manual_seed(hl)
+        full = torch.rand(1, 1, Hh, Ww, generator=g)
+        single = pyca_b200.Lenia((Hh, Ww), num_channels=1, params=dict(dd), state_init=full, device=dev, conv_path="direct")
+        params = pyca_b200.LeniaParams(param_dict=dict(dd), channels=1)
+        sl = LeniaSlabCUDA(params, 1, Hh, Ww, rank, world, device=dev, overlap=True, conv_path="direct")
+        sl.set_interior(full[:, :, sl.r0:sl.r1].to(dev))
+        for _ in range(4):
+            single.step()
+            sl.step()
+        torch.cuda.synchronize()
+        err = (sl.interior() - single.state[:, :, sl.r0:sl.r1]).abs().max().item()
+        print(f"[rank {rank}] Lenia direct hl={hl} (tile rows {sl.tile_rows}, boundary {sl.n_boundary}/{sl.n_boundary_bot}) "
+              f"overlap={sl.overlap}: max |slab - torus| = {err:.2e}", flush=True)
+        ok &= err <= 1e-6
     # ---- MaCE-Lenia XChan slabs (two exchanges per step: affinity rows, then state rows), 3 steps, mass conserved
     from pyca_b200.slab import MaceSlabCUDA
 
