@@ -1,9 +1,10 @@
-"""Headless loader for the UNMODIFIED PyCA reference (``/root/reference``).
+"""Headless loader for the UNMODIFIED PyCA reference.
 
-Only used in the build container to (a) pin ``oracle/`` against the reference
-and (b) generate the fixtures in ``tests/golden/`` (see ``generate.py``).  The
-GPU box has no ``/root/reference``; nothing in ``-m gpu`` tests, ``smoke()`` or
-``bench.py`` imports this module.
+Search order: ``$PYCA_REFERENCE``, ``/root/reference`` (build container only), ``baseline/_ref`` (the offline install made
+by ``baseline/install_ref.py``: git-ignored, travels to the GPU box).  Used (a) in the build container to pin ``oracle/``
+against the reference and to generate the fixtures in ``tests/golden/`` (``tests/golden/generate.py``), and (b) by
+``bench.py --impl reference`` / its ``cpu_baseline`` leg, which time the reference's own ``step()`` on the host cores
+from ``baseline/_ref``.  ``pyca_b200`` never imports this module.
 
 The reference cannot be imported as-is (``pygame``, ``pygame_gui``,
 ``easydict``, ``torchenhanced``, ``pyperlin``, ``showtens``, ``matplotlib``
@@ -24,7 +25,17 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("PYCA_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    for cand in (os.environ.get("PYCA_REFERENCE"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "pyca")):
+            return cand
+    return os.environ.get("PYCA_REFERENCE", "/root/reference")
+
+
+REF_ROOT = _find_root()
 
 
 class _Fake(types.ModuleType):

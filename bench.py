@@ -14,8 +14,13 @@ extracted from the reference's demo_data):
   mace_xchan_4k   MaCE-Lenia cross-channel 4096x4096 C=3, demo_macelenia_xchan/arborical_asbestosis
   nca_256         NCA inference 256 x 128x128 worlds (betta weights), batch-sharded for N>1
   flow_lenia_4k   FlowLenia 4096x4096 C=3, demo_macelenia/anencephalic_brakeman
-`--impl reference` times the CPU implementation of the same path (the oracle port of the reference's torch
-step, all host threads) on the same workload.
+`--impl reference` times the reference's own CPU implementation of the same path on the same workload: the UNMODIFIED
+reference from baseline/_ref (baseline/install_ref.py; cpu_baseline.kind "reference"), all host threads; the oracle port
+only if that install is absent (kind "port").  That arm imports neither pyca_b200 nor the CUDA library.
+
+Timing: W warm-up steps, then R blocks of EXACTLY K steps, each block between its own pair of CUDA events (barrier +
+synchronize around the whole timed region); R is chosen so that the region lasts >= 50 ms whatever K is, and
+ms_per_step = median block time (max over ranks per block) / K.  `timing` in the JSON line says what really ran.
 """
 from __future__ import annotations
 
@@ -30,6 +35,26 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+
+def _pin_malloc():
+    """glibc's dynamic mmap / trim thresholds make the CPU step time depend on the allocation HISTORY of the process (the torch
+    CPU step allocates and frees 8-32 MB temporaries every step; whether they come from mmap, with a page fault per 4 KB, or
+    from the heap depends on what was freed before): the same 16-thread Lenia step measured 0.97 ms inside the CUDA arm and
+    1.81 ms in the reference arm in round 1.  Both arms therefore fix the thresholds up front (heap allocation up to 32 MB,
+    no trimming), which is also the setting under which the CPU path is fastest."""
+    try:
+        import ctypes
+
+        libc = ctypes.CDLL("libc.so.6")
+        libc.mallopt(-3, 32 << 20)   # M_MMAP_THRESHOLD (its maximum)
+        libc.mallopt(-1, 1 << 30)    # M_TRIM_THRESHOLD
+        libc.mallopt(-2, 64 << 20)   # M_TOP_PAD
+    except Exception:
+        pass
+
+
+_pin_malloc()
 
 # Native libraries (NCCL's version banner, ...) write to file descriptor 1 behind Python's back; the contract is ONE JSON
 # line on stdout, so fd 1 points at stderr while the benchmark runs and is restored for the final print.
@@ -59,6 +84,16 @@ def load_params(name):
     d = {k: t(p[k]) for k in ["mu", "sigma", "beta", "mu_k", "sigma_k", "weights"]}
     d["k_size"] = int(p["k_size"])
     return d, p
+
+
+def cpu_params(npz_name, C=3):
+    """Sanitised parameter tensors for the oracle port (no pyca_b200 import): leniaparams.py:68-87."""
+    from oracle import pyca_oracle as orc
+
+    d, _ = load_params(npz_name)
+    if C != 3:
+        d = {k: (v[:, :C, :C].clone() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+    return orc.sanitize_params(d)
 
 
 def measured_peaks():
@@ -130,6 +165,136 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+
+# ------------------------------------------------------------------------------------------------
+# workload descriptions shared by BOTH arms (the reference arm prints the same `config` without importing pyca_b200)
+# ------------------------------------------------------------------------------------------------
+SHAPES = {
+    "lenia_1k": ("lenia", 1, 1024, 1024), "lenia3_1k": ("lenia", 3, 1024, 1024), "lenia_4k": ("lenia", 1, 4096, 4096),
+    "lenia_seg": ("lenia", 1, 4096, 3976), "lenia_16k": ("lenia", 1, 16384, 16384),
+    "gol_64k": ("gol", 0, 65536, 65536), "gol_16k": ("gol", 0, 16384, 16384), "gol_250": ("gol", 0, 250, 250),
+    "mace_xchan_4k": ("xchan", 3, 4096, 4096), "mace_xchan_1k": ("xchan", 3, 1024, 1024),
+    "nca_256": ("nca", 16, 128, 128), "flow_lenia_1k": ("flow", 3, 1024, 1024), "flow_lenia_4k": ("flow", 3, 4096, 4096),
+}
+REPLICA_WORKLOADS = ("lenia_1k",)          # one independent world per GPU at N > 1
+SLAB_WORKLOADS = ("lenia_16k", "lenia_4k", "gol_64k", "gol_16k")
+GOL_GHOST = 64
+L2_BYTES = 126 << 20
+
+
+def lenia_ring_worlds(C, H, W, steps=0):
+    """Worlds in the round-robin ring of a Lenia workload smaller than L2 (1 = no ring)."""
+    per_world = H * W * C * 4 * (2 + 2 * max(1, C))
+    if per_world > L2_BYTES:
+        return 1
+    return max(-(-(192 << 20) // per_world), (steps + 1) // 2 if steps >= 18 else 0)
+
+
+def static_config(name, n):
+    fam, C, H, W = SHAPES[name]
+    if fam == "lenia":
+        per_rank = H * W * C * 8 // (1 if name in REPLICA_WORKLOADS else n)
+        cfg = {"workload": name, "shape": [1, C, H, W], "k_size": 31,
+               "params": "demo_lenia/abominable_mongolic" + (f" sliced to C={C}" if C != 3 else ""),
+               "partition": "single GPU" if n == 1 else (f"{n} independent worlds, one per GPU, no communication"
+                                                         if name in REPLICA_WORKLOADS else f"{n} row slabs, halo rows over NVLink"),
+               "l2": ("inputs larger than L2: a ring of independent worlds (>= 192 MB of state + workspace) advanced round-robin, one "
+                      "world per step, no flush kernel between timed steps") if lenia_ring_worlds(C, H, W) > 1 else
+                     ("inputs larger than L2" if per_rank > L2_BYTES else f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)")}
+    elif fam == "gol":
+        small = H * ((W + 31) // 32) <= 4096
+        cfg = {"workload": name, "shape": [H, W], "rule": "B3/S23", "layout": "1 bit/cell",
+               "generations_per_step": 100 if (small and n == 1) else (16 if n > 1 else 1),
+               "partition": "single GPU" if n == 1 else f"{n} row slabs, {GOL_GHOST} ghost rows exchanged every {GOL_GHOST} generations",
+               "l2": "inputs larger than L2" if H * W // 8 // n > L2_BYTES else f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)"}
+    elif fam == "xchan":
+        cfg = {"workload": name, "shape": [1, 3, H, W], "params": "demo_macelenia_xchan/arborical_asbestosis", "beta": 6, "alpha": 0.03,
+               "partition": "one world per GPU", "l2": "inputs larger than L2" if H * W * 12 > L2_BYTES else "flushed between timed steps"}
+    elif fam == "flow":
+        cfg = {"workload": name, "shape": [1, 3, H, W], "params": "demo_macelenia/anencephalic_brakeman", "dd": 2, "sigma_rt": 0.65,
+               "partition": "one world per GPU", "l2": "inputs larger than L2" if H * W * 12 > L2_BYTES else "flushed between timed steps"}
+    else:
+        B = 256
+        cfg = {"workload": name, "shape": [B, 16, H, W], "weights": "NCA_models/betta", "rng": "Bernoulli(1/2) update mask per cell and step",
+               "partition": f"batch sharded over {n} GPU(s)",
+               "l2": "inputs larger than L2" if B // n * 16 * H * W * 4 > L2_BYTES else "flushed between timed steps"}
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the UNMODIFIED reference (baseline/_ref) stepped through its own public API on the host cores
+# ------------------------------------------------------------------------------------------------
+class RefArm:
+    """One BASELINE workload on the reference's own classes (`Automaton.step()` on device='cpu'), at a size the host finishes in
+    bounded time (the `sample`).  Falls back to the oracle port (tests infrastructure, oracle/pyca_oracle.py) only when
+    baseline/_ref is absent -- kind says which."""
+
+    def __init__(self, name):
+        self.name = name
+        self.fam, self.C, H, W = SHAPES[name]
+        cap = {"lenia": 4096, "gol": 4096, "xchan": 1024, "flow": 1024, "nca": 128}[self.fam]
+        self.H, self.W = min(H, cap), min(W, cap)
+        self.B = 16 if self.fam == "nca" else 1
+        self.kind = "reference"
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "baseline"))
+            from ref_loader import load_reference
+
+            self.ref = load_reference()
+        except Exception as e:
+            log(f"reference install not usable ({e!r}): CPU arm falls back to the oracle port")
+            self.ref = None
+            self.kind = "port"
+
+    def _param_file(self):
+        sub = {"lenia": "demo_lenia/abominable_mongolic.pt", "xchan": "demo_macelenia_xchan/arborical_asbestosis.pt",
+               "flow": "demo_macelenia/anencephalic_brakeman.pt"}[self.fam]
+        return os.path.join(self.ref.root, "demo_data", sub)
+
+    def setup(self):
+        torch.set_num_threads(os.cpu_count() or 1)
+        torch.set_grad_enabled(False)
+        g = torch.Generator().manual_seed(0)
+        if self.ref is None:
+            self._port = make_workload(self.name, 0, 1, "cpu")
+            self._port.cpu_setup()
+            self.step = self._port.cpu_step
+            self.H, self.W = getattr(self._port, "cH", self.H), getattr(self._port, "cW", self.W)
+            self.B = getattr(self._port, "cB", self.B)
+            return
+        R = self.ref
+        if self.fam == "gol":
+            self.auto = R.CA2D((self.H, self.W), device="cpu")
+            self.auto.world = (torch.rand(self.H, self.W, generator=g) < 0.5).to(torch.int)
+        elif self.fam == "nca":
+            self.auto = R.NeuralCA((self.H, self.W), os.path.join(R.root, "demo_data", "NCA_models"), device="cpu")
+            self.auto.load_model(os.path.join(R.root, "demo_data", "NCA_models", "betta.pt"))
+            self.auto.state = torch.rand(self.B, 16, self.H, self.W, generator=g)
+        else:
+            C = self.C
+            P = R.LeniaParams(from_file=self._param_file())
+            if C != 3:
+                d = {k: (v[:, :C, :C].clone() if isinstance(v, torch.Tensor) else v) for k, v in P.param_dict.items()}
+                P = R.LeniaParams(param_dict=d, channels=C)
+            s0 = torch.rand(1, C, self.H, self.W, generator=g) * (1.5 if self.fam == "flow" else 1.0)
+            cls = {"lenia": R.Lenia, "xchan": R.MaCELeniaXChan, "flow": R.FlowLenia}[self.fam]
+            kw = dict(num_channels=C, params=P, state_init=s0, device="cpu")
+            if self.fam == "lenia":
+                kw["dt"] = 0.1
+            self.auto = cls((self.H, self.W), **kw)
+        self.step = self.auto.step
+
+    def cells_per_step(self):
+        return self.B * self.H * self.W
+
+    def sample(self):
+        what = {"lenia": f"Lenia C={self.C} {self.H}x{self.W} Lenia.step() (lenia.py:430-469)",
+                "xchan": f"MaCE-XChan C=3 {self.H}x{self.W} MaCELeniaXChan.step() (mace_lenia_xchan.py:59-76, macelenia.py:89-159)",
+                "flow": f"FlowLenia C=3 {self.H}x{self.W} FlowLenia.step() (flow_lenia.py:246-253)",
+                "gol": f"GoL {self.H}x{self.W} int32 CA2D.step() (ca2d.py:195-209)",
+                "nca": f"NCA {self.B}x16x{self.H}x{self.W} NeuralCA.step() (nca.py:67-72, 239-263)"}[self.fam]
+        return what + (" of the unmodified reference in baseline/_ref" if self.kind == "reference" else " -- oracle port")
+
 # ------------------------------------------------------------------------------------------------
 # workloads
 # ------------------------------------------------------------------------------------------------
@@ -188,6 +353,7 @@ class LeniaWL(Workload):
     def __init__(self, rank, world, device, H, W, C=1, name="lenia_1k", replicas=False):
         super().__init__(rank, world, device)
         self.H, self.W, self.C, self.name = H, W, C, name
+        self.steps_hint = 0   # K of the timed blocks (set by main() before setup(): sizes the ring / the captured graph)
         # replicas: one independent world per GPU (no communication, weak scaling); else one world in row slabs
         self.replicas = replicas and world > 1
         self.slab = None
@@ -214,8 +380,7 @@ class LeniaWL(Workload):
             # A world smaller than L2 is benchmarked as a ring of independent worlds advanced round-robin, the ring sized
             # well above L2 (two state buffers + spectra workspace per world): every step then works on data that was
             # last touched `n_rot` steps ago, i.e. inputs larger than L2, with no flush kernel between the timed steps.
-            per_world = self.H * self.W * self.C * 4 * (2 + 2 * max(1, self.C))
-            self.n_rot = 1 if per_world > (126 << 20) else -(-(192 << 20) // per_world)
+            self.n_rot = lenia_ring_worlds(self.C, self.H, self.W, self.steps_hint)
             self.autos = []
             for r in range(self.n_rot):
                 st = self.h_state if r == 0 else torch.rand(1, self.C, self.H, self.W, generator=g)
@@ -227,13 +392,18 @@ class LeniaWL(Workload):
             self.rot_i = 0
             self.rotating = self.n_rot > 1
             self.slab = None
-            # small worlds: the ring's steps (one per world, twice round) are captured into a CUDA graph -- a 20 us step is
-            # otherwise paced by the Python launch path and its jitter (B200CA_BENCH_GRAPH=0 issues every step from Python)
+            # small worlds: a timed block of K steps is captured into ONE CUDA graph -- a 10-20 us step is otherwise paced by
+            # the Python launch path and its jitter (B200CA_BENCH_GRAPH=0 issues every step from Python).  The graph steps the
+            # first K/2 worlds of the ring twice round (2 x K/2 = K steps; an even count per world brings its ping-pong buffers
+            # back, so the graph can be replayed); K/2 worlds of 16 MB must exceed L2, hence K >= 18.
             self.graph = None
-            if self.rotating and os.environ.get("B200CA_BENCH_GRAPH", "1") != "0":
+            self.graph_steps = 0
+            k = self.steps_hint
+            if self.rotating and k >= 18 and os.environ.get("B200CA_BENCH_GRAPH", "1") != "0":
                 from pyca_b200.graph import StepGraph
 
-                self.graph = StepGraph(self.autos, reps=2)
+                self.graph = StepGraph(self.autos[:k // 2], reps=2)
+                self.graph_steps = self.graph.steps_per_replay
         else:
             self.slab = LeniaSlabCUDA(self.params, self.C, self.H, self.W, self.rank, self.world, device=self.device)
             g = torch.Generator(device=self.device).manual_seed(1000 + self.rank)
@@ -247,24 +417,21 @@ class LeniaWL(Workload):
         else:
             self.slab.step()
 
-    def align(self):
-        """(untimed, after the warm-up) finishes the current turn of the ring so that the timed steps start at world 0"""
-        while getattr(self, "graph", None) is not None and self.rot_i != 0:
-            self.step()
-
     def run(self, k):
-        """exactly k steps of the ring (one world per step, round-robin): whole turns of the ring by graph replay, the rest
-        step by step"""
+        """exactly k steps (one world per step): one graph replay of 2 x (K/2) steps when the block was captured, the
+        remainder (K odd) / everything else step by step from Python, round-robin over the ring"""
         g = getattr(self, "graph", None)
-        if g is not None:
-            while k > 0 and self.rot_i != 0:   # finish the current turn of the ring
-                self.step()
-                k -= 1
-            while k >= g.steps_per_replay:
-                g.replay()
-                k -= g.steps_per_replay
+        if g is not None and k >= self.graph_steps:
+            g.replay()
+            k -= self.graph_steps
         for _ in range(k):
             self.step()
+
+    def issue_note(self):
+        if getattr(self, "graph", None) is not None:
+            return (f"each timed block of K steps = one CUDA-graph replay of {self.graph_steps} steps ({self.graph_steps // 2} worlds of "
+                    f"the {self.n_rot}-world ring, twice round)" + (" + 1 step from Python" if self.steps_hint % 2 else ""))
+        return "steps issued one by one from Python (ctypes call per step)"
 
     def cells_per_step(self):
         return self.H * self.W * (self.world if self.replicas else 1)
@@ -274,9 +441,7 @@ class LeniaWL(Workload):
             return self.slab.use_fft
         if self.auto is not None:
             return self.auto.use_fft
-        import pyca_b200  # (reference arm on CPU: say which path the CUDA arm would take for this shape)
-
-        return pyca_b200.lib().b200ca_lenia_fft_length(self.H, self.W) > 0
+        return True
 
     def launches_per_step(self):
         if self.slab is not None:
@@ -299,25 +464,7 @@ class LeniaWL(Workload):
         return {"kernel": "lenia_conv_kernel", "bytes": cells * self.C * 8, "fma": cells * self.C * self.C * 496}
 
     def config(self):
-        path = f"row-FFT x column-FIR hybrid + growth + clamp, {self._fft_kernels()} kernels/step" if self._fft() else \
-            "direct folded conv (TMA tiles) + growth + clamp, 1 kernel/step"
-        return {"workload": self.name, "shape": [1, self.C, self.H, self.W], "k_size": 31,
-                "params": "demo_lenia/abominable_mongolic" + (f" sliced to C={self.C}" if self.C != 3 else ""),
-                "path": path,
-                "partition": "single GPU" if self.world == 1 else (
-                    f"{self.world} independent worlds, one per GPU, no communication" if self.replicas else
-                    f"{self.world} row slabs, NCCL halo exchange" + (" overlapped with interior" if not (self.slab and self.slab.use_fft) else "")),
-                "l2": self._l2_note()}
-
-    def _l2_note(self):
-        if getattr(self, "rotating", False):
-            return (f"inputs larger than L2: {self.n_rot} independent worlds advanced round-robin (one world per step; a world is "
-                    f"revisited after {self.n_rot} steps), no flush kernel between timed steps"
-                    + ("; steps issued by CUDA-graph replay (2 turns of the ring per launch), remainder from Python"
-                       if getattr(self, "graph", None) is not None else ""))
-        if self.H * self.W * self.C * 8 // max(1, 1 if self.replicas else self.world) > (126 << 20):
-            return "inputs larger than L2"
-        return f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)"
+        return static_config(self.name, self.world)
 
     def e2e_setup(self):
         import pyca_b200
@@ -346,7 +493,7 @@ class LeniaWL(Workload):
         from tests.util import load_npz, t
 
         self.orc = orc
-        p = self.params.param_dict
+        p = cpu_params("params_lenia_abominable_mongolic.npz", self.C)
         self.cK = orc.lenia_kernel(p["beta"].cpu(), p["mu_k"].cpu(), p["sigma_k"].cpu(), 31)
         self.cH, self.cW = min(self.H, 4096), min(self.W, 4096)
         g = torch.Generator().manual_seed(0)
@@ -370,7 +517,7 @@ class GolWL(Workload):
     def __init__(self, rank, world, device, H, W, name):
         super().__init__(rank, world, device)
         self.H, self.W, self.name = H, W, name
-        self.ghost = 64   # ghost rows per side = generations between halo exchanges (redundant rows: 2*64 / 8192 at 8 GPUs)
+        self.ghost = GOL_GHOST   # ghost rows per side = generations between halo exchanges (redundant rows: 2*64 / 8192 at 8 GPUs)
         # the 250x250 world fits in shared memory: CA2D.step(nsteps) runs 100 generations per launch (a "step" of this
         # workload is 100 generations; cells_per_step counts them all)
         self.steps_per_call = 100 if H * ((W + 31) // 32) <= 4096 and world == 1 else 1
@@ -410,12 +557,7 @@ class GolWL(Workload):
                 "fma": 0}
 
     def config(self):
-        return {"workload": self.name, "shape": [self.H, self.W], "rule": "B3/S23", "layout": "1 bit/cell",
-                "generations_per_launch": self.steps_per_call,
-                "partition": "single GPU" if self.world == 1 else
-                f"{self.world} row slabs, {self.ghost} ghost rows exchanged every {self.ghost} generations (NCCL)",
-                "l2": "inputs larger than L2" if self.H * self.W // 8 // self.world > (126 << 20) else
-                f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)"}
+        return static_config(self.name, self.world)
 
     def e2e_setup(self):
         import pyca_b200
@@ -490,9 +632,7 @@ class MaceWL(Workload):
         return {"kernel": "lenia_conv_kernel", "bytes": cells * 3 * 8, "fma": cells * 9 * 496}
 
     def config(self):
-        return {"workload": self.name, "shape": [1, 3, self.H, self.W], "params": "demo_macelenia_xchan/arborical_asbestosis",
-                "beta": 6, "alpha": 0.03, "partition": "one world per GPU",
-                "l2": "inputs larger than L2" if self.H * self.W * 12 > (126 << 20) else "flushed between timed steps"}
+        return static_config(self.name, self.world)
 
     def e2e_setup(self):
         import pyca_b200
@@ -519,7 +659,7 @@ class MaceWL(Workload):
         from oracle import pyca_oracle as orc
 
         self.orc = orc
-        p = self.params.param_dict
+        p = cpu_params("params_xchan_arborical_asbestosis.npz")
         self.cH, self.cW = min(self.H, 1024), min(self.W, 1024)
         self.cK = orc.lenia_kernel(p["beta"].cpu(), p["mu_k"].cpu(), p["sigma_k"].cpu(), 31)
         self.cKf = orc.kernel_fft(self.cK, self.cH, self.cW)
@@ -556,10 +696,6 @@ class FlowWL(MaceWL):
         cells = self.H * self.W
         return {"kernel": "affinity (lenia_fft_rows + lenia_fft_firinv) + flow_rt_kernel", "bytes": cells * 3 * 8, "fma": 0}
 
-    def config(self):
-        return {"workload": self.name, "shape": [1, 3, self.H, self.W], "params": "demo_macelenia/anencephalic_brakeman",
-                "dd": 2, "sigma_rt": 0.65, "partition": "one world per GPU",
-                "l2": "inputs larger than L2" if self.H * self.W * 12 > (126 << 20) else "flushed between timed steps"}
 
     def e2e_setup(self):
         self.h_out = torch.empty(1, 3, self.H, self.W).pin_memory()
@@ -574,7 +710,7 @@ class FlowWL(MaceWL):
         from oracle import pyca_oracle as orc
 
         self.orc = orc
-        p = self.params.param_dict
+        p = cpu_params("params_mace_anencephalic_brakeman.npz")
         self.cH, self.cW = min(self.H, 1024), min(self.W, 1024)
         self.cK = orc.lenia_kernel(p["beta"].cpu(), p["mu_k"].cpu(), p["sigma_k"].cpu(), 31)
         self.cKf = orc.kernel_fft(self.cK, self.cH, self.cW)
@@ -641,9 +777,7 @@ class NcaWL(Workload):
                 "flops_issued_tf32": cells * 2 * 3 * (128 * 40 + 16 * 128)}
 
     def config(self):
-        return {"workload": self.name, "shape": [self.B, 16, self.H, self.W], "weights": "NCA_models/betta", "rng": "in-kernel Philox",
-                "mlp": "tcgen05 split-tf32" if self.impl == 1 else "fp32 SIMT", "partition": f"batch sharded over {self.world} GPU(s)",
-                "l2": "inputs larger than L2" if self.Bl * 16 * self.H * self.W * 4 > (126 << 20) else "flushed between timed steps"}
+        return static_config(self.name, self.world)
 
     def e2e_setup(self):
         self.h_out = torch.empty_like(self.h_state).pin_memory()
@@ -666,7 +800,8 @@ class NcaWL(Workload):
         self.cB = min(self.B, 16)
         g = torch.Generator().manual_seed(0)
         self.cstate = torch.rand(self.cB, 16, self.H, self.W, generator=g)
-        self.cw = [t(self.fx[k]) for k in ("W1", "b1", "W2", "b2")]
+        fx = getattr(self, "fx", None) or __import__("tests.util", fromlist=["load_npz"]).load_npz("nca_betta.npz")
+        self.cw = [t(fx[k]) for k in ("W1", "b1", "W2", "b2")]
 
     def cpu_step(self):
         mask = torch.rand(self.cB, 1, self.H, self.W, device=self.cstate.device) <= 0.5
@@ -718,57 +853,87 @@ def barrier(world):
     torch.cuda.synchronize()
 
 
-def time_steps(wl, steps, warmup, world, flush):
-    """W untimed + exactly K timed steps; per-step CUDA events (the L2 flush between steps is untimed); returns
-    total ms over the K steps (max over ranks is taken by the caller)."""
-    for _ in range(warmup):
-        wl.step()
-    barrier(world)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    for i in range(steps):
-        if flush is not None:
-            flush.zero_()
-        evs[i][0].record()
-        wl.step()
-        evs[i][1].record()
-    barrier(world)
-    return sum(a.elapsed_time(b) for a, b in evs)
-
-
-def time_block(wl, steps, warmup, world):
-    """K steps back to back between one pair of events (used when the working set exceeds L2)."""
-    for _ in range(warmup):
-        wl.step()
-    if hasattr(wl, "align"):
-        wl.align()
-    barrier(world)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+def _one_block(wl, steps, flush):
+    """exactly `steps` steps; returns the CUDA events whose intervals add up to the block's device time"""
+    if flush is not None:
+        evs = []
+        for _ in range(steps):
+            flush.zero_()   # (untimed) evicts the previous step's lines
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            wl.step()
+            b.record()
+            evs.append((a, b))
+        return evs
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
     if hasattr(wl, "run"):
         wl.run(steps)
     else:
         for _ in range(steps):
             wl.step()
-    e1.record()
+    b.record()
+    return [(a, b)]
+
+
+def timed_blocks(wl, steps, warmup, world, flush, device, min_ms=50.0, max_blocks=2000):
+    """W untimed steps, then R blocks of EXACTLY K steps, every block between its own CUDA events on the launching stream, the
+    whole region bracketed by barrier + synchronize.  R is sized from one untimed block so that the region lasts >= min_ms
+    whatever K is (round 1's 20 x 21 us = 0.4 ms window let one host hiccup decide the figure).  Per block the MAX over ranks
+    is taken; the reported step time is the MEDIAN block / K.  Returns (ms_per_step, info)."""
+    for _ in range(warmup):
+        wl.step()
     barrier(world)
-    return e0.elapsed_time(e1)
+    evs = _one_block(wl, steps, flush)
+    torch.cuda.synchronize()
+    est = max(sum(a.elapsed_time(b) for a, b in evs), 1e-3)
+    R = torch.tensor([int(min(max(-(-min_ms // est), 3), max_blocks))], dtype=torch.int64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(R, op=torch.distributed.ReduceOp.MAX)
+    R = int(R.item())
+    barrier(world)
+    t0 = time.perf_counter()
+    blocks = [_one_block(wl, steps, flush) for _ in range(R)]
+    barrier(world)
+    wall = time.perf_counter() - t0
+    bt = torch.tensor([sum(a.elapsed_time(b) for a, b in blk) for blk in blocks], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(bt, op=torch.distributed.ReduceOp.MAX)
+    bt = bt.cpu()
+    med = float(bt.median())
+    info = {"blocks": R, "steps_per_block": steps, "block_ms_median": med, "block_ms_min": float(bt.min()), "block_ms_max": float(bt.max()),
+            "device_ms_total": float(bt.sum()), "wall_ms_total": wall * 1e3,
+            "statistic": "median over blocks of (max over ranks of the block's CUDA-event time) / K",
+            "issue": wl.issue_note() if hasattr(wl, "issue_note") else "steps issued one by one from Python (ctypes call per step)"}
+    return med / steps, info
 
 
-def cpu_baseline(wl, budget_s=12.0):
-    torch.set_num_threads(os.cpu_count() or 1)
-    wl.cpu_setup()
-    wl.cpu_step()  # warm-up
+def flush_for(wl, device):
+    """None when the workload's inputs exceed L2 by construction (big worlds, rings of worlds), else the flush buffer."""
+    big = wl.dominant()["bytes"] > L2_BYTES or getattr(wl, "rotating", False)
+    return None if big else torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
+
+
+def cpu_baseline(name, budget_s=12.0):
+    """The reference's own step (baseline/_ref; oracle port if absent) on all host cores, a bounded sample of the workload."""
+    arm = RefArm(name)
+    arm.setup()
+    t0 = time.perf_counter()
+    n0 = 0
+    while time.perf_counter() - t0 < min(2.0, 0.25 * budget_s) or n0 < 1:   # spin-up: thread pools, first-touch pages
+        arm.step()
+        n0 += 1
     t0 = time.perf_counter()
     n = 0
     while True:
-        wl.cpu_step()
+        arm.step()
         n += 1
         el = time.perf_counter() - t0
         if el > budget_s or (n >= 200 and el > 0.8 * budget_s):
             break
-    gcups = wl.cpu_cells_per_step() * n / el / 1e9
-    return {"value": gcups, "unit": "GCUPS", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} x {wl.cpu_sample()}, {el:.1f} s", "ms_per_step": el / n * 1e3}
+    gcups = arm.cells_per_step() * n / el / 1e9
+    return {"value": gcups, "unit": "GCUPS", "cores": torch.get_num_threads(), "kind": arm.kind,
+            "sample": f"{n} x {arm.sample()}, {el:.1f} s", "ms_per_step": el / n * 1e3}
 
 
 def torch_gpu_baseline(wl, device, budget_s=1.5):
@@ -799,56 +964,38 @@ def torch_gpu_baseline(wl, device, budget_s=1.5):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the CPU implementation of the path (oracle port), all host threads, rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path (baseline/_ref), all host threads, rank 0 only.
+    Imports neither the product package nor the CUDA library, and creates no CUDA context."""
     if rank != 0:
         return
     name = args.workload or "lenia_1k"
-    wl = make_workload(name, 0, 1, "cpu")
-    if hasattr(wl, "_params"):
-        wl.params = wl._params()
-    elif isinstance(wl, MaceWL):
-        import pyca_b200
-
-        d, _ = load_params("params_mace_anencephalic_brakeman.npz" if isinstance(wl, FlowWL) else "params_xchan_arborical_asbestosis.npz")
-        wl.params = pyca_b200.LeniaParams(param_dict=d)
-    elif isinstance(wl, NcaWL):
-        from tests.util import load_npz
-
-        wl.fx = load_npz("nca_betta.npz")
-    torch.set_num_threads(os.cpu_count() or 1)
-    if torch.cuda.is_available():
-        # Measured on the B200 box (tools/cpu_arm_probe.py): the same torch CPU step runs at 0.98 ms in a process that has
-        # created a CUDA context and a pinned allocation and at 1.9 ms in one that has not (16 threads either way).  The CPU
-        # arm gets the faster setting -- it is also the one `cpu_baseline` of the CUDA arm runs under.  No kernel is launched.
-        torch.zeros(1, device="cuda")
-        torch.empty(1 << 20).pin_memory()
-    wl.cpu_setup()
+    arm = RefArm(name)
+    arm.setup()
     # one "step" of this arm = a bounded sample of `reps` consecutive CPU steps (>= 50 ms of work), so that K steps are not
-    # dominated by start-up effects; a 4 s untimed spin-up precedes the W warm-up steps (on the box the step time keeps
-    # falling for the first ~3 s of a fresh process: 1.5, 1.1, 0.98 ms in consecutive 2 s windows)
+    # dominated by start-up effects; a 4 s untimed spin-up precedes the W warm-up steps (thread pools, first-touch pages)
     t0 = time.perf_counter()
     n0 = 0
     while time.perf_counter() - t0 < 4.0 or n0 < 1:
-        wl.cpu_step()
+        arm.step()
         n0 += 1
     t_one = (time.perf_counter() - t0) / n0
     reps = max(1, min(int(0.05 / t_one + 0.999), 1000))
     for _ in range(args.warmup):
         for _ in range(reps):
-            wl.cpu_step()
+            arm.step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for _ in range(reps):
-            wl.cpu_step()
+            arm.step()
     el = time.perf_counter() - t0
-    v = wl.cpu_cells_per_step() * args.steps * reps / el / 1e9
-    cfg = dict(wl.config())
-    cfg["cpu_sample"] = wl.cpu_sample()
+    v = arm.cells_per_step() * args.steps * reps / el / 1e9
+    scaling = "weak" if name in REPLICA_WORKLOADS or SHAPES[name][0] in ("xchan", "flow") else "strong"
     line = {"impl": "reference", "metric": "cell-updates/sec", "value": v, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": el / (args.steps * reps) * 1e3, "higher_is_better": True, "scaling": wl.scaling,
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
-            "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"{args.steps} steps x {reps} consecutive CPU updates of {wl.cpu_sample()}"},
+            "warmup": args.warmup, "ms_per_step": el / (args.steps * reps) * 1e3, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "f32" if SHAPES[name][0] != "gol" else "int32", "data": "synthetic",
+            "config": static_config(name, args.gpus),
+            "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": torch.get_num_threads(), "kind": arm.kind,
+                             "sample": f"{args.steps} steps x {reps} consecutive CPU updates of {arm.sample()}"},
             "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -880,22 +1027,22 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=torch.device(device))
     name = args.workload or "lenia_1k"
+    from pyca_b200 import _lib as b200lib
+
     wl = make_workload(name, rank, world, device)
+    wl.steps_hint = args.steps
     wl.setup()
     dom = wl.dominant()
-    big = dom["bytes"] > (126 << 20) or getattr(wl, "rotating", False)
-    flush = None if big else torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
+    flush = flush_for(wl, device)
+    b200lib.variants(reset=True)
+    wl.step()   # (untimed) records which kernel instantiations one step of this workload launches
+    kernels = b200lib.variants(reset=True)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    total_ms = time_block(wl, args.steps, args.warmup, world) if big else time_steps(wl, args.steps, args.warmup, world, flush)
+    ms_per_step, timing = timed_blocks(wl, args.steps, args.warmup, world, flush, device)
     clocks = sampler.stop() if sampler else None
-    tms = torch.tensor([total_ms], dtype=torch.float64, device=device)
-    if world > 1:
-        torch.distributed.all_reduce(tms, op=torch.distributed.ReduceOp.MAX)
-    total_ms = float(tms.item())
-    ms_per_step = total_ms / args.steps
     value = wl.cells_per_step() / (ms_per_step * 1e-3) / 1e9
 
     # dominant kernel: average launch duration measured live with CUDA events on the launching stream
@@ -980,16 +1127,22 @@ def main():
                 continue
             try:
                 ow = make_workload(other, 0, 1, device)
+                k = 4 if other in ("mace_xchan_4k", "flow_lenia_4k") else 20
+                ow.steps_hint = k
                 ow.setup()
                 od = ow.dominant()
-                k = 3 if other in ("mace_xchan_4k", "flow_lenia_4k") else 10
-                ms = time_block(ow, k, 3, 1) / k
+                b200lib.variants(reset=True)
+                ow.step()
+                okern = b200lib.variants(reset=True)
+                ms, otiming = timed_blocks(ow, k, 3, 1, flush_for(ow, device), device, min_ms=30.0)
                 ent = {"gcups": ow.cells_per_step() / (ms * 1e-3) / 1e9, "ms_per_step": ms,
-                       "hbm_frac_algorithmic": od["bytes"] / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "config": ow.config()}
+                       "hbm_frac_algorithmic": od["bytes"] / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "config": ow.config(),
+                       "kernels": okern, "blocks": otiming["blocks"]}
                 if not args.no_cpu:
-                    cb = cpu_baseline(ow, budget_s=3.0)
+                    cb = cpu_baseline(other, budget_s=3.0)
                     ent["cpu_gcups"] = cb["value"]
                     ent["cpu_sample"] = cb["sample"]
+                    ent["cpu_kind"] = cb["kind"]
                     try:
                         ent["torch_gpu_gcups"] = torch_gpu_baseline(ow, device)["value"]
                     except Exception as e:
@@ -1045,16 +1198,16 @@ def main():
                 sw = make_workload(big, rank, world, device)
                 sw.setup()
                 k = 30  # a slab step is 0.2-0.9 ms: a window of several ms, so that one host hiccup does not decide the figure
-                t = torch.tensor([time_block(sw, k, 3, world) / k], dtype=torch.float64, device=device)
-                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-                ent["ms_per_step"] = float(t.item())
+                ms_n, tim_n = timed_blocks(sw, k, 3, world, None, device, min_ms=40.0)
+                ent["ms_per_step"] = ms_n
+                ent["blocks"] = tim_n["blocks"]
                 ent["gcups"] = sw.cells_per_step() / (ent["ms_per_step"] * 1e-3) / 1e9
                 ent["config"] = sw.config()
                 del sw
                 torch.cuda.empty_cache()
                 s1 = make_workload(big, 0, 1, device)
                 s1.setup()
-                ms1 = time_block(s1, k, 3, 1) / k
+                ms1, _ = timed_blocks(s1, k, 3, 1, None, device, min_ms=40.0)
                 ent["single_gpu_ms_per_step"] = ms1
                 ent["single_gpu_gcups"] = s1.cells_per_step() / (ms1 * 1e-3) / 1e9
                 del s1
@@ -1067,7 +1220,7 @@ def main():
     cpu = None
     torch_gpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(wl)
+        cpu = cpu_baseline(name)
         try:
             torch_gpu = torch_gpu_baseline(wl, device)
         except Exception as e:
@@ -1077,7 +1230,8 @@ def main():
         line = {"metric": "cell-updates/sec", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": wl.scaling, "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.config(),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": wl.launches_per_step() * args.steps, "roofline": roofline,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": wl.launches_per_step() * args.steps * timing["blocks"],
+                "gpu_launches_per_step": wl.launches_per_step(), "kernels": kernels, "timing": timing, "roofline": roofline,
                 "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu, "per_model": extras, "sharded": sharded}
         emit(line)
     if world > 1:

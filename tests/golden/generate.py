@@ -27,7 +27,7 @@ import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "baseline"))
 from ref_loader import load_reference  # noqa: E402
 
 REF = load_reference()

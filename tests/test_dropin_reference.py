@@ -15,7 +15,7 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF_ROOT, "pyca")
 
 
 def _ref():
-    sys.path.insert(0, os.path.join(HERE, "golden"))
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "baseline"))
     from ref_loader import load_reference
 
     return load_reference()

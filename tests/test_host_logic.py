@@ -63,3 +63,26 @@ def test_default_gen_draws_the_reference_parameters(tag):
     for k in ["mu", "sigma", "beta", "mu_k", "sigma_k", "weights"]:
         assert torch.equal(p[k], t(fx[f"{tag}_{k}"])), k
     assert p.k_size == 31 and p.k_mult == km
+
+
+def test_reference_arm_of_bench_is_free_of_the_product():
+    """bench.py --impl reference must not import pyca_b200 or load the CUDA library: its code path -- RefArm,
+    run_reference, static_config -- names neither."""
+    import importlib.util
+    import inspect
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "bench.py")).read()
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    assert spec is not None
+    import ast
+
+    tree = ast.parse(src)
+    wanted = {"RefArm", "run_reference", "static_config", "cpu_baseline", "lenia_ring_worlds"}
+    for node in tree.body:
+        if isinstance(node, (ast.FunctionDef, ast.ClassDef)) and node.name in wanted:
+            seg = ast.get_source_segment(src, node)
+            assert "pyca_b200" not in seg and "b200ca" not in seg.replace("B200CA", ""), node.name
+            wanted.discard(node.name)
+    assert not wanted, f"not found in bench.py: {wanted}"
