@@ -464,9 +464,11 @@ static int launch_gol_rows(const uint32_t *a, uint32_t *dst, const GolGeom &g, u
     if (life) {
         if (smem > 48 * 1024) B200CA_CUDA(cudaFuncSetAttribute(gol_rows_kernel<WPR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gol_rows_kernel<WPR, true><<<1, threads, smem, st>>>(a, dst, g, s_mask, b_mask, nsteps);
+        note_variant("gol_rows<%d,life>", WPR);
     } else {
         if (smem > 48 * 1024) B200CA_CUDA(cudaFuncSetAttribute(gol_rows_kernel<WPR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gol_rows_kernel<WPR, false><<<1, threads, smem, st>>>(a, dst, g, s_mask, b_mask, nsteps);
+        note_variant("gol_rows<%d,generic>", WPR);
     }
     B200CA_LAUNCH_CHECK("gol_rows_kernel");
     return 0;
@@ -705,9 +707,11 @@ extern "C" int b200ca_gol_run(uint32_t *a, uint32_t *b, int H, int W, int stride
             if (life) {
                 if (smem > 48 * 1024) B200CA_CUDA(cudaFuncSetAttribute(gol_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 gol_small_kernel<true><<<1, GOL_SMALL_THREADS, smem, st>>>(a, dst, g, s_mask, b_mask, nsteps);
+                note_variant("gol_small<life>");
             } else {
                 if (smem > 48 * 1024) B200CA_CUDA(cudaFuncSetAttribute(gol_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 gol_small_kernel<false><<<1, GOL_SMALL_THREADS, smem, st>>>(a, dst, g, s_mask, b_mask, nsteps);
+                note_variant("gol_small<generic>");
             }
             B200CA_LAUNCH_CHECK("gol_small_kernel");
             return 0;

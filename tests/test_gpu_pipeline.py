@@ -111,23 +111,22 @@ def test_step_graph_matches_eager_steps():
     mk = lambda s: pyca_b200.Lenia((64, 1024), params=params, state_init=s, device="cuda")
     eager = [mk(s) for s in states]
     graphed = [mk(s) for s in states]
-    sg = StepGraph(graphed, reps=2)          # refresh() itself advances every automaton by 2 warm-up steps
-    for a in eager:
-        a.step()
-        a.step()
+    sg = StepGraph(graphed, reps=2)          # (the warm-up steps inside refresh() are undone: nothing has advanced yet)
+    for a, b in zip(eager, graphed):
+        assert torch.equal(a.state, b.state) and b.frames == 0
     for _ in range(3):
         sg.replay()
         for a in eager:
             a.step()
             a.step()
     for a, b in zip(eager, graphed):
-        assert torch.equal(a.state, b.state) and a.frames == b.frames == 8
+        assert torch.equal(a.state, b.state) and a.frames == b.frames == 6
     graphed[1].state[:, :, :8] = 0.25        # edit between replays -> refresh() re-captures
     eager[1].state[:, :, :8] = 0.25
     sg.refresh()
     sg.replay()
     for a in eager:
-        for _ in range(4):
+        for _ in range(2):
             a.step()
     for a, b in zip(eager, graphed):
         assert torch.equal(a.state, b.state)
@@ -135,4 +134,9 @@ def test_step_graph_matches_eager_steps():
     w0 = ca.world.clone()
     sgc = StepGraph(ca, reps=4)
     sgc.replay()
-    assert np.array_equal(ca.world.cpu().numpy(), orc.gol_run(w0.cpu().numpy(), 6))
+    assert np.array_equal(ca.world.cpu().numpy(), orc.gol_run(w0.cpu().numpy(), 4))
+    # NeuralCA is refused: its update mask is keyed by a step index passed by value at launch
+    class _FakeNca:
+        rng, device = "philox", "cuda"
+    with pytest.raises(pyca_b200.B200CAError):
+        StepGraph(_FakeNca(), reps=2)
