@@ -151,6 +151,24 @@ int b200ca_lenia_step_fft_phase(const float *state_in, float *state_out, const f
                                 const float *weights, float *workspace, int B, int C, int k_mult, int H, int W, float dt,
                                 int mode, int row_wrap, int phase, void *stream);
 
+/* "Marching" FFT path (pyca_b200/csrc/lenia_march.cu), the default for every world with H, W >= 32: the same operator and
+ * arguments as b200ca_lenia_step, computed by ONE kernel per source channel in which a CTA marches down a band of rows of
+ * one 224-column overlap-save strip -- forward row transforms (N = 256), the real 31-tap column FIR on the spectra, inverse
+ * transforms, growth, source sum and Euler step -- with the spectra kept in a shared-memory ring (no workspace, no HBM
+ * round trip of the spectra).
+ *   b200ca_lenia_march_supported      1 if the path handles an HxW world
+ *   b200ca_lenia_march_kernel_elems   floats of the prepared tap table (B, C*k_mult, C, 16, 256)
+ *   b200ca_lenia_march_prepare_kernel K (B, C*k_mult, C, ks, ks) -> tap table (cold path, update_params)
+ *   b200ca_lenia_march_band_rows      image rows per band for this shape; band_begin/band_end of the step restrict a launch
+ *                                     to bands [begin, end) (0,0 = all) so that a row slab can issue its boundary bands first */
+int b200ca_lenia_march_supported(int H, int W);
+int64_t b200ca_lenia_march_kernel_elems(int B, int C, int k_mult);
+int b200ca_lenia_march_prepare_kernel(const float *K, float *Kf, int B, int C, int k_mult, int ks, void *stream);
+int b200ca_lenia_march_band_rows(int H, int W, int B, int C);
+int b200ca_lenia_step_march(const float *state_in, float *state_out, const float *Kf, const float *mu, const float *sigma,
+                            const float *weights, int B, int C, int k_mult, int H, int W, float dt, int mode, int row_wrap,
+                            int band_begin, int band_end, void *stream);
+
 /* Mass-conserving redistribution (+ optional cross-channel mixing).  Replaces
  * MaCELenia._mace_step (macelenia.py:89-120) after the affinity, and
  * MaCELeniaXChan._cross_chan_step (mace_lenia_xchan.py:68-76) when alpha_on != 0:

@@ -1,0 +1,537 @@
+// Lenia-family step, "marching" FFT path for sm_100a: ONE kernel per source channel, spectra never leave the SM.
+//
+// Same decomposition as lenia_fft.cu -- row FFT x real 31-tap column FIR on the spectra x inverse row FFT, fused with the
+// growth function, the weighted source sum and the Euler step / clamp (lenia.py:430-469; affinity only for the MaCE
+// family, macelenia.py:122-159) -- but organised so that the row spectra are produced, filtered and consumed inside one
+// CTA's shared memory instead of round-tripping through HBM/L2 between a row-FFT kernel and a FIR+inverse kernel:
+//
+//   * x direction: overlap-save strips of N = 256 samples, V = 224 valid outputs (16-sample halo on both sides, so the
+//     strip starts on a 64-byte boundary of the framed row and the frame's 16 periodic columns are exactly the halo).
+//   * y direction: a CTA owns a BAND of 2*Lp image rows of one strip and marches down it 8 row pairs at a time.  Rows
+//     y0+p and y0+Lp+p ride in one complex transform (real taps keep re and im apart), so a band needs Lp+30 forward
+//     transforms for 2*Lp output rows.  The last 40 spectra rows live in a shared-memory ring (5 blocks of 8 rows).
+//   * per iteration: FIR of 8 output row pairs from 38 ring rows (FFMA2 on (re0,re1)/(im0,im1) pairs, all 256 threads) ->
+//     [warps 0-3: 8 inverse transforms | warps 4-7: 8 forward transforms of the block needed 5 iterations later] ->
+//     epilogue on all threads (growth, source sum, Euler/clamp, coalesced stores + periodic frame).
+//   * the 256-point transform is 16 x 16 in registers: 16 lanes per row, 16 samples per lane, ONE shared-memory exchange
+//     (XOR-swizzled, conflict free), constants of the 16-point kernels as immediates; two rows per warp, __syncwarp only.
+// HBM traffic per cell and step: the state once (+14 % strip halo, + (Lp+30)/Lp band halo, mostly L2 hits), the Euler
+// operand (an L2 hit: the same CTA loaded that row <= 38 rows earlier) and the output: ~1.1-1.3x the algorithmic 8 B.
+// tools/march_proto.py is the numpy model of the index arithmetic below.
+#include "common.cuh"
+
+namespace b200ca {
+
+namespace march {
+
+constexpr int F = B200CA_FRAME;
+constexpr int R = 15;
+constexpr int KROWS = R + 1;
+constexpr int N = 256;            // transform length
+constexpr int HALO = 16;          // samples discarded on each side of a strip (>= R)
+constexpr int V = N - 2 * HALO;   // valid outputs per strip
+constexpr int FT = 8;             // row pairs per iteration
+constexpr int NBLK = 5;           // ring blocks of FT rows: 40 rows >= FT + 2R
+constexpr int RING = NBLK * FT;
+constexpr int ROW4 = N / 2;       // float4 per spectra row
+constexpr int THREADS = 256;
+constexpr size_t SMEM = (size_t)(RING + FT) * ROW4 * sizeof(float4) + 256 * sizeof(float2);
+
+struct Args {
+    const float *state_in;
+    float *out;
+    const float2 *kf;   // (B, NS, C, KROWS, 128) tap pairs in FIR-thread order (march_prepare_kernel)
+    const float *mu, *sigma, *weights;
+    int B, C, NS, k_mult, H, W, pitch;
+    int Lp, niter;      // row pairs per band (multiple of FT), Lp / FT
+    int band0;          // first band of this launch (row slabs issue their boundary bands first)
+    int src;            // source-kernel index i*k_mult + m of this launch
+    int acc_in;         // 1: add to the partial sums already in `out` (sources after the first)
+    int final_src;      // 1: last source -> Euler step / clamp (LENIA) or plain sum (AFF)
+    float dt;
+    int mode, row_wrap;
+};
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+// a - b as ONE packed instruction (FADD2 has no negate modifier: a packed subtract written as an add costs two sign flips)
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+// a * (c + i s)
+__device__ __forceinline__ float2 cmul_cs(float2 a, float c, float s) { return make_float2(a.x * c - a.y * s, a.x * s + a.y * c); }
+
+// 4-point DFT, natural order in and out; INV: e^{+i...}
+template <bool INV>
+__device__ __forceinline__ void dft4(float2 &a, float2 &b, float2 &c, float2 &d) {
+    const float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), bd = csub(b, d);
+    a = cadd(t0, t2);
+    c = csub(t0, t2);
+    // t1 +- (b-d) * (-+i): scalar adds (a packed form would need the pair (bd.y, bd.x) swapped first)
+    if (INV) {
+        b = make_float2(t1.x - bd.y, t1.y + bd.x);
+        d = make_float2(t1.x + bd.y, t1.y - bd.x);
+    } else {
+        b = make_float2(t1.x + bd.y, t1.y - bd.x);
+        d = make_float2(t1.x - bd.y, t1.y + bd.x);
+    }
+}
+
+// 16-point DFT on registers, natural order in and out (two radix-4 stages, constants as immediates).
+// V[ka + 4 kb] = sum_{q1} (-+i)^{q1 kb} w^{q1 ka} sum_{q2} v[q1 + 4 q2] (-+i)^{q2 ka},  w = exp(-+2 pi i / 16)
+template <bool INV>
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, C2 = 0.70710678118654752f;
+    constexpr float SG = INV ? 1.f : -1.f;
+#pragma unroll
+    for (int q1 = 0; q1 < 4; ++q1) dft4<INV>(v[q1], v[q1 + 4], v[q1 + 8], v[q1 + 12]);  // v[q1 + 4 ka]
+    // twiddles w^{q1 ka}: exponents 1,2,3 / 2,4,6 / 3,6,9
+    v[1 + 4] = cmul_cs(v[1 + 4], C1, SG * S1);
+    v[1 + 8] = cmul_cs(v[1 + 8], C2, SG * C2);
+    v[1 + 12] = cmul_cs(v[1 + 12], S1, SG * C1);
+    v[2 + 4] = cmul_cs(v[2 + 4], C2, SG * C2);
+    v[2 + 8] = INV ? make_float2(-v[2 + 8].y, v[2 + 8].x) : make_float2(v[2 + 8].y, -v[2 + 8].x);
+    v[2 + 12] = cmul_cs(v[2 + 12], -C2, SG * C2);
+    v[3 + 4] = cmul_cs(v[3 + 4], S1, SG * C1);
+    v[3 + 8] = cmul_cs(v[3 + 8], -C2, SG * C2);
+    v[3 + 12] = cmul_cs(v[3 + 12], -C1, -SG * S1);
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka) dft4<INV>(v[4 * ka], v[4 * ka + 1], v[4 * ka + 2], v[4 * ka + 3]);  // V[ka + 4 kb] at v[4 ka + kb]
+    // transpose the 4 x 4 register grid back to natural order (pure renaming once unrolled)
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = a + 1; b < 4; ++b) {
+            const float2 tmp = v[4 * a + b];
+            v[4 * a + b] = v[4 * b + a];
+            v[4 * b + a] = tmp;
+        }
+}
+
+// One forward transform by a 16-lane group (lane t): image rows `ra` (re) and `rb` (im), 256 samples from framed column
+// `col0` on; the spectrum goes to `row4` in slot layout: float4 index ka*8 + (j ^ (ka & 7)) = (re, re', im, im') of the
+// frequencies ka + 16*(2j), ka + 16*(2j+1).  The 16 x 16 exchange runs in place in the destination row.
+__device__ __forceinline__ void forward_row(const float *__restrict__ ra, const float *__restrict__ rb, int col0, int pitch, float4 *row4,
+                                            const float2 *tw, int t) {
+    float2 v[16];
+    ra += col0 + t;
+    rb += col0 + t;
+    if (col0 + N <= pitch) {  // every strip but the last: plain loads at immediate offsets
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = make_float2(__ldg(ra + 16 * q), __ldg(rb + 16 * q));
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const bool ok = col0 + t + 16 * q < pitch;
+            v[q] = make_float2(ok ? __ldg(ra + 16 * q) : 0.f, ok ? __ldg(rb + 16 * q) : 0.f);
+        }
+    }
+    dft16<false>(v);  // v[ka] = sum_q x[t + 16 q] W16^{q ka}
+    float2 *row2 = reinterpret_cast<float2 *>(row4);
+#pragma unroll
+    for (int ka = 1; ka < 16; ++ka) {
+        const float2 w = tw[16 * t + (ka ^ t)];  // W256^{t ka}
+        v[ka] = cmul_cs(v[ka], w.x, w.y);
+    }
+#pragma unroll
+    for (int ka = 0; ka < 16; ++ka) row2[16 * t + (ka ^ t)] = v[ka];
+    __syncwarp();
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) v[n1] = row2[16 * n1 + (t ^ n1)];  // lane t now owns ka = t
+    __syncwarp();
+    dft16<false>(v);  // v[kb] = X[t + 16 kb]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) row4[8 * t + (j ^ (t & 7))] = make_float4(v[2 * j].x, v[2 * j + 1].x, v[2 * j].y, v[2 * j + 1].y);
+}
+
+// One inverse transform by a 16-lane group, in place: filtered spectrum (slot layout) -> float2 slot n = (out row a, out row b)
+__device__ __forceinline__ void inverse_row(float4 *row4, const float2 *tw, int t) {
+    float2 v[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 z = row4[8 * t + (j ^ (t & 7))];
+        v[2 * j] = make_float2(z.x, z.z);
+        v[2 * j + 1] = make_float2(z.y, z.w);
+    }
+    dft16<true>(v);  // v[n1] = sum_kb Y[t + 16 kb] W16^{-n1 kb}
+    float2 *row2 = reinterpret_cast<float2 *>(row4);
+#pragma unroll
+    for (int n1 = 1; n1 < 16; ++n1) {
+        const float2 w = tw[16 * t + (n1 ^ t)];
+        v[n1] = cmul_cs(v[n1], w.x, -w.y);  // conj(W256^{t n1})
+    }
+    // (a lane's slot-layout float4s and its exchange slots are the same 128 bytes: no hazard with the other lanes' loads)
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) row2[16 * t + (n1 ^ t)] = v[n1];
+    __syncwarp();
+#pragma unroll
+    for (int ka = 0; ka < 16; ++ka) v[ka] = row2[16 * ka + (t ^ ka)];  // lane t now owns n1 = t
+    __syncwarp();
+    dft16<true>(v);  // v[n2] = y[t + 16 n2]
+#pragma unroll
+    for (int q = 0; q < 16; ++q) row2[t + 16 * q] = v[q];
+}
+
+// writes the periodic images (not the cell itself) of interior cell (y, x) into the frame; rare, kept out of line
+__device__ __noinline__ void store_mirrors(float *__restrict__ plane, int H, int W, int pitch, int y, int x, float v, bool row_wrap) {
+    const int fy = y + F, fx = x + F;
+    int ys[3], xs[3], ny = 0, nx = 0;
+    ys[ny++] = fy;
+    if (row_wrap) {
+        if (y < F) ys[ny++] = fy + H;
+        if (y >= H - F) ys[ny++] = fy - H;
+    }
+    xs[nx++] = fx;
+    if (x < F) xs[nx++] = fx + W;
+    if (x >= W - F) xs[nx++] = fx - W;
+    for (int a = 0; a < ny; ++a)
+        for (int b = 0; b < nx; ++b)
+            if (a | b) plane[(size_t)ys[a] * pitch + xs[b]] = v;
+}
+
+// Column FIR of 4 output row pairs (4*H4 .. 4*H4+3 of the current block of 8) for the thread's two frequencies.  The 34 input
+// rows start at row 4*H4 of ring block b0 and run through blocks b0 .. b0+4; `blk[i]` points at this thread's float4 of the
+// first row of block (b0 + i) % 5, so every load is pointer + immediate offset (no per-row wrap arithmetic).
+template <int H4>
+__device__ __forceinline__ void fir_half(const float4 *const (&blk)[NBLK], const float2 (&kt)[KROWS], float4 *fout) {
+    float2 are[4], aim[4];
+#pragma unroll
+    for (int y = 0; y < 4; ++y) are[y] = aim[y] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int rr = 0; rr < 4 + 2 * R; ++rr) {
+        constexpr int unused = 0;
+        (void)unused;
+        const int row = 4 * H4 + rr;
+        const float4 z = blk[row / FT][(row % FT) * ROW4];
+        const float2 zre = make_float2(z.x, z.y), zim = make_float2(z.z, z.w);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int dy = rr - R - y;
+            if (dy >= -R && dy <= R) {
+                are[y] = __ffma2_rn(kt[dy < 0 ? -dy : dy], zre, are[y]);
+                aim[y] = __ffma2_rn(kt[dy < 0 ? -dy : dy], zim, aim[y]);
+            }
+        }
+    }
+#pragma unroll
+    for (int y = 0; y < 4; ++y) fout[y * ROW4] = make_float4(are[y].x, are[y].y, aim[y].x, aim[y].y);
+}
+
+struct EpiArgs {
+    const float2 *u;       // this thread's sample of output pair 0 (stride N float2 per pair)
+    const float *sa;       // state, row pair 0 (EULER)
+    float *oa;             // output, row pair 0
+    float *oplane;
+    long long half;        // Lp * pitch: distance of the second row of a pair
+    int pitch, H, W, ya0, Lp, xw, row_wrap;
+    float mu, nc2, w2, wn, dt;   // growth(u) * weight = exp2((u - mu)^2 * nc2) * w2 + wn
+};
+
+// growth + weighted source sum (+ partial sums of earlier sources) (+ Euler step / clamp) and the stores of 8 row pairs.
+// EDGE = false: a CTA whose cells have no periodic images and whose rows all lie inside the world.
+template <bool EDGE, bool ACC, bool EULER>
+__device__ __forceinline__ void epilogue(const EpiArgs &e) {
+    float s0[FT], s1[FT], p0[FT], p1[FT];
+    // operands from global memory first, all in flight together
+#pragma unroll
+    for (int r = 0; r < FT; ++r) {
+        const bool oka = !EDGE || e.ya0 + r < e.H, okb = !EDGE || e.ya0 + e.Lp + r < e.H;
+        if (EULER) {
+            s0[r] = oka ? __ldg(e.sa + (size_t)r * e.pitch) : 0.f;
+            s1[r] = okb ? __ldg(e.sa + e.half + (size_t)r * e.pitch) : 0.f;
+        }
+        if (ACC) {
+            p0[r] = oka ? e.oa[(size_t)r * e.pitch] : 0.f;
+            p1[r] = okb ? e.oa[e.half + (size_t)r * e.pitch] : 0.f;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < FT; ++r) {
+        const float2 u = e.u[r * N];
+        const float d0 = u.x - e.mu, d1 = u.y - e.mu;
+        float v0 = fmaf(exp2f(d0 * d0 * e.nc2), e.w2, e.wn), v1 = fmaf(exp2f(d1 * d1 * e.nc2), e.w2, e.wn);
+        if (ACC) {
+            v0 += p0[r];
+            v1 += p1[r];
+        }
+        if (EULER) {
+            v0 = fminf(fmaxf(fmaf(e.dt, v0, s0[r]), 0.f), 1.f);
+            v1 = fminf(fmaxf(fmaf(e.dt, v1, s1[r]), 0.f), 1.f);
+        }
+        if (!EDGE) {
+            e.oa[(size_t)r * e.pitch] = v0;
+            e.oa[e.half + (size_t)r * e.pitch] = v1;
+        } else {
+            const int ya = e.ya0 + r, yb = ya + e.Lp;
+            const bool xe = (e.xw < F) || (e.xw >= e.W - F);
+            if (ya < e.H) {
+                e.oa[(size_t)r * e.pitch] = v0;
+                if (xe || (e.row_wrap && (ya < F || ya >= e.H - F))) store_mirrors(e.oplane, e.H, e.W, e.pitch, ya, e.xw, v0, e.row_wrap != 0);
+            }
+            if (yb < e.H) {
+                e.oa[e.half + (size_t)r * e.pitch] = v1;
+                if (xe || (e.row_wrap && (yb < F || yb >= e.H - F))) store_mirrors(e.oplane, e.H, e.W, e.pitch, yb, e.xw, v1, e.row_wrap != 0);
+            }
+        }
+    }
+}
+
+// grid (strips, bands of this launch, B), block 256.  SINGLE: one destination plane (C == 1): taps stay in registers.
+template <bool SINGLE>
+__global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
+    extern __shared__ __align__(16) float4 msm[];
+    float4 *ring = msm;                                  // RING rows of ROW4 float4
+    float4 *filt = msm + RING * ROW4;                    // FT rows: filtered spectra -> inverse exchange -> outputs
+    float2 *tw = reinterpret_cast<float2 *>(filt + FT * ROW4);  // W256^{t r} at [16 t + (r ^ t)]
+    const int tid = threadIdx.x, lane16 = tid & 15, grp = tid >> 4;  // 16 groups of 16 lanes
+    const int strip = blockIdx.x, band = a.band0 + blockIdx.y, b = blockIdx.z;
+    const int y0 = band * 2 * a.Lp;
+    const int col0 = strip * V;                          // framed column of sample n = 0 (world column strip*V - HALO)
+    const int src_plane = b * a.C + a.src / a.k_mult;
+    const size_t plane_elems = (size_t)(a.H + 2 * F) * a.pitch;
+    const float *splane = a.state_in + (size_t)src_plane * plane_elems;
+    const int max_frow = a.H + 2 * F - 1;
+
+    // input-independent prologue: twiddle table, taps of the first destination
+    {
+        const int t = tid >> 4, r = tid & 15;
+        float sn, cs;
+        sincospif(-2.f * (float)((t * r) & 255) / 256.f, &sn, &cs);
+        tw[16 * t + (r ^ t)] = make_float2(cs, sn);
+    }
+    const int f = tid & 127, h = tid >> 7;
+    float2 kt[KROWS];
+    const float2 *kf0 = a.kf + (size_t)((b * a.NS + a.src) * a.C) * KROWS * ROW4 + f;
+#pragma unroll
+    for (int dy = 0; dy < KROWS; ++dy) kt[dy] = __ldg(kf0 + dy * ROW4);
+    pdl_wait_then_release();  // the state is the previous step's output
+    __syncthreads();          // twiddle table
+
+    // spectra row z of the band <- image rows (y0 + z - R, y0 + Lp + z - R), clamped into the framed plane
+    auto forward_block = [&](int z, int g) {
+        const int fa = min(y0 + z - R + F, max_frow), fb = min(y0 + a.Lp + z - R + F, max_frow);
+        forward_row(splane + (size_t)fa * a.pitch, splane + (size_t)fb * a.pitch, col0, a.pitch, ring + (z % RING) * ROW4, tw, lane16);
+        (void)g;
+    };
+    // prologue: blocks 0..4 (40 rows) by all 16 groups
+#pragma unroll 1
+    for (int z = grp; z < RING; z += 16) forward_block(z, grp);
+
+    const int xw = col0 - HALO + tid;                    // world column of this thread's sample n = tid (epilogue)
+    const bool col_ok = tid >= HALO && tid < N - HALO && xw < a.W;
+    const bool lenia = a.mode == B200CA_MODE_LENIA;
+    // CTAs that own cells with periodic images (first / last columns, first / last rows of a torus) or a partial last band
+    const bool edge = strip == 0 || col0 - HALO + N - HALO > a.W - F || y0 + 2 * a.Lp > a.H ||
+                      (a.row_wrap && (y0 < F || y0 + 2 * a.Lp > a.H - F));
+#pragma unroll 1
+    for (int it = 0; it < a.niter; ++it) {
+#pragma unroll 1
+        for (int j = 0; j < (SINGLE ? 1 : a.C); ++j) {
+            const int pidx = (b * a.NS + a.src) * a.C + j;
+            if (!SINGLE) {
+                const float2 *kfj = kf0 + (size_t)j * KROWS * ROW4;
+#pragma unroll
+                for (int dy = 0; dy < KROWS; ++dy) kt[dy] = __ldg(kfj + dy * ROW4);
+            }
+            __syncthreads();  // ring rows of this iteration are complete; the previous epilogue is done with `filt`
+            // ---- FIR: output pairs 4h .. 4h+3 of this block from ring rows (8 it + 4h) .. (+33), two frequencies per thread
+            {
+                const float4 *blk[NBLK];
+                int bb = it % NBLK;
+#pragma unroll
+                for (int i = 0; i < NBLK; ++i) {
+                    blk[i] = ring + bb * FT * ROW4 + f;
+                    bb = bb + 1 == NBLK ? 0 : bb + 1;
+                }
+                if (h == 0) fir_half<0>(blk, kt, filt + f);
+                else fir_half<1>(blk, kt, filt + 4 * ROW4 + f);
+            }
+            __syncthreads();
+            // ---- inverse transforms (groups 0-7) | forward transforms of the block needed next (groups 8-15, last destination)
+            if (grp < FT) {
+                inverse_row(filt + grp * ROW4, tw, lane16);
+            } else if (j == (SINGLE ? 0 : a.C - 1) && it + 1 < a.niter) {
+                forward_block(FT * (it + NBLK) + (grp - FT), grp);
+            }
+            __syncthreads();
+            // ---- epilogue: growth + weighted source sum (+ Euler / clamp), sample n = tid of the 8 row pairs
+            if (col_ok) {
+                const float mu = __ldg(a.mu + pidx), sg = __ldg(a.sigma + pidx), wt = __ldg(a.weights + pidx);
+                const size_t dplane = (size_t)(b * a.C + j) * plane_elems;
+                const size_t o0 = (size_t)(y0 + FT * it + F) * a.pitch + F + xw;
+                EpiArgs e;
+                e.u = reinterpret_cast<const float2 *>(filt) + tid;
+                e.sa = a.state_in + dplane + o0;
+                e.oplane = a.out + dplane;
+                e.oa = e.oplane + o0;
+                e.half = (long long)a.Lp * a.pitch;
+                e.pitch = a.pitch;
+                e.H = a.H;
+                e.W = a.W;
+                e.ya0 = y0 + FT * it;
+                e.Lp = a.Lp;
+                e.xw = xw;
+                e.row_wrap = a.row_wrap;
+                e.mu = mu;
+                e.nc2 = -1.4426950408889634f / (2.f * sg * sg);   // growth = 2 exp(-(u-mu)^2 / (2 sigma^2)) - 1  (lenia.py:423-426)
+                e.w2 = 2.f * wt;
+                e.wn = -wt;
+                e.dt = a.dt;
+                const bool euler = a.final_src && lenia;
+                if (SINGLE) {
+                    if (euler) { if (edge) epilogue<true, false, true>(e); else epilogue<false, false, true>(e); }
+                    else { if (edge) epilogue<true, false, false>(e); else epilogue<false, false, false>(e); }
+                } else if (a.acc_in) {
+                    if (euler) { if (edge) epilogue<true, true, true>(e); else epilogue<false, true, true>(e); }
+                    else { if (edge) epilogue<true, true, false>(e); else epilogue<false, true, false>(e); }
+                } else {
+                    if (euler) { if (edge) epilogue<true, false, true>(e); else epilogue<false, false, true>(e); }
+                    else { if (edge) epilogue<true, false, false>(e); else epilogue<false, false, false>(e); }
+                }
+            }
+        }
+    }
+}
+
+// Tap table: kf[pair][dy][f] = (Khat[dy][k0(f)], Khat[dy][k1(f)]),  Khat[dy][k] = (1/N) sum_dx K[R+dy][R+dx] cos(2 pi k dx / N)
+// with the FIR thread's two frequencies  ka = f >> 3, j = (f & 7) ^ (ka & 7), k0 = ka + 32 j, k1 = k0 + 16.
+__global__ void march_prepare_kernel(const float *__restrict__ K, float2 *__restrict__ kf, int nker, int ks, int *__restrict__ asym_flag) {
+    const int ker = blockIdx.y;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= ROW4 || ker >= nker) return;
+    const int ka = f >> 3, j = (f & 7) ^ (ka & 7);
+    const int k0 = ka + 32 * j, k1 = k0 + 16;
+    const int off = (2 * R + 1 - ks) / 2;
+    const float *kk = K + (size_t)ker * ks * ks;
+    for (int dy = 0; dy < KROWS; ++dy) {
+        double a0 = 0.0, a1 = 0.0;
+        const int rp = R + dy - off, rm = R - dy - off;
+        if (rp >= 0 && rp < ks && rm >= 0) {
+            for (int c = 0; c < ks; ++c) {
+                const int dx = c + off - R;
+                const double up = kk[rp * ks + c], um = kk[rm * ks + c], mir = kk[rp * ks + (ks - 1 - c)];
+                if (fabs(up - um) > 1e-6 * fmax(fabs(up), fabs(um)) + 1e-12 || fabs(up - mir) > 1e-6 * fmax(fabs(up), fabs(mir)) + 1e-12)
+                    atomicExch(asym_flag, 1);
+                const double s = 0.5 * (up + um);
+                a0 += s * cospi(2.0 * (double)(((long long)k0 * dx % N + N) % N) / (double)N);
+                a1 += s * cospi(2.0 * (double)(((long long)k1 * dx % N + N) % N) / (double)N);
+            }
+        }
+        kf[((size_t)ker * KROWS + dy) * ROW4 + f] = make_float2((float)(a0 / N), (float)(a1 / N));
+    }
+}
+
+// row pairs per band: tall bands amortise the 32 extra forward transforms; small worlds trade that for enough CTAs
+static int choose_lp(int H, int W, int B, int C) {
+    const long long strips = ceil_div(W, V);
+    const long long slots = 2LL * num_sms();
+    int best = FT;
+    double best_cost = 1e30;
+    for (int lp = 128; lp >= FT; lp >>= 1) {
+        const long long ctas = strips * ceil_div(H, 2 * lp) * B;
+        const double waves = (double)ceil_div64(ctas, slots);
+        // per CTA: lp + 32 forward transforms, lp x C x (FIR + inverse + epilogue ~ 2.5 forward transforms each)
+        const double cost = waves * ((lp + 32) + 2.5 * C * lp);
+        if (cost < best_cost * 0.97) {
+            best_cost = cost;
+            best = lp;
+        }
+    }
+    return best;
+}
+
+}  // namespace march
+}  // namespace b200ca
+
+using namespace b200ca;
+
+extern "C" int b200ca_lenia_march_supported(int H, int W) { return (H >= 2 * march::F && W >= 2 * march::F) ? 1 : 0; }
+
+extern "C" int64_t b200ca_lenia_march_kernel_elems(int B, int C, int k_mult) {
+    return (int64_t)B * C * k_mult * C * march::KROWS * march::ROW4 * 2;
+}
+
+extern "C" int b200ca_lenia_march_band_rows(int H, int W, int B, int C) { return 2 * march::choose_lp(H, W, B, C); }
+
+extern "C" int b200ca_lenia_march_prepare_kernel(const float *K, float *Kf, int B, int C, int k_mult, int ks, void *stream) {
+    B200CA_REQUIRE(K && Kf && B >= 1 && C >= 1 && k_mult >= 1, "lenia_march_prepare_kernel: bad arguments");
+    if (ks < 1 || ks > 2 * march::R + 1 || (ks % 2) == 0) {
+        set_error("lenia_march_prepare_kernel: k_size %d not supported (odd, <= 31)", ks);
+        return B200CA_E_UNSUPPORTED;
+    }
+    cudaStream_t st = as_stream(stream);
+    int *flag = nullptr;
+    B200CA_CUDA(cudaMalloc(&flag, sizeof(int)));
+    int h_flag = 0;
+    int rc = check_cuda(cudaMemsetAsync(flag, 0, sizeof(int), st), "memset");
+    if (!rc) {
+        const int nker = B * C * k_mult * C;
+        dim3 grid(1, nker);
+        march::march_prepare_kernel<<<grid, march::ROW4, 0, st>>>(K, reinterpret_cast<float2 *>(Kf), nker, ks, flag);
+        rc = check_cuda(cudaPeekAtLastError(), "march_prepare_kernel");
+    }
+    if (!rc) rc = check_cuda(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st), "D2H flag");
+    if (!rc) rc = check_cuda(cudaStreamSynchronize(st), "sync");
+    cudaFree(flag);
+    if (rc) return rc;
+    if (h_flag) {
+        set_error("lenia_march_prepare_kernel: kernel rows are not symmetric (the FFT path needs K[dy][dx]==K[-dy][dx]==K[dy][-dx])");
+        return B200CA_E_UNSUPPORTED;
+    }
+    return 0;
+}
+
+extern "C" int b200ca_lenia_step_march(const float *state_in, float *state_out, const float *Kf, const float *mu, const float *sigma,
+                                       const float *weights, int B, int C, int k_mult, int H, int W, float dt, int mode, int row_wrap,
+                                       int band_begin, int band_end, void *stream) {
+    B200CA_REQUIRE(state_in && state_out && Kf && mu && sigma && weights, "lenia_step_march: null pointer");
+    B200CA_REQUIRE(state_in != state_out, "lenia_step_march: in-place update is not supported");
+    B200CA_REQUIRE(mode == B200CA_MODE_LENIA || mode == B200CA_MODE_AFF, "lenia_step_march: bad mode %d", mode);
+    B200CA_REQUIRE(B >= 1 && B <= 65535 && C >= 1 && k_mult >= 1, "lenia_step_march: bad B/C/k_mult");
+    if (!b200ca_lenia_march_supported(H, W)) {
+        set_error("lenia_step_march: world %dx%d not supported (H, W >= 32)", H, W);
+        return B200CA_E_UNSUPPORTED;
+    }
+    cudaStream_t st = as_stream(stream);
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    B200CA_CUDA(cudaGetDevice(&dev));
+    if (!attr_done[dev & 63]) {
+        B200CA_CUDA(cudaFuncSetAttribute(march::lenia_march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march::SMEM));
+        B200CA_CUDA(cudaFuncSetAttribute(march::lenia_march_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march::SMEM));
+        attr_done[dev & 63] = true;
+    }
+    march::Args a;
+    a.state_in = state_in;
+    a.out = state_out;
+    a.kf = reinterpret_cast<const float2 *>(Kf);
+    a.mu = mu;
+    a.sigma = sigma;
+    a.weights = weights;
+    a.B = B;
+    a.C = C;
+    a.NS = C * k_mult;
+    a.k_mult = k_mult;
+    a.H = H;
+    a.W = W;
+    a.pitch = b200ca_frame_pitch(W);
+    a.Lp = march::choose_lp(H, W, B, C);
+    a.niter = a.Lp / march::FT;
+    a.dt = dt;
+    a.mode = mode;
+    a.row_wrap = row_wrap;
+    const int nbands = ceil_div(H, 2 * a.Lp);
+    if (band_begin == 0 && band_end == 0) band_end = nbands;
+    B200CA_REQUIRE(band_begin >= 0 && band_end <= nbands && band_begin <= band_end, "lenia_step_march: band range [%d,%d) outside [0,%d)",
+                   band_begin, band_end, nbands);
+    if (band_begin == band_end) return 0;
+    a.band0 = band_begin;
+    dim3 grid(ceil_div(W, march::V), band_end - band_begin, B);
+    for (int s = 0; s < a.NS; ++s) {
+        a.src = s;
+        a.acc_in = s > 0;
+        a.final_src = s == a.NS - 1;
+        if (C == 1) B200CA_CUDA(launch_pdl(march::lenia_march_kernel<true>, grid, dim3(march::THREADS), march::SMEM, st, a));
+        else B200CA_CUDA(launch_pdl(march::lenia_march_kernel<false>, grid, dim3(march::THREADS), march::SMEM, st, a));
+    }
+    B200CA_LAUNCH_CHECK("lenia_march_kernel");
+    note_variant("lenia_march<%s,Lp=%d>x%d", C == 1 ? "single" : "multi", a.Lp, a.NS);
+    return 0;
+}

@@ -134,8 +134,9 @@ class Lenia(Automaton):
 
     def __init__(self, size, dt=0.1, num_channels=3, params=None, state_init=None, device="cuda",
                  interest_files=None, save_dir=".", conv_path="auto"):
-        """conv_path: 'direct' (TMA-tiled folded spatial convolution), 'fft' (row-FFT x column-direct hybrid) or
-        'auto' (fft when the world shape supports it, else direct)."""
+        """conv_path: 'direct' (TMA-tiled folded spatial convolution), 'fft' (marching row-FFT x column-FIR kernel),
+        'fft_rows' (the two-kernel row-FFT + fused FIR/inverse hybrid) or 'auto' (fft when the world shape supports it, else
+        direct)."""
         self.conv_path = conv_path
         if len(size) == 2:
             size = (1,) + tuple(size)
@@ -244,13 +245,28 @@ class Lenia(Automaton):
         with _lib.device_guard(self.device):
             _lib.call("b200ca_lenia_prepare_kernel", _lib.ptr(self.k), _lib.ptr(self._kprep), self.batch, self.C, self.k_mult,
                       int(self.k_size), _lib.current_stream(self.device))
-        # FFT path (optional): prepared kernel spectra + row-spectra workspace
-        self._kfft = self._fft_ws = None
-        fft_ok = L.b200ca_lenia_fft_length(self.h, self.w) > 0
-        if self.conv_path == "fft" and not fft_ok:
-            raise _lib.B200CAError(f"conv_path='fft' is not supported for a {self.h}x{self.w} world (H even >= 32, W >= 64)")
-        self.use_fft = fft_ok and self.conv_path in ("fft", "auto") and not self.g_arbi  # Fourier growth: direct path only
-        if self.use_fft:
+        # FFT paths: "fft" = the marching kernel (lenia_march.cu: one kernel, spectra stay in shared memory; every world with
+        # H, W >= 32), "fft_rows" = the row-FFT + fused FIR/inverse hybrid (lenia_fft.cu: H even, W >= 64; kept for A/B runs
+        # and for the phase-split row slabs); "auto" = marching kernel when supported, else direct.
+        self._kfft = self._fft_ws = self._kmarch = None
+        march_ok = L.b200ca_lenia_march_supported(self.h, self.w) > 0 and not self.g_arbi  # Fourier growth: direct path only
+        rows_ok = L.b200ca_lenia_fft_length(self.h, self.w) > 0 and not self.g_arbi
+        if self.conv_path not in ("auto", "direct", "fft", "fft_rows"):
+            raise _lib.B200CAError(f"conv_path must be 'auto', 'direct', 'fft' or 'fft_rows' (got {self.conv_path!r})")
+        if self.conv_path == "fft" and not march_ok:
+            raise _lib.B200CAError(f"conv_path='fft' is not supported for a {self.h}x{self.w} world (H, W >= 32, Gaussian growth)")
+        if self.conv_path == "fft_rows" and not rows_ok:
+            raise _lib.B200CAError(f"conv_path='fft_rows' is not supported for a {self.h}x{self.w} world (H even >= 32, W >= 64)")
+        self.conv_algo = {"auto": "march" if march_ok else "direct", "fft": "march", "fft_rows": "fft_rows",
+                          "direct": "direct"}[self.conv_path]
+        self.use_fft = self.conv_algo != "direct"
+        if self.conv_algo == "march":
+            self._kmarch = torch.empty(L.b200ca_lenia_march_kernel_elems(self.batch, self.C, self.k_mult), dtype=torch.float32,
+                                       device=self.device)
+            with _lib.device_guard(self.device):
+                _lib.call("b200ca_lenia_march_prepare_kernel", _lib.ptr(self.k), _lib.ptr(self._kmarch), self.batch, self.C, self.k_mult,
+                          int(self.k_size), _lib.current_stream(self.device))
+        elif self.conv_algo == "fft_rows":
             self._kfft = torch.empty(L.b200ca_lenia_fft_kernel_elems(self.batch, self.C, self.k_mult, self.h, self.w),
                                      dtype=torch.float32, device=self.device)
             with _lib.device_guard(self.device):
@@ -265,7 +281,11 @@ class Lenia(Automaton):
         with _lib.device_guard(fs.device):
             if self._garbi is not None:
                 conv_garbi(fs, dst, self._kprep, self.weights, self._garbi, self.k_mult, self.dt, mode)
-            elif self.use_fft:
+            elif self.conv_algo == "march":
+                _lib.call("b200ca_lenia_step_march", _lib.ptr(fs.buf), _lib.ptr(dst), _lib.ptr(self._kmarch), _lib.ptr(self.mu),
+                          _lib.ptr(self.sigma), _lib.ptr(self.weights), fs.B, fs.C, self.k_mult, fs.H, fs.W, float(self.dt), mode, 1,
+                          0, 0, _lib.current_stream(fs.device))
+            elif self.conv_algo == "fft_rows":
                 _lib.call("b200ca_lenia_step_fft", _lib.ptr(fs.buf), _lib.ptr(dst), _lib.ptr(self._kfft), _lib.ptr(self.mu),
                           _lib.ptr(self.sigma), _lib.ptr(self.weights), _lib.ptr(self._fft_ws), fs.B, fs.C, self.k_mult, fs.H, fs.W,
                           float(self.dt), mode, 1, _lib.current_stream(fs.device))

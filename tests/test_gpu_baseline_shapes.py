@@ -70,7 +70,7 @@ def tiles_err(big, ref_tile):
     return (v - r).abs().max().item()
 
 
-@pytest.mark.parametrize("path", ["fft", "direct"])
+@pytest.mark.parametrize("path", ["fft", "fft_rows", "direct"])
 @pytest.mark.parametrize("C", [1, 3])
 def test_lenia_1k_vs_oracle(C, path):
     """BASELINE configs[1] (C=1) and the unsliced C=3 case, 1024x1024, one step, both convolution paths."""

@@ -18,7 +18,7 @@ def _params(name):
     return pyca_b200.LeniaParams(param_dict=d), p
 
 
-@pytest.mark.parametrize("path", ["fft", "direct"])
+@pytest.mark.parametrize("path", ["fft", "fft_rows", "direct"])
 def test_flow_lenia_golden(path):
     import pyca_b200
 
@@ -30,7 +30,7 @@ def test_flow_lenia_golden(path):
         dt, dd, srt, thx, n = [float(v) for v in fx[f"c{ci}_meta"]]
         a = pyca_b200.FlowLenia((H, W), dt=dt, params=params, state_init=s0, device="cuda", dd=int(dd), sigma_rt=srt,
                                 conv_path=path)
-        assert a.use_fft == (path == "fft")
+        assert a.use_fft == (path != "direct")
         i = 1
         while f"c{ci}_state{i}" in fx:
             a.step()

@@ -26,7 +26,7 @@ def sliced(d, c):
     return {k: (v[:, :c, :c].clone() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
 
 
-PATHS = ["direct", "fft"]
+PATHS = ["direct", "fft", "fft_rows"]   # direct conv, marching FFT kernel (default), row-FFT + fused FIR/inverse hybrid
 
 
 @pytest.mark.parametrize("path", PATHS)
@@ -38,7 +38,7 @@ def test_lenia_golden(name, path):
     s0 = t(fx["state_in"])
     a = pyca_b200.Lenia(tuple(s0.shape[2:]), dt=float(fx["dt"]), params=params_dict(p), state_init=s0, device="cuda",
                         conv_path=path)
-    assert a.use_fft == (path == "fft")
+    assert a.use_fft == (path != "direct") and a.conv_algo == {"direct": "direct", "fft": "march", "fft_rows": "fft_rows"}[path]
     assert torch.allclose(a.k.cpu(), t(p["K"]), atol=1e-8), "host kernel construction differs from the reference's"
     a.step()
     err = (a.state.cpu() - t(fx["state_out"])).abs().max().item()
@@ -98,13 +98,14 @@ def _oracle_params(name="abominable_mongolic", tag="lenia"):
 
 @pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("shape", [(32, 32), (50, 70), (64, 64), (65, 129), (100, 47), (31 + 1, 200), (256, 256), (34, 500),
-                                   (96, 1024), (40, 1100)])
+                                   (96, 1024), (40, 1100), (48, 224), (49, 225), (40, 448), (33, 449), (131, 300), (600, 260),
+                                   (1030, 96)])
 def test_lenia_odd_shapes_vs_oracle(shape, path):
     """Tile overhang, partial strips, worlds narrower than a tile; FFT path: periodic (W = 256, 1024) and overlap-save
     segments (one, several, partial last)."""
     import pyca_b200
 
-    if path == "fft" and pyca_b200.lib().b200ca_lenia_fft_length(*shape) == 0:
+    if path == "fft_rows" and pyca_b200.lib().b200ca_lenia_fft_length(*shape) == 0:
         pytest.skip("shape not supported by the FFT path")
     d, K, mu, sg, w = _oracle_params()
     g = torch.Generator().manual_seed(shape[0] * 1000 + shape[1])
