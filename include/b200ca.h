@@ -161,6 +161,12 @@ int b200ca_lenia_step_fft_phase(const float *state_in, float *state_out, const f
  *   b200ca_lenia_march_prepare_kernel K (B, C*k_mult, C, ks, ks) -> tap table (cold path, update_params)
  *   b200ca_lenia_march_band_rows      image rows per band for this shape; band_begin/band_end of the step restrict a launch
  *                                     to bands [begin, end) (0,0 = all) so that a row slab can issue its boundary bands first */
+#define B200CA_ALGO_DIRECT 0
+#define B200CA_ALGO_FFT_ROWS 1
+#define B200CA_ALGO_MARCH 2
+/* which of the three convolution paths conv_path='auto' takes for B worlds of HxW with NS = C*k_mult source kernels per
+ * destination plane (a rule fitted to B200 measurements; Gaussian growth -- Fourier growth functions are direct-only) */
+int b200ca_lenia_pick_algo(int B, int NS, int H, int W);
 int b200ca_lenia_march_supported(int H, int W);
 int64_t b200ca_lenia_march_kernel_elems(int B, int C, int k_mult);
 int b200ca_lenia_march_prepare_kernel(const float *K, float *Kf, int B, int C, int k_mult, int ks, void *stream);

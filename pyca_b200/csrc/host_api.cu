@@ -58,7 +58,8 @@ struct Lane {
 struct Pipe {
     int dev = 0, B = 0, C = 0, km = 0, H = 0, W = 0, family = 0, depth = 0, next = 0;
     float dt = 0.f, beta = 0.f, alpha = 0.f;
-    bool fft = false;
+    bool fft = false;   // the two-kernel hybrid (needs a workspace per lane)
+    int algo = 0;       // B200CA_ALGO_*
     size_t dbytes = 0;
     float *kprep = nullptr, *kfft = nullptr, *mu = nullptr, *sigma = nullptr, *weights = nullptr;
     Lane *lanes = nullptr;
@@ -108,6 +109,9 @@ int pipe_build(Pipe *p, const float *K, const float *mu, const float *sigma, con
         if (p->fft) {
             rc = check_cuda(cudaMalloc(&p->kfft, (size_t)b200ca_lenia_fft_kernel_elems(B, C, km, H, W) * sizeof(float)), "cudaMalloc");
             if (!rc) rc = b200ca_lenia_fft_prepare_kernel(dK, p->kfft, B, C, km, ks, H, W, nullptr);
+        } else if (p->algo == B200CA_ALGO_MARCH) {
+            rc = check_cuda(cudaMalloc(&p->kfft, (size_t)b200ca_lenia_march_kernel_elems(B, C, km) * sizeof(float)), "cudaMalloc");
+            if (!rc) rc = b200ca_lenia_march_prepare_kernel(dK, p->kfft, B, C, km, ks, nullptr);
         } else {
             rc = check_cuda(cudaMalloc(&p->kprep, (size_t)b200ca_lenia_kprep_elems(B, C, km) * sizeof(float)), "cudaMalloc");
             if (!rc) rc = b200ca_lenia_prepare_kernel(dK, p->kprep, B, C, km, ks, nullptr);
@@ -152,7 +156,8 @@ extern "C" int b200ca_lenia_pipe_create(void **pipe, const float *K, const float
     p->dev = dev;
     p->B = B, p->C = C, p->km = k_mult, p->H = H, p->W = W, p->family = family, p->depth = depth;
     p->dt = dt, p->beta = beta, p->alpha = alpha;
-    p->fft = b200ca_lenia_fft_length(H, W) > 0;
+    p->algo = b200ca_lenia_pick_algo(B, C * k_mult, H, W);
+    p->fft = p->algo == B200CA_ALGO_FFT_ROWS;
     p->dbytes = (size_t)B * C * H * W * sizeof(float);
     const int rc = pipe_build(p, K, mu, sigma, weights, ks);
     if (rc) {
@@ -182,6 +187,8 @@ extern "C" int b200ca_lenia_pipe_submit(void *pipe, const float *h_state_in, flo
         float *conv_out = p->family == 0 ? dst : l.aff;
         const int mode = p->family == 0 ? B200CA_MODE_LENIA : B200CA_MODE_AFF;
         rc = p->fft ? b200ca_lenia_step_fft(src, conv_out, p->kfft, p->mu, p->sigma, p->weights, l.ws, B, C, km, H, W, p->dt, mode, 1, l.st)
+             : p->algo == B200CA_ALGO_MARCH
+                 ? b200ca_lenia_step_march(src, conv_out, p->kfft, p->mu, p->sigma, p->weights, B, C, km, H, W, p->dt, mode, 1, 0, 0, l.st)
                     : b200ca_lenia_step(src, conv_out, p->kprep, p->mu, p->sigma, p->weights, B, C, km, H, W, p->dt, mode, 1, 0, 0, l.st);
         if (!rc && p->family > 0)
             rc = b200ca_mace_redistribute(src, l.aff, dst, B, C, H, W, p->beta, p->family == 2, p->alpha, 1, l.st);

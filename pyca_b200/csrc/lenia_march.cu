@@ -20,6 +20,23 @@
 // tools/march_proto.py is the numpy model of the index arithmetic below.
 #include "common.cuh"
 
+// A/B switches of the developer builds (tools/march_ab.sh); the defaults are what ships
+#ifndef MARCH_PACKED_MUL
+#define MARCH_PACKED_MUL 0   // complex x constant as FMUL2 + FFMA2 on a swapped pair (0: four scalar instructions)
+#endif
+#ifndef MARCH_PACKED_ROT
+#define MARCH_PACKED_ROT 0   // the +-i legs of the radix-4 butterfly as FFMA2 on a swapped pair (0: four scalar adds)
+#endif
+#ifndef MARCH_PREFETCH
+#define MARCH_PREFETCH 0     // forward-row loads issued before the FIR, Euler operands before the transforms
+#endif
+#ifndef MARCH_MAXLP
+#define MARCH_MAXLP 128      // rows pairs per band at most (taller bands: fewer redundant forward transforms, but too few CTAs)
+#endif
+#ifndef MARCH_FORCELP
+#define MARCH_FORCELP 0      // != 0: fixed band height (A/B runs)
+#endif
+
 namespace b200ca {
 
 namespace march {
@@ -33,9 +50,15 @@ constexpr int V = N - 2 * HALO;   // valid outputs per strip
 constexpr int FT = 8;             // row pairs per iteration
 constexpr int NBLK = 5;           // ring blocks of FT rows: 40 rows >= FT + 2R
 constexpr int RING = NBLK * FT;
-constexpr int ROW4 = N / 2;       // float4 per spectra row
+constexpr int ROW4 = N / 2;       // float4 of a spectra row (tap-table stride)
+// Shared-memory rows are PADDED so that every access is base + immediate offset (an XOR swizzle costs two integer
+// instructions per access -- 27 % of the kernel's instructions in the first version):
+//   slot layout      float4 index 9*ka + j        (lane ka's 8 frequency pairs; quarter-warp conflict free)
+//   exchange layout  float2 index 17*t + r        (16 x 16 transpose between the two 16-point stages)
+//   sample layout    float2 index n               (inverse output: (row a, row b) of sample n)
+constexpr int ROWP4 = 144;        // float4 per padded row (2304 B >= 16*17 float2)
 constexpr int THREADS = 256;
-constexpr size_t SMEM = (size_t)(RING + FT) * ROW4 * sizeof(float4) + 256 * sizeof(float2);
+constexpr size_t SMEM = (size_t)(RING + FT) * ROWP4 * sizeof(float4) + 16 * 17 * sizeof(float2);
 
 struct Args {
     const float *state_in;
@@ -52,26 +75,41 @@ struct Args {
     int mode, row_wrap;
 };
 
+// Every fp32 instruction with three register operands -- scalar or packed -- occupies the FMA pipe for two cycles per warp
+// (ncu: pipe time = 2 x the fp instruction count), so the transforms are written in PACKED fp32x2 form throughout: a complex
+// number is one register pair, an add / real-scale / multiply-accumulate is one FADD2 / FMUL2 / FFMA2.  Products with i
+// need the swapped pair (a.y, a.x): two MOVs on the ALU pipe, which has room.
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
-// a - b as ONE packed instruction (FADD2 has no negate modifier: a packed subtract written as an add costs two sign flips)
+// a - b as ONE packed instruction (FADD2 has no negate modifier)
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
-// a * (c + i s)
-__device__ __forceinline__ float2 cmul_cs(float2 a, float c, float s) { return make_float2(a.x * c - a.y * s, a.x * s + a.y * c); }
+__device__ __forceinline__ float2 cswap(float2 a) { return make_float2(a.y, a.x); }
+// a * (c + i s) = a * (c, c) + (a.y, a.x) * (-s, s)
+__device__ __forceinline__ float2 cmul_cs(float2 a, float c, float s) {
+#if MARCH_PACKED_MUL
+    return __ffma2_rn(cswap(a), make_float2(-s, s), __fmul2_rn(a, make_float2(c, c)));
+#else
+    return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+#endif
+}
 
 // 4-point DFT, natural order in and out; INV: e^{+i...}
 template <bool INV>
 __device__ __forceinline__ void dft4(float2 &a, float2 &b, float2 &c, float2 &d) {
+    // t1 +- (b-d) * (-+i) = t1 +- (bd.y, -bd.x)  (forward)
+    constexpr float S = INV ? -1.f : 1.f;
+#if MARCH_PACKED_ROT
+    const float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), bd = cswap(csub(b, d));
+    a = cadd(t0, t2);
+    c = csub(t0, t2);
+    b = __ffma2_rn(bd, make_float2(S, -S), t1);
+    d = __ffma2_rn(bd, make_float2(-S, S), t1);
+#else
     const float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), bd = csub(b, d);
     a = cadd(t0, t2);
     c = csub(t0, t2);
-    // t1 +- (b-d) * (-+i): scalar adds (a packed form would need the pair (bd.y, bd.x) swapped first)
-    if (INV) {
-        b = make_float2(t1.x - bd.y, t1.y + bd.x);
-        d = make_float2(t1.x + bd.y, t1.y - bd.x);
-    } else {
-        b = make_float2(t1.x + bd.y, t1.y - bd.x);
-        d = make_float2(t1.x - bd.y, t1.y + bd.x);
-    }
+    b = make_float2(t1.x + S * bd.y, t1.y - S * bd.x);
+    d = make_float2(t1.x - S * bd.y, t1.y + S * bd.x);
+#endif
 }
 
 // 16-point DFT on registers, natural order in and out (two radix-4 stages, constants as immediates).
@@ -87,7 +125,11 @@ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
     v[1 + 8] = cmul_cs(v[1 + 8], C2, SG * C2);
     v[1 + 12] = cmul_cs(v[1 + 12], S1, SG * C1);
     v[2 + 4] = cmul_cs(v[2 + 4], C2, SG * C2);
+#if MARCH_PACKED_MUL
+    v[2 + 8] = __fmul2_rn(cswap(v[2 + 8]), make_float2(-SG, SG));  // * (-+i)
+#else
     v[2 + 8] = INV ? make_float2(-v[2 + 8].y, v[2 + 8].x) : make_float2(v[2 + 8].y, -v[2 + 8].x);
+#endif
     v[2 + 12] = cmul_cs(v[2 + 12], -C2, SG * C2);
     v[3 + 4] = cmul_cs(v[3 + 4], S1, SG * C1);
     v[3 + 8] = cmul_cs(v[3 + 8], -C2, SG * C2);
@@ -106,11 +148,10 @@ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
 }
 
 // One forward transform by a 16-lane group (lane t): image rows `ra` (re) and `rb` (im), 256 samples from framed column
-// `col0` on; the spectrum goes to `row4` in slot layout: float4 index ka*8 + (j ^ (ka & 7)) = (re, re', im, im') of the
+// `col0` on; the spectrum goes to `row4` in slot layout: float4 index 9*ka + j = (re, re', im, im') of the
 // frequencies ka + 16*(2j), ka + 16*(2j+1).  The 16 x 16 exchange runs in place in the destination row.
-__device__ __forceinline__ void forward_row(const float *__restrict__ ra, const float *__restrict__ rb, int col0, int pitch, float4 *row4,
-                                            const float2 *tw, int t) {
-    float2 v[16];
+__device__ __forceinline__ void forward_load(const float *__restrict__ ra, const float *__restrict__ rb, int col0, int pitch, int t,
+                                             float2 (&v)[16]) {
     ra += col0 + t;
     rb += col0 + t;
     if (col0 + N <= pitch) {  // every strip but the last: plain loads at immediate offsets
@@ -123,22 +164,25 @@ __device__ __forceinline__ void forward_row(const float *__restrict__ ra, const 
             v[q] = make_float2(ok ? __ldg(ra + 16 * q) : 0.f, ok ? __ldg(rb + 16 * q) : 0.f);
         }
     }
+}
+
+__device__ __forceinline__ void forward_compute(float2 (&v)[16], float4 *row4, const float2 *tw, int t) {
     dft16<false>(v);  // v[ka] = sum_q x[t + 16 q] W16^{q ka}
     float2 *row2 = reinterpret_cast<float2 *>(row4);
 #pragma unroll
     for (int ka = 1; ka < 16; ++ka) {
-        const float2 w = tw[16 * t + (ka ^ t)];  // W256^{t ka}
+        const float2 w = tw[17 * t + ka];  // W256^{t ka}
         v[ka] = cmul_cs(v[ka], w.x, w.y);
     }
 #pragma unroll
-    for (int ka = 0; ka < 16; ++ka) row2[16 * t + (ka ^ t)] = v[ka];
+    for (int ka = 0; ka < 16; ++ka) row2[17 * t + ka] = v[ka];
     __syncwarp();
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) v[n1] = row2[16 * n1 + (t ^ n1)];  // lane t now owns ka = t
+    for (int n1 = 0; n1 < 16; ++n1) v[n1] = row2[17 * n1 + t];  // lane t now owns ka = t
     __syncwarp();
     dft16<false>(v);  // v[kb] = X[t + 16 kb]
 #pragma unroll
-    for (int j = 0; j < 8; ++j) row4[8 * t + (j ^ (t & 7))] = make_float4(v[2 * j].x, v[2 * j + 1].x, v[2 * j].y, v[2 * j + 1].y);
+    for (int j = 0; j < 8; ++j) row4[9 * t + j] = make_float4(v[2 * j].x, v[2 * j + 1].x, v[2 * j].y, v[2 * j + 1].y);
 }
 
 // One inverse transform by a 16-lane group, in place: filtered spectrum (slot layout) -> float2 slot n = (out row a, out row b)
@@ -146,23 +190,23 @@ __device__ __forceinline__ void inverse_row(float4 *row4, const float2 *tw, int 
     float2 v[16];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float4 z = row4[8 * t + (j ^ (t & 7))];
+        const float4 z = row4[9 * t + j];
         v[2 * j] = make_float2(z.x, z.z);
         v[2 * j + 1] = make_float2(z.y, z.w);
     }
+    __syncwarp();    // every lane has its spectrum before the row is reused for the exchange
     dft16<true>(v);  // v[n1] = sum_kb Y[t + 16 kb] W16^{-n1 kb}
     float2 *row2 = reinterpret_cast<float2 *>(row4);
 #pragma unroll
     for (int n1 = 1; n1 < 16; ++n1) {
-        const float2 w = tw[16 * t + (n1 ^ t)];
+        const float2 w = tw[17 * t + n1];
         v[n1] = cmul_cs(v[n1], w.x, -w.y);  // conj(W256^{t n1})
     }
-    // (a lane's slot-layout float4s and its exchange slots are the same 128 bytes: no hazard with the other lanes' loads)
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) row2[16 * t + (n1 ^ t)] = v[n1];
+    for (int n1 = 0; n1 < 16; ++n1) row2[17 * t + n1] = v[n1];
     __syncwarp();
 #pragma unroll
-    for (int ka = 0; ka < 16; ++ka) v[ka] = row2[16 * ka + (t ^ ka)];  // lane t now owns n1 = t
+    for (int ka = 0; ka < 16; ++ka) v[ka] = row2[17 * ka + t];  // lane t now owns n1 = t
     __syncwarp();
     dft16<true>(v);  // v[n2] = y[t + 16 n2]
 #pragma unroll
@@ -199,7 +243,7 @@ __device__ __forceinline__ void fir_half(const float4 *const (&blk)[NBLK], const
         constexpr int unused = 0;
         (void)unused;
         const int row = 4 * H4 + rr;
-        const float4 z = blk[row / FT][(row % FT) * ROW4];
+        const float4 z = blk[row / FT][(row % FT) * ROWP4];
         const float2 zre = make_float2(z.x, z.y), zim = make_float2(z.z, z.w);
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
@@ -211,11 +255,11 @@ __device__ __forceinline__ void fir_half(const float4 *const (&blk)[NBLK], const
         }
     }
 #pragma unroll
-    for (int y = 0; y < 4; ++y) fout[y * ROW4] = make_float4(are[y].x, are[y].y, aim[y].x, aim[y].y);
+    for (int y = 0; y < 4; ++y) fout[y * ROWP4] = make_float4(are[y].x, are[y].y, aim[y].x, aim[y].y);
 }
 
 struct EpiArgs {
-    const float2 *u;       // this thread's sample of output pair 0 (stride N float2 per pair)
+    const float2 *u;       // this thread's sample of output pair 0 (stride 2*ROWP4 float2 per pair)
     const float *sa;       // state, row pair 0 (EULER)
     float *oa;             // output, row pair 0
     float *oplane;
@@ -224,50 +268,60 @@ struct EpiArgs {
     float mu, nc2, w2, wn, dt;   // growth(u) * weight = exp2((u - mu)^2 * nc2) * w2 + wn
 };
 
-// growth + weighted source sum (+ partial sums of earlier sources) (+ Euler step / clamp) and the stores of 8 row pairs.
-// EDGE = false: a CTA whose cells have no periodic images and whose rows all lie inside the world.
-template <bool EDGE, bool ACC, bool EULER>
-__device__ __forceinline__ void epilogue(const EpiArgs &e) {
-    float s0[FT], s1[FT], p0[FT], p1[FT];
-    // operands from global memory first, all in flight together
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// the Euler operands (state rows a and b of 8 row pairs), issued long before they are needed
+template <bool EDGE>
+__device__ __forceinline__ void epilogue_prefetch(const EpiArgs &e, float2 (&st)[FT]) {
 #pragma unroll
     for (int r = 0; r < FT; ++r) {
         const bool oka = !EDGE || e.ya0 + r < e.H, okb = !EDGE || e.ya0 + e.Lp + r < e.H;
-        if (EULER) {
-            s0[r] = oka ? __ldg(e.sa + (size_t)r * e.pitch) : 0.f;
-            s1[r] = okb ? __ldg(e.sa + e.half + (size_t)r * e.pitch) : 0.f;
-        }
-        if (ACC) {
-            p0[r] = oka ? e.oa[(size_t)r * e.pitch] : 0.f;
-            p1[r] = okb ? e.oa[e.half + (size_t)r * e.pitch] : 0.f;
+        st[r] = make_float2(oka ? __ldg(e.sa + (size_t)r * e.pitch) : 0.f, okb ? __ldg(e.sa + e.half + (size_t)r * e.pitch) : 0.f);
+    }
+}
+
+// growth + weighted source sum (+ partial sums of earlier sources) (+ Euler step / clamp) and the stores of 8 row pairs;
+// the two rows of a pair are the two halves of packed fp32x2 operations.
+// EDGE = false: a CTA whose cells have no periodic images and whose rows all lie inside the world.
+template <bool EDGE, bool ACC, bool EULER>
+__device__ __forceinline__ void epilogue(const EpiArgs &e, const float2 (&st)[FT]) {
+    float2 pv[FT];
+    if (ACC) {
+#pragma unroll
+        for (int r = 0; r < FT; ++r) {
+            const bool oka = !EDGE || e.ya0 + r < e.H, okb = !EDGE || e.ya0 + e.Lp + r < e.H;
+            pv[r] = make_float2(oka ? e.oa[(size_t)r * e.pitch] : 0.f, okb ? e.oa[e.half + (size_t)r * e.pitch] : 0.f);
         }
     }
+    const float2 nmu = make_float2(-e.mu, -e.mu), nc2 = make_float2(e.nc2, e.nc2), w2 = make_float2(e.w2, e.w2), wn = make_float2(e.wn, e.wn),
+                 dt2 = make_float2(e.dt, e.dt);
 #pragma unroll
     for (int r = 0; r < FT; ++r) {
-        const float2 u = e.u[r * N];
-        const float d0 = u.x - e.mu, d1 = u.y - e.mu;
-        float v0 = fmaf(exp2f(d0 * d0 * e.nc2), e.w2, e.wn), v1 = fmaf(exp2f(d1 * d1 * e.nc2), e.w2, e.wn);
-        if (ACC) {
-            v0 += p0[r];
-            v1 += p1[r];
-        }
+        const float2 d = __fadd2_rn(e.u[r * 2 * ROWP4], nmu);
+        const float2 q = __fmul2_rn(__fmul2_rn(d, d), nc2);
+        float2 v = __ffma2_rn(make_float2(ex2_approx(q.x), ex2_approx(q.y)), w2, wn);
+        if (ACC) v = __fadd2_rn(v, pv[r]);
         if (EULER) {
-            v0 = fminf(fmaxf(fmaf(e.dt, v0, s0[r]), 0.f), 1.f);
-            v1 = fminf(fmaxf(fmaf(e.dt, v1, s1[r]), 0.f), 1.f);
+            v = __ffma2_rn(dt2, v, st[r]);
+            v = make_float2(fminf(fmaxf(v.x, 0.f), 1.f), fminf(fmaxf(v.y, 0.f), 1.f));
         }
         if (!EDGE) {
-            e.oa[(size_t)r * e.pitch] = v0;
-            e.oa[e.half + (size_t)r * e.pitch] = v1;
+            e.oa[(size_t)r * e.pitch] = v.x;
+            e.oa[e.half + (size_t)r * e.pitch] = v.y;
         } else {
             const int ya = e.ya0 + r, yb = ya + e.Lp;
             const bool xe = (e.xw < F) || (e.xw >= e.W - F);
             if (ya < e.H) {
-                e.oa[(size_t)r * e.pitch] = v0;
-                if (xe || (e.row_wrap && (ya < F || ya >= e.H - F))) store_mirrors(e.oplane, e.H, e.W, e.pitch, ya, e.xw, v0, e.row_wrap != 0);
+                e.oa[(size_t)r * e.pitch] = v.x;
+                if (xe || (e.row_wrap && (ya < F || ya >= e.H - F))) store_mirrors(e.oplane, e.H, e.W, e.pitch, ya, e.xw, v.x, e.row_wrap != 0);
             }
             if (yb < e.H) {
-                e.oa[e.half + (size_t)r * e.pitch] = v1;
-                if (xe || (e.row_wrap && (yb < F || yb >= e.H - F))) store_mirrors(e.oplane, e.H, e.W, e.pitch, yb, e.xw, v1, e.row_wrap != 0);
+                e.oa[e.half + (size_t)r * e.pitch] = v.y;
+                if (xe || (e.row_wrap && (yb < F || yb >= e.H - F))) store_mirrors(e.oplane, e.H, e.W, e.pitch, yb, e.xw, v.y, e.row_wrap != 0);
             }
         }
     }
@@ -277,9 +331,9 @@ __device__ __forceinline__ void epilogue(const EpiArgs &e) {
 template <bool SINGLE>
 __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
     extern __shared__ __align__(16) float4 msm[];
-    float4 *ring = msm;                                  // RING rows of ROW4 float4
-    float4 *filt = msm + RING * ROW4;                    // FT rows: filtered spectra -> inverse exchange -> outputs
-    float2 *tw = reinterpret_cast<float2 *>(filt + FT * ROW4);  // W256^{t r} at [16 t + (r ^ t)]
+    float4 *ring = msm;                                  // RING rows of ROWP4 float4
+    float4 *filt = msm + RING * ROWP4;                   // FT rows: filtered spectra -> inverse exchange -> outputs
+    float2 *tw = reinterpret_cast<float2 *>(filt + FT * ROWP4);  // W256^{t r} at [17 t + r]
     const int tid = threadIdx.x, lane16 = tid & 15, grp = tid >> 4;  // 16 groups of 16 lanes
     const int strip = blockIdx.x, band = a.band0 + blockIdx.y, b = blockIdx.z;
     const int y0 = band * 2 * a.Lp;
@@ -294,9 +348,10 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
         const int t = tid >> 4, r = tid & 15;
         float sn, cs;
         sincospif(-2.f * (float)((t * r) & 255) / 256.f, &sn, &cs);
-        tw[16 * t + (r ^ t)] = make_float2(cs, sn);
+        tw[17 * t + r] = make_float2(cs, sn);
     }
     const int f = tid & 127, h = tid >> 7;
+    const int fslot = 9 * (f >> 3) + (f & 7);            // this FIR thread's float4 in a padded spectra row
     float2 kt[KROWS];
     const float2 *kf0 = a.kf + (size_t)((b * a.NS + a.src) * a.C) * KROWS * ROW4 + f;
 #pragma unroll
@@ -305,14 +360,17 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
     __syncthreads();          // twiddle table
 
     // spectra row z of the band <- image rows (y0 + z - R, y0 + Lp + z - R), clamped into the framed plane
-    auto forward_block = [&](int z, int g) {
+    auto forward_fetch = [&](int z, float2 (&v)[16]) {
         const int fa = min(y0 + z - R + F, max_frow), fb = min(y0 + a.Lp + z - R + F, max_frow);
-        forward_row(splane + (size_t)fa * a.pitch, splane + (size_t)fb * a.pitch, col0, a.pitch, ring + (z % RING) * ROW4, tw, lane16);
-        (void)g;
+        forward_load(splane + (size_t)fa * a.pitch, splane + (size_t)fb * a.pitch, col0, a.pitch, lane16, v);
     };
     // prologue: blocks 0..4 (40 rows) by all 16 groups
 #pragma unroll 1
-    for (int z = grp; z < RING; z += 16) forward_block(z, grp);
+    for (int z = grp; z < RING; z += 16) {
+        float2 v[16];
+        forward_fetch(z, v);
+        forward_compute(v, ring + (z % RING) * ROWP4, tw, lane16);
+    }
 
     const int xw = col0 - HALO + tid;                    // world column of this thread's sample n = tid (epilogue)
     const bool col_ok = tid >= HALO && tid < N - HALO && xw < a.W;
@@ -330,6 +388,14 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
 #pragma unroll
                 for (int dy = 0; dy < KROWS; ++dy) kt[dy] = __ldg(kfj + dy * ROW4);
             }
+            // the forward transform this group runs after the FIR (groups 8-15, last destination): its 32 loads are issued
+            // now and stay in flight behind the FIR
+            const bool do_fwd = grp >= FT && j == (SINGLE ? 0 : a.C - 1) && it + 1 < a.niter;
+            const int zf = FT * (it + NBLK) + (grp - FT);
+            float2 vf[16];
+#if MARCH_PREFETCH
+            if (do_fwd) forward_fetch(zf, vf);
+#endif
             __syncthreads();  // ring rows of this iteration are complete; the previous epilogue is done with `filt`
             // ---- FIR: output pairs 4h .. 4h+3 of this block from ring rows (8 it + 4h) .. (+33), two frequencies per thread
             {
@@ -337,53 +403,67 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
                 int bb = it % NBLK;
 #pragma unroll
                 for (int i = 0; i < NBLK; ++i) {
-                    blk[i] = ring + bb * FT * ROW4 + f;
+                    blk[i] = ring + bb * FT * ROWP4 + fslot;
                     bb = bb + 1 == NBLK ? 0 : bb + 1;
                 }
-                if (h == 0) fir_half<0>(blk, kt, filt + f);
-                else fir_half<1>(blk, kt, filt + 4 * ROW4 + f);
+                if (h == 0) fir_half<0>(blk, kt, filt + fslot);
+                else fir_half<1>(blk, kt, filt + 4 * ROWP4 + fslot);
             }
+            // Euler operands of the epilogue: in flight behind the transforms
+            const float mu = __ldg(a.mu + pidx), sg = __ldg(a.sigma + pidx), wt = __ldg(a.weights + pidx);
+            const size_t dplane = (size_t)(b * a.C + j) * plane_elems;
+            const size_t o0 = (size_t)(y0 + FT * it + F) * a.pitch + F + xw;
+            EpiArgs e;
+            e.u = reinterpret_cast<const float2 *>(filt) + tid;
+            e.sa = a.state_in + dplane + o0;
+            e.oplane = a.out + dplane;
+            e.oa = e.oplane + o0;
+            e.half = (long long)a.Lp * a.pitch;
+            e.pitch = a.pitch;
+            e.H = a.H;
+            e.W = a.W;
+            e.ya0 = y0 + FT * it;
+            e.Lp = a.Lp;
+            e.xw = xw;
+            e.row_wrap = a.row_wrap;
+            e.mu = mu;
+            e.nc2 = -1.4426950408889634f / (2.f * sg * sg);   // growth = 2 exp(-(u-mu)^2 / (2 sigma^2)) - 1  (lenia.py:423-426)
+            e.w2 = 2.f * wt;
+            e.wn = -wt;
+            e.dt = a.dt;
+            const bool euler = a.final_src && lenia;
+            float2 st[FT];
+#if MARCH_PREFETCH
+            if (col_ok && euler) {
+                if (edge) epilogue_prefetch<true>(e, st);
+                else epilogue_prefetch<false>(e, st);
+            }
+#endif
             __syncthreads();
             // ---- inverse transforms (groups 0-7) | forward transforms of the block needed next (groups 8-15, last destination)
             if (grp < FT) {
-                inverse_row(filt + grp * ROW4, tw, lane16);
-            } else if (j == (SINGLE ? 0 : a.C - 1) && it + 1 < a.niter) {
-                forward_block(FT * (it + NBLK) + (grp - FT), grp);
+                inverse_row(filt + grp * ROWP4, tw, lane16);
+            } else if (do_fwd) {
+#if !MARCH_PREFETCH
+                forward_fetch(zf, vf);
+#endif
+                forward_compute(vf, ring + (zf % RING) * ROWP4, tw, lane16);
             }
             __syncthreads();
+#if !MARCH_PREFETCH
+            if (col_ok && euler) {
+                if (edge) epilogue_prefetch<true>(e, st);
+                else epilogue_prefetch<false>(e, st);
+            }
+#endif
             // ---- epilogue: growth + weighted source sum (+ Euler / clamp), sample n = tid of the 8 row pairs
             if (col_ok) {
-                const float mu = __ldg(a.mu + pidx), sg = __ldg(a.sigma + pidx), wt = __ldg(a.weights + pidx);
-                const size_t dplane = (size_t)(b * a.C + j) * plane_elems;
-                const size_t o0 = (size_t)(y0 + FT * it + F) * a.pitch + F + xw;
-                EpiArgs e;
-                e.u = reinterpret_cast<const float2 *>(filt) + tid;
-                e.sa = a.state_in + dplane + o0;
-                e.oplane = a.out + dplane;
-                e.oa = e.oplane + o0;
-                e.half = (long long)a.Lp * a.pitch;
-                e.pitch = a.pitch;
-                e.H = a.H;
-                e.W = a.W;
-                e.ya0 = y0 + FT * it;
-                e.Lp = a.Lp;
-                e.xw = xw;
-                e.row_wrap = a.row_wrap;
-                e.mu = mu;
-                e.nc2 = -1.4426950408889634f / (2.f * sg * sg);   // growth = 2 exp(-(u-mu)^2 / (2 sigma^2)) - 1  (lenia.py:423-426)
-                e.w2 = 2.f * wt;
-                e.wn = -wt;
-                e.dt = a.dt;
-                const bool euler = a.final_src && lenia;
-                if (SINGLE) {
-                    if (euler) { if (edge) epilogue<true, false, true>(e); else epilogue<false, false, true>(e); }
-                    else { if (edge) epilogue<true, false, false>(e); else epilogue<false, false, false>(e); }
-                } else if (a.acc_in) {
-                    if (euler) { if (edge) epilogue<true, true, true>(e); else epilogue<false, true, true>(e); }
-                    else { if (edge) epilogue<true, true, false>(e); else epilogue<false, true, false>(e); }
+                if (SINGLE || !a.acc_in) {
+                    if (euler) { if (edge) epilogue<true, false, true>(e, st); else epilogue<false, false, true>(e, st); }
+                    else { if (edge) epilogue<true, false, false>(e, st); else epilogue<false, false, false>(e, st); }
                 } else {
-                    if (euler) { if (edge) epilogue<true, false, true>(e); else epilogue<false, false, true>(e); }
-                    else { if (edge) epilogue<true, false, false>(e); else epilogue<false, false, false>(e); }
+                    if (euler) { if (edge) epilogue<true, true, true>(e, st); else epilogue<false, true, true>(e, st); }
+                    else { if (edge) epilogue<true, true, false>(e, st); else epilogue<false, true, false>(e, st); }
                 }
             }
         }
@@ -391,12 +471,12 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
 }
 
 // Tap table: kf[pair][dy][f] = (Khat[dy][k0(f)], Khat[dy][k1(f)]),  Khat[dy][k] = (1/N) sum_dx K[R+dy][R+dx] cos(2 pi k dx / N)
-// with the FIR thread's two frequencies  ka = f >> 3, j = (f & 7) ^ (ka & 7), k0 = ka + 32 j, k1 = k0 + 16.
+// with the FIR thread's two frequencies  ka = f >> 3, j = f & 7, k0 = ka + 32 j, k1 = k0 + 16.
 __global__ void march_prepare_kernel(const float *__restrict__ K, float2 *__restrict__ kf, int nker, int ks, int *__restrict__ asym_flag) {
     const int ker = blockIdx.y;
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= ROW4 || ker >= nker) return;
-    const int ka = f >> 3, j = (f & 7) ^ (ka & 7);
+    const int ka = f >> 3, j = f & 7;
     const int k0 = ka + 32 * j, k1 = k0 + 16;
     const int off = (2 * R + 1 - ks) / 2;
     const float *kk = K + (size_t)ker * ks * ks;
@@ -422,9 +502,10 @@ __global__ void march_prepare_kernel(const float *__restrict__ K, float2 *__rest
 static int choose_lp(int H, int W, int B, int C) {
     const long long strips = ceil_div(W, V);
     const long long slots = 2LL * num_sms();
+    if (MARCH_FORCELP) return MARCH_FORCELP;
     int best = FT;
     double best_cost = 1e30;
-    for (int lp = 128; lp >= FT; lp >>= 1) {
+    for (int lp = MARCH_MAXLP; lp >= FT; lp >>= 1) {
         const long long ctas = strips * ceil_div(H, 2 * lp) * B;
         const double waves = (double)ceil_div64(ctas, slots);
         // per CTA: lp + 32 forward transforms, lp x C x (FIR + inverse + epilogue ~ 2.5 forward transforms each)
@@ -443,6 +524,22 @@ static int choose_lp(int H, int W, int B, int C) {
 using namespace b200ca;
 
 extern "C" int b200ca_lenia_march_supported(int H, int W) { return (H >= 2 * march::F && W >= 2 * march::F) ? 1 : 0; }
+
+// conv_path = 'auto' (profiles/r02_conv_paths.md has the measurements behind the rule):
+//   one source kernel per destination: the two-kernel hybrid for small worlds (a single wave of CTAs: shorter serial chain),
+//   the marching kernel otherwise;  several sources: the hybrid (its fused kernel sums the sources in registers; the marching
+//   kernel accumulates through the output planes, one launch per source);  whatever the preferred path cannot do falls to the
+//   next one, the direct convolution last.
+extern "C" int b200ca_lenia_pick_algo(int B, int NS, int H, int W) {
+    const bool march_ok = b200ca_lenia_march_supported(H, W) != 0, rows_ok = b200ca_lenia_fft_length(H, W) > 0;
+    const bool small = (long long)B * H * W <= 1536LL * 1536LL;
+    if (NS == 1) {
+        if (rows_ok && small) return B200CA_ALGO_FFT_ROWS;
+        return march_ok ? B200CA_ALGO_MARCH : (rows_ok ? B200CA_ALGO_FFT_ROWS : B200CA_ALGO_DIRECT);
+    }
+    if (rows_ok) return B200CA_ALGO_FFT_ROWS;
+    return march_ok ? B200CA_ALGO_MARCH : B200CA_ALGO_DIRECT;
+}
 
 extern "C" int64_t b200ca_lenia_march_kernel_elems(int B, int C, int k_mult) {
     return (int64_t)B * C * k_mult * C * march::KROWS * march::ROW4 * 2;

@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from .ca2d import PackedWorld
-from .lenia import FramedState, conv_garbi, garbi_tables
+from .lenia import FramedState, conv_garbi, garbi_tables, pick_conv_algo
 from .nca import NCAWeights, nca_step
 
 F = _lib.FRAME
@@ -110,14 +110,21 @@ class _LeniaEngine:
             self.kprep = torch.empty(self.L.b200ca_lenia_kprep_elems(fs.B, fs.C, self.k_mult), dtype=torch.float32, device=dev)
             _lib.call("b200ca_lenia_prepare_kernel", _lib.ptr(self.K), _lib.ptr(self.kprep), fs.B, fs.C, self.k_mult, ks,
                       _lib.current_stream(dev))
-            self.use_fft = self.L.b200ca_lenia_fft_length(fs.H, fs.W) > 0 and self.garbi is None
-            if self.use_fft:
+            rows_ok = self.L.b200ca_lenia_fft_length(fs.H, fs.W) > 0 and self.garbi is None
+            march_ok = self.L.b200ca_lenia_march_supported(fs.H, fs.W) > 0 and self.garbi is None
+            self.algo = "direct" if self.garbi is not None else pick_conv_algo(fs.B, fs.C * self.k_mult, fs.H, fs.W, march_ok, rows_ok)
+            self.use_fft = self.algo != "direct"
+            if self.algo == "fft_rows":
                 self.kfft = torch.empty(self.L.b200ca_lenia_fft_kernel_elems(fs.B, fs.C, self.k_mult, fs.H, fs.W), dtype=torch.float32,
                                         device=dev)
                 _lib.call("b200ca_lenia_fft_prepare_kernel", _lib.ptr(self.K), _lib.ptr(self.kfft), fs.B, fs.C, self.k_mult, ks,
                           fs.H, fs.W, _lib.current_stream(dev))
                 self.ws = torch.empty(self.L.b200ca_lenia_fft_workspace_elems(fs.B, fs.C, self.k_mult, fs.H, fs.W),
                                       dtype=torch.float32, device=dev)
+            elif self.algo == "march":
+                self.kmarch = torch.empty(self.L.b200ca_lenia_march_kernel_elems(fs.B, fs.C, self.k_mult), dtype=torch.float32, device=dev)
+                _lib.call("b200ca_lenia_march_prepare_kernel", _lib.ptr(self.K), _lib.ptr(self.kmarch), fs.B, fs.C, self.k_mult, ks,
+                          _lib.current_stream(dev))
         self.key = key
 
     def sync_state(self, owner):
@@ -130,7 +137,10 @@ class _LeniaEngine:
             st = _lib.current_stream(fs.device)
             if self.garbi is not None:
                 conv_garbi(fs, dst, self.kprep, self.weights, self.garbi, self.k_mult, dt, mode)
-            elif self.use_fft:
+            elif self.algo == "march":
+                _lib.call("b200ca_lenia_step_march", _lib.ptr(fs.buf), _lib.ptr(dst), _lib.ptr(self.kmarch), _lib.ptr(self.mu),
+                          _lib.ptr(self.sigma), _lib.ptr(self.weights), fs.B, fs.C, self.k_mult, fs.H, fs.W, float(dt), mode, 1, 0, 0, st)
+            elif self.algo == "fft_rows":
                 _lib.call("b200ca_lenia_step_fft", _lib.ptr(fs.buf), _lib.ptr(dst), _lib.ptr(self.kfft), _lib.ptr(self.mu),
                           _lib.ptr(self.sigma), _lib.ptr(self.weights), _lib.ptr(self.ws), fs.B, fs.C, self.k_mult, fs.H, fs.W,
                           float(dt), mode, 1, st)

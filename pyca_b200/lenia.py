@@ -51,6 +51,20 @@ def garbi_tables(p, B, C, k_mult):
             "stats": torch.zeros((n, 2), dtype=torch.float32, device=co.device)}
 
 
+def pick_conv_algo(B, NS, H, W, march_ok=True, rows_ok=True):
+    """conv_path='auto': which convolution kernel steps a (B, C, H, W) world with NS = C * k_mult source kernels per
+    destination.  Measured on B200 (profiles/r02_conv_paths.md; all paths agree with the oracle to <= 1e-5):
+      * one source (C = 1): the marching kernel (lenia_march.cu) wins from 4096^2 up (118 vs 140 us at 4096^2, 1.26 vs 1.58 ms
+        at 16384^2: the spectra never leave shared memory); at 1024^2 the whole world is a single wave of CTAs and the
+        two-kernel hybrid (lenia_fft.cu, 512-thread small-world variant) has the shorter serial chain: 19.6 vs 22.1 us;
+      * several sources: the hybrid's fused kernel keeps the per-destination sum over sources in registers, the marching kernel
+        accumulates it through the output planes, one launch per source (843 vs 932 us at 4096^2, C = 3);
+      * the direct convolution (lenia.cu) is FMA-bound at R = 15 and serves what the FFT paths do not (Fourier growth
+        functions, worlds narrower than 32)."""
+    del march_ok, rows_ok   # (the library applies the same support checks)
+    return ("direct", "fft_rows", "march")[_lib.lib().b200ca_lenia_pick_algo(int(B), int(NS), int(H), int(W))]
+
+
 def conv_garbi(fs, dst, kprep, weights, g, k_mult, dt, mode):
     """b200ca_lenia_step_garbi on a FramedState (direct path; two passes when the growth is globally rescaled)."""
     rs, cl = g["rescale"], g["clip"]
@@ -257,8 +271,8 @@ class Lenia(Automaton):
             raise _lib.B200CAError(f"conv_path='fft' is not supported for a {self.h}x{self.w} world (H, W >= 32, Gaussian growth)")
         if self.conv_path == "fft_rows" and not rows_ok:
             raise _lib.B200CAError(f"conv_path='fft_rows' is not supported for a {self.h}x{self.w} world (H even >= 32, W >= 64)")
-        self.conv_algo = {"auto": "march" if march_ok else "direct", "fft": "march", "fft_rows": "fft_rows",
-                          "direct": "direct"}[self.conv_path]
+        self.conv_algo = {"auto": pick_conv_algo(self.batch, self.C * self.k_mult, self.h, self.w, march_ok, rows_ok), "fft": "march",
+                          "fft_rows": "fft_rows", "direct": "direct"}[self.conv_path]
         self.use_fft = self.conv_algo != "direct"
         if self.conv_algo == "march":
             self._kmarch = torch.empty(L.b200ca_lenia_march_kernel_elems(self.batch, self.C, self.k_mult), dtype=torch.float32,

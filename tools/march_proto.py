@@ -1,6 +1,6 @@
 """numpy model of lenia_march_kernel's data flow (pyca_b200/csrc/lenia_march.cu): validates, on the CPU, the index
 arithmetic of the 16 x 16 register FFT (thread t, register q <-> sample t + 16 q), the slot layout of the spectra rows
-(float4 = two adjacent k_b of one k_a, swizzled), the tap table the FIR threads read, and the band-local row pairing
+(float4 = two adjacent k_b of one k_a), the tap table the FIR threads read, and the band-local row pairing
 (rows y0 + p and y0 + Lp + p ride in one complex transform) against a direct periodic correlation.
 
     python tools/march_proto.py
@@ -61,13 +61,13 @@ def inv256(Y):
 def slot_of(ka, kb):
     """float4 index and lane (0/1) inside the spectra row for frequency ka + 16 kb"""
     j = kb >> 1
-    return ka * 8 + (j ^ (ka & 7)), kb & 1
+    return ka * 8 + j, kb & 1      # (the shared-memory row pads this to 9 * ka + j)
 
 
 def freq_of_f(f):
     """the two frequencies FIR thread f (float4 index f) owns"""
     ka = f >> 3
-    j = (f & 7) ^ (ka & 7)
+    j = f & 7
     return ka + 16 * (2 * j), ka + 16 * (2 * j + 1)
 
 
