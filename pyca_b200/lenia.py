@@ -261,7 +261,7 @@ class Lenia(Automaton):
                       int(self.k_size), _lib.current_stream(self.device))
         # FFT paths: "fft" = the marching kernel (lenia_march.cu: one kernel, spectra stay in shared memory; every world with
         # H, W >= 32), "fft_rows" = the row-FFT + fused FIR/inverse hybrid (lenia_fft.cu: H even, W >= 64; kept for A/B runs
-        # and for the phase-split row slabs); "auto" = marching kernel when supported, else direct.
+        # and for the phase-split row slabs); "auto" = b200ca_lenia_pick_algo (a rule fitted to measurements).
         self._kfft = self._fft_ws = self._kmarch = None
         march_ok = L.b200ca_lenia_march_supported(self.h, self.w) > 0 and not self.g_arbi  # Fourier growth: direct path only
         rows_ok = L.b200ca_lenia_fft_length(self.h, self.w) > 0 and not self.g_arbi
@@ -271,8 +271,12 @@ class Lenia(Automaton):
             raise _lib.B200CAError(f"conv_path='fft' is not supported for a {self.h}x{self.w} world (H, W >= 32, Gaussian growth)")
         if self.conv_path == "fft_rows" and not rows_ok:
             raise _lib.B200CAError(f"conv_path='fft_rows' is not supported for a {self.h}x{self.w} world (H even >= 32, W >= 64)")
-        self.conv_algo = {"auto": pick_conv_algo(self.batch, self.C * self.k_mult, self.h, self.w, march_ok, rows_ok), "fft": "march",
-                          "fft_rows": "fft_rows", "direct": "direct"}[self.conv_path]
+        if self.g_arbi:
+            self.conv_algo = "direct"
+        elif self.conv_path == "auto":
+            self.conv_algo = pick_conv_algo(self.batch, self.C * self.k_mult, self.h, self.w, march_ok, rows_ok)
+        else:
+            self.conv_algo = {"fft": "march", "fft_rows": "fft_rows", "direct": "direct"}[self.conv_path]
         self.use_fft = self.conv_algo != "direct"
         if self.conv_algo == "march":
             self._kmarch = torch.empty(L.b200ca_lenia_march_kernel_elems(self.batch, self.C, self.k_mult), dtype=torch.float32,

@@ -113,7 +113,7 @@ def test_step_graph_matches_eager_steps():
     graphed = [mk(s) for s in states]
     sg = StepGraph(graphed, reps=2)          # (the warm-up steps inside refresh() are undone: nothing has advanced yet)
     for a, b in zip(eager, graphed):
-        assert torch.equal(a.state, b.state) and b.frames == 0
+        assert torch.equal(a.state.cpu(), b.state.cpu()) and b.frames == 0
     for _ in range(3):
         sg.replay()
         for a in eager:
