@@ -405,10 +405,48 @@ class LeniaWL(Workload):
                 self.graph = StepGraph(self.autos[:k // 2], reps=2)
                 self.graph_steps = self.graph.steps_per_replay
         else:
-            self.slab = LeniaSlabCUDA(self.params, self.C, self.H, self.W, self.rank, self.world, device=self.device)
-            g = torch.Generator(device=self.device).manual_seed(1000 + self.rank)
-            dense = torch.rand(1, self.C, self.slab.hl, self.W, generator=g, device=self.device)
-            self.slab.set_interior(dense)
+            # one torus in row slabs: halo exchange inside the step kernel (P2P stores over NVLink, one launch per step);
+            # NCCL send/recv slabs if symmetric memory / peer access is not available (B200CA_SLAB_HALO=nccl forces them)
+            from pyca_b200.slab import LeniaSlabP2P
+
+            self.halo = "p2p"
+            try:
+                if os.environ.get("B200CA_SLAB_HALO", "p2p") != "p2p":
+                    raise RuntimeError("forced")
+                self.slab = LeniaSlabP2P(self.params, self.C, self.H, self.W, self.rank, self.world, device=self.device)
+            except Exception as e:
+                log(f"P2P-halo slabs unavailable ({e!r}): NCCL send/recv slabs")
+                self.halo = "nccl"
+                self.slab = LeniaSlabCUDA(self.params, self.C, self.H, self.W, self.rank, self.world, device=self.device)
+            self._fill_slab()
+
+    def _full_world(self):
+        """the whole torus, generated identically on every rank (same device generator seed)"""
+        g = torch.Generator(device=self.device).manual_seed(4242)
+        return torch.rand(1, self.C, self.H, self.W, generator=g, device=self.device)
+
+    def _fill_slab(self):
+        full = self._full_world()
+        self.slab.set_interior(full[:, :, self.slab.r0:self.slab.r1])
+        del full
+
+    def check_against_single_gpu(self, steps=3):
+        """N-GPU slabs == the same world stepped on ONE GPU (this rank's, the same kernels): max |diff| over this rank's rows."""
+        import pyca_b200
+
+        self._fill_slab()
+        for _ in range(steps):
+            self.slab.step()
+        torch.cuda.synchronize()
+        single = pyca_b200.Lenia((self.H, self.W), num_channels=self.C, params=self.params, state_init=self._full_world(),
+                                 device=self.device)
+        for _ in range(steps):
+            single.step()
+        err = (self.slab.interior() - single.state[:, :, self.slab.r0:self.slab.r1]).abs().max().item()
+        res = {"steps": steps, "max_abs_err": err, "tolerance": 2e-6,
+               "timed_out": bool(self.slab.timed_out()) if hasattr(self.slab, "timed_out") else False}
+        self.single = single
+        return res
 
     def step(self):
         if self.slab is None:
@@ -547,6 +585,20 @@ class GolWL(Workload):
     def cells_per_step(self):
         return self.H * self.W * self.steps_per_call
 
+    def check_against_single_gpu(self, steps=48):
+        """bit-exact: the slabs' owned rows and the global population against the whole torus on one GPU"""
+        import pyca_b200
+
+        self.slab.random_fill(seed=2024)
+        self.slab.run(steps)
+        ref = pyca_b200.PackedWorld(self.H, self.W, self.device)
+        ref.random_fill(seed=2024)
+        ref.step(0b1100, 0b1000, steps)
+        same = bool(torch.equal(self.slab.owned()[:, :ref.wpr], ref.bits[self.slab.r0:self.slab.r1, :ref.wpr]))
+        pop = torch.tensor([self.slab.population()], device=self.device)
+        torch.distributed.all_reduce(pop)
+        return {"steps": steps, "bit_exact": same, "population": int(pop.item()), "population_single_gpu": ref.population()}
+
     def launches_per_step(self):
         return 1
 
@@ -599,6 +651,62 @@ class GolWL(Workload):
 
     def cpu_sample(self):
         return f"GoL {self.cH}x{self.cW} int32 torch roll/where step (ca2d.py:195-209)"
+
+
+class MaceSlabWL(Workload):
+    """MaCE-XChan 4096^2 C=3 as ONE torus in row slabs: two NCCL exchanges per step (affinity rows, state
+    rows); `sharded` block of the N > 1 runs."""
+    scaling = "strong"
+
+    def __init__(self, rank, world, device, H, W, name="mace_xchan_4k"):
+        super().__init__(rank, world, device)
+        self.H, self.W, self.name = H, W, name
+
+    def _full_world(self):
+        g = torch.Generator(device=self.device).manual_seed(777)
+        return torch.rand(1, 3, self.H, self.W, generator=g, device=self.device)
+
+    def setup(self):
+        import pyca_b200
+        from pyca_b200.slab import MaceSlabCUDA
+
+        d, _ = load_params("params_xchan_arborical_asbestosis.npz")
+        self.params = pyca_b200.LeniaParams(param_dict=d)
+        self.slab = MaceSlabCUDA(self.params, 3, self.H, self.W, self.rank, self.world, device=self.device, beta=6.0, alpha=0.03)
+        self.slab.set_interior(self._full_world()[:, :, self.slab.r0:self.slab.r1])
+
+    def step(self):
+        self.slab.step()
+
+    def cells_per_step(self):
+        return self.H * self.W
+
+    def launches_per_step(self):
+        return self.slab.launches_per_step
+
+    def dominant(self):
+        return {"kernel": "affinity + mace_fast", "bytes": self.H * self.W * 24 // self.world, "fma": 0}
+
+    def config(self):
+        c = static_config(self.name, self.world)
+        c["partition"] = f"{self.world} row slabs, two NCCL halo exchanges per step (affinity rows, state rows)"
+        return c
+
+    def check_against_single_gpu(self, steps=2):
+        import pyca_b200
+
+        full = self._full_world()
+        self.slab.set_interior(full[:, :, self.slab.r0:self.slab.r1])
+        for _ in range(steps):
+            self.slab.step()
+        single = pyca_b200.MaCELeniaXChan((self.H, self.W), params=self.params, state_init=full, device=self.device)
+        for _ in range(steps):
+            single.step()
+        err = (self.slab.interior() - single.state[:, :, self.slab.r0:self.slab.r1]).abs().max().item()
+        mass = self.slab.interior().double().sum().reshape(1)
+        torch.distributed.all_reduce(mass)
+        self.single = single
+        return {"steps": steps, "max_abs_err": err, "tolerance": 1e-5, "mass": float(mass.item()), "mass_initial": float(full.double().sum().item())}
 
 
 class MaceWL(Workload):
@@ -766,6 +874,22 @@ class NcaWL(Workload):
 
     def cells_per_step(self):
         return self.B * self.H * self.W
+
+    def check_against_single_gpu(self, steps=2):
+        """this rank's shard of worlds against the same worlds inside the UNSPLIT 256-world batch stepped on one GPU (bit-exact:
+        the in-kernel update mask is keyed by the global cell index)"""
+        import pyca_b200
+
+        g = torch.Generator(device=self.device).manual_seed(99)
+        full = torch.rand(self.B, 16, self.H, self.W, generator=g, device=self.device)
+        lo = self.rank * self.Bl
+        a = full[lo:lo + self.Bl].contiguous()
+        for t_ in range(steps):
+            a = pyca_b200.nca_step(a, self.wts, seed=1, step_index=t_, impl=self.impl, first_world=lo)
+        f = full
+        for t_ in range(steps):
+            f = pyca_b200.nca_step(f, self.wts, seed=1, step_index=t_, impl=self.impl)
+        return {"steps": steps, "bit_exact": bool(torch.equal(a, f[lo:lo + self.Bl]))}
 
     def launches_per_step(self):
         return 2
@@ -1189,25 +1313,55 @@ def main():
 
     sharded = None
     if world > 1 and not args.no_extras:
-        # BASELINE configs[4]: one big torus in row slabs with NVLink halo exchange; raw values at N GPUs and, for
-        # reference, the same world on one GPU of this box (every rank runs it alone, rank 0's number is kept)
+        # The sharded BASELINE configs at N GPUs: configs[4] (one big torus in row slabs, halo rows over NVLink), configs[3] (NCA
+        # batch shards, no communication) and the MaCE-XChan world of configs[2] in row slabs.  Each entry carries the N-GPU time,
+        # the same workload on ONE GPU of this box (every rank runs it alone; max over ranks) and a correctness check of the
+        # N-GPU result against the single-GPU result made inside this run.
         sharded = {}
-        for big in ["lenia_16k", "gol_64k"]:
+
+        def reduce_max(x):
+            t_ = torch.tensor([float(x)], dtype=torch.float64, device=device)
+            torch.distributed.all_reduce(t_, op=torch.distributed.ReduceOp.MAX)
+            return float(t_.item())
+
+        def reduce_all(flag):
+            t_ = torch.tensor([1 if flag else 0], device=device)
+            torch.distributed.all_reduce(t_, op=torch.distributed.ReduceOp.MIN)
+            return bool(t_.item())
+
+        for big in ["lenia_16k", "gol_64k", "nca_256", "mace_xchan_4k"]:
             try:
                 ent = {}
-                sw = make_workload(big, rank, world, device)
+                sw = MaceSlabWL(rank, world, device, 4096, 4096) if big == "mace_xchan_4k" else make_workload(big, rank, world, device)
                 sw.setup()
-                k = 30  # a slab step is 0.2-0.9 ms: a window of several ms, so that one host hiccup does not decide the figure
-                ms_n, tim_n = timed_blocks(sw, k, 3, world, None, device, min_ms=40.0)
+                k = 30 if big != "mace_xchan_4k" else 8
+                ms_n, tim_n = timed_blocks(sw, k, 3, world, flush_for(sw, device), device, min_ms=40.0)
                 ent["ms_per_step"] = ms_n
                 ent["blocks"] = tim_n["blocks"]
-                ent["gcups"] = sw.cells_per_step() / (ent["ms_per_step"] * 1e-3) / 1e9
+                ent["gcups"] = sw.cells_per_step() / (ms_n * 1e-3) / 1e9
                 ent["config"] = sw.config()
+                if hasattr(sw, "halo"):
+                    ent["halo"] = ("P2P stores + arrival counters from inside the step kernel, one launch per step" if sw.halo == "p2p"
+                                   else "NCCL send/recv per step on a side stream")
+                b200lib.variants(reset=True)
+                sw.step()
+                ent["kernels"] = b200lib.variants(reset=True)
+                chk = sw.check_against_single_gpu()
+                if "max_abs_err" in chk:
+                    chk["max_abs_err"] = reduce_max(chk["max_abs_err"])
+                    chk["ok"] = reduce_all(chk["max_abs_err"] <= chk["tolerance"] and not chk.get("timed_out", False))
+                else:
+                    chk["ok"] = reduce_all(chk["bit_exact"] and chk.get("population", 0) == chk.get("population_single_gpu", 0))
+                    chk["bit_exact"] = chk["ok"]
+                ent["check_vs_single_gpu"] = chk
+                if hasattr(getattr(sw, "slab", None), "close"):
+                    sw.slab.close()
                 del sw
                 torch.cuda.empty_cache()
                 s1 = make_workload(big, 0, 1, device)
                 s1.setup()
-                ms1, _ = timed_blocks(s1, k, 3, 1, None, device, min_ms=40.0)
+                ms1, _ = timed_blocks(s1, k, 3, 1, flush_for(s1, device), device, min_ms=40.0)
+                ms1 = reduce_max(ms1)
                 ent["single_gpu_ms_per_step"] = ms1
                 ent["single_gpu_gcups"] = s1.cells_per_step() / (ms1 * 1e-3) / 1e9
                 del s1
@@ -1215,6 +1369,9 @@ def main():
                 torch.distributed.barrier()
                 sharded[big] = ent
             except Exception as e:
+                import traceback
+
+                log(traceback.format_exc())
                 sharded[big] = {"error": repr(e)[:300]}
 
     cpu = None

@@ -175,6 +175,21 @@ int b200ca_lenia_step_march(const float *state_in, float *state_out, const float
                             const float *weights, int B, int C, int k_mult, int H, int W, float dt, int mode, int row_wrap,
                             int band_begin, int band_end, void *stream);
 
+/* Row slab of a torus sharded over the GPUs of one box, halo exchange by P2P stores from inside the step kernel (one launch per
+ * step and source channel, no host-side send/recv): the slab's first / last 16 rows are also stored into the ghost rows of the
+ * neighbours' `state_out` buffers (`peer_up_out` / `peer_dn_out`: those buffers mapped into this process, e.g. through
+ * torch.distributed._symmetric_memory or CUDA IPC), then every boundary CTA adds 1 to the neighbour's arrival counter
+ * (`sig_up`: the up neighbour's bottom-ghost counter, `sig_dn`: the down neighbour's top-ghost counter).  The CTAs of the first
+ * / last band wait until this rank's own counters `wait_top` / `wait_bot` reach `wait_target` = step_index *
+ * b200ca_lenia_march_slab_ctas() before they read their ghost rows (step 0 reads ghost rows the caller exchanged itself).
+ * A wait that lasts longer than ~4 s sets *err_flag and goes on (no hang).  Every rank must issue the same sequence of steps. */
+int b200ca_lenia_march_slab_ctas(int H, int W, int B, int C);
+int b200ca_lenia_step_march_slab(const float *state_in, float *state_out, const float *Kf, const float *mu, const float *sigma,
+                                 const float *weights, int B, int C, int k_mult, int H, int W, float dt, int mode,
+                                 float *peer_up_out, float *peer_dn_out, uint32_t *sig_up, uint32_t *sig_dn,
+                                 const uint32_t *wait_top, const uint32_t *wait_bot, uint32_t wait_target, uint32_t *err_flag,
+                                 void *stream);
+
 /* Mass-conserving redistribution (+ optional cross-channel mixing).  Replaces
  * MaCELenia._mace_step (macelenia.py:89-120) after the affinity, and
  * MaCELeniaXChan._cross_chan_step (mace_lenia_xchan.py:68-76) when alpha_on != 0:

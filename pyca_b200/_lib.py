@@ -55,6 +55,10 @@ SIGNATURES = {
     "b200ca_lenia_march_band_rows": (c_int, [c_int, c_int, c_int, c_int]),
     "b200ca_lenia_step_march": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                         c_int, c_float, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200ca_lenia_march_slab_ctas": (c_int, [c_int, c_int, c_int, c_int]),
+    "b200ca_lenia_step_march_slab": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                             c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32,
+                                             c_void_p, c_void_p]),
     "b200ca_mace_redistribute": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_float,
                                          c_int, c_void_p]),
     "b200ca_lenia_conv_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -73,6 +73,18 @@ struct Args {
     int final_src;      // 1: last source -> Euler step / clamp (LENIA) or plain sum (AFF)
     float dt;
     int mode, row_wrap;
+    // Row slab of a torus sharded over GPUs (NVLink P2P halo, no host-side exchange; all null / 0 otherwise).  The slab's first
+    // and last F rows are ALSO stored into the neighbours' ghost rows (their `out` buffer, mapped into this address space),
+    // then this CTA bumps the neighbour's arrival counter; CTAs of the first / last band wait until the counters of THIS rank
+    // say that the ghost rows they are about to read have arrived.  The CTAs that read a rank's ghost rows are the same CTAs
+    // that produce the rows sent back to the writer of those ghost rows, so the one counter orders both directions
+    // (read-after-write of the halo, write-after-read of the buffer that is reused two steps later).
+    float *peer_up_out, *peer_dn_out;            // out buffers of the ranks owning the rows above / below (framed, same shape)
+    unsigned *sig_up, *sig_dn;                   // their counters: "your bottom ghost rows arrived" / "your top ghost rows arrived"
+    const unsigned *wait_top, *wait_bot;         // this rank's counters for its top / bottom ghost rows
+    unsigned wait_target;                        // arrivals expected before this step may read its ghost rows
+    int nbands;                                  // bands of the whole slab (blockIdx.y is permuted: boundary bands first)
+    unsigned *err_flag;                          // set if a wait timed out (no hang: the step then reads stale ghost rows)
 };
 
 // Every fp32 instruction with three register operands -- scalar or packed -- occupies the FMA pipe for two cycles per warp
@@ -150,18 +162,28 @@ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
 // One forward transform by a 16-lane group (lane t): image rows `ra` (re) and `rb` (im), 256 samples from framed column
 // `col0` on; the spectrum goes to `row4` in slot layout: float4 index 9*ka + j = (re, re', im, im') of the
 // frequencies ka + 16*(2j), ka + 16*(2j+1).  The 16 x 16 exchange runs in place in the destination row.
+template <bool COHERENT>
+__device__ __forceinline__ float ld_state(const float *p) {
+#ifdef MARCH_SLAB_LDG
+    return __ldg(p);
+#else
+    return COHERENT ? __ldcg(p) : __ldg(p);
+#endif   // ghost rows written by a peer GPU during this kernel: L2 path, not the read-only one
+}
+
+template <bool COHERENT>
 __device__ __forceinline__ void forward_load(const float *__restrict__ ra, const float *__restrict__ rb, int col0, int pitch, int t,
                                              float2 (&v)[16]) {
     ra += col0 + t;
     rb += col0 + t;
     if (col0 + N <= pitch) {  // every strip but the last: plain loads at immediate offsets
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = make_float2(__ldg(ra + 16 * q), __ldg(rb + 16 * q));
+        for (int q = 0; q < 16; ++q) v[q] = make_float2(ld_state<COHERENT>(ra + 16 * q), ld_state<COHERENT>(rb + 16 * q));
     } else {
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const bool ok = col0 + t + 16 * q < pitch;
-            v[q] = make_float2(ok ? __ldg(ra + 16 * q) : 0.f, ok ? __ldg(rb + 16 * q) : 0.f);
+            v[q] = make_float2(ok ? ld_state<COHERENT>(ra + 16 * q) : 0.f, ok ? ld_state<COHERENT>(rb + 16 * q) : 0.f);
         }
     }
 }
@@ -266,7 +288,19 @@ struct EpiArgs {
     long long half;        // Lp * pitch: distance of the second row of a pair
     int pitch, H, W, ya0, Lp, xw, row_wrap;
     float mu, nc2, w2, wn, dt;   // growth(u) * weight = exp2((u - mu)^2 * nc2) * w2 + wn
+    float *peer_up, *peer_dn;    // destination plane in the neighbours' out buffers (row slabs), or null
 };
+
+// a row slab's first / last F rows go to the neighbour's bottom / top ghost rows as well (with their periodic x images)
+__device__ __forceinline__ void store_peer(const EpiArgs &e, int y, float v) {
+    float *dst = nullptr;
+    if (e.peer_up && y < F) dst = e.peer_up + (size_t)(e.H + F + y) * e.pitch;
+    else if (e.peer_dn && y >= e.H - F) dst = e.peer_dn + (size_t)(y - e.H + F) * e.pitch;
+    if (!dst) return;
+    dst[F + e.xw] = v;
+    if (e.xw < F) dst[F + e.xw + e.W] = v;
+    if (e.xw >= e.W - F) dst[F + e.xw - e.W] = v;
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -318,10 +352,12 @@ __device__ __forceinline__ void epilogue(const EpiArgs &e, const float2 (&st)[FT
             if (ya < e.H) {
                 e.oa[(size_t)r * e.pitch] = v.x;
                 if (xe || (e.row_wrap && (ya < F || ya >= e.H - F))) store_mirrors(e.oplane, e.H, e.W, e.pitch, ya, e.xw, v.x, e.row_wrap != 0);
+                store_peer(e, ya, v.x);
             }
             if (yb < e.H) {
                 e.oa[e.half + (size_t)r * e.pitch] = v.y;
                 if (xe || (e.row_wrap && (yb < F || yb >= e.H - F))) store_mirrors(e.oplane, e.H, e.W, e.pitch, yb, e.xw, v.y, e.row_wrap != 0);
+                store_peer(e, yb, v.y);
             }
         }
     }
@@ -335,13 +371,20 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
     float4 *filt = msm + RING * ROWP4;                   // FT rows: filtered spectra -> inverse exchange -> outputs
     float2 *tw = reinterpret_cast<float2 *>(filt + FT * ROWP4);  // W256^{t r} at [17 t + r]
     const int tid = threadIdx.x, lane16 = tid & 15, grp = tid >> 4;  // 16 groups of 16 lanes
-    const int strip = blockIdx.x, band = a.band0 + blockIdx.y, b = blockIdx.z;
+    const int strip = blockIdx.x, b = blockIdx.z;
+    // row slabs: boundary bands first (blockIdx.y = 0 -> first band, 1 -> last band), so that the neighbours' ghost rows are on
+    // their way while the interior bands run
+    int band = a.band0 + blockIdx.y;
+#ifndef MARCH_NOPERM
+    if (a.nbands > 1 && (a.sig_up || a.sig_dn)) band = blockIdx.y == 0 ? 0 : (blockIdx.y == 1 ? a.nbands - 1 : (int)blockIdx.y - 1);
+#endif
     const int y0 = band * 2 * a.Lp;
     const int col0 = strip * V;                          // framed column of sample n = 0 (world column strip*V - HALO)
     const int src_plane = b * a.C + a.src / a.k_mult;
     const size_t plane_elems = (size_t)(a.H + 2 * F) * a.pitch;
     const float *splane = a.state_in + (size_t)src_plane * plane_elems;
     const int max_frow = a.H + 2 * F - 1;
+    const bool slab = a.wait_top != nullptr || a.wait_bot != nullptr;
 
     // input-independent prologue: twiddle table, taps of the first destination
     {
@@ -357,12 +400,39 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
 #pragma unroll
     for (int dy = 0; dy < KROWS; ++dy) kt[dy] = __ldg(kf0 + dy * ROW4);
     pdl_wait_then_release();  // the state is the previous step's output
-    __syncthreads();          // twiddle table
+    if (tid == 0 && (a.wait_top || a.wait_bot)) {
+        // ghost rows written by the neighbours' previous step: wait for their arrival counters (bounded: a lost neighbour must
+        // not hang the GPU -- after ~4 s the error flag is raised and the step goes on)
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (int side = 0; side < 2; ++side) {
+            const unsigned *cnt = side == 0 ? a.wait_top : a.wait_bot;
+            const bool mine = side == 0 ? band == 0 : band == a.nbands - 1;
+            if (!cnt || !mine) continue;
+            for (;;) {
+                unsigned v;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+                if ((int)(v - a.wait_target) >= 0) break;
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 4000000000ull) {
+                    if (a.err_flag) atomicExch(a.err_flag, 1u);
+                    break;
+                }
+                __nanosleep(200);
+            }
+        }
+    }
+    __syncthreads();          // twiddle table, ghost rows
 
     // spectra row z of the band <- image rows (y0 + z - R, y0 + Lp + z - R), clamped into the framed plane
     auto forward_fetch = [&](int z, float2 (&v)[16]) {
         const int fa = min(y0 + z - R + F, max_frow), fb = min(y0 + a.Lp + z - R + F, max_frow);
-        forward_load(splane + (size_t)fa * a.pitch, splane + (size_t)fb * a.pitch, col0, a.pitch, lane16, v);
+        // ghost rows (the frame rows of a slab) are written by a peer GPU while this kernel may already run: they are read
+        // through L2 (ld.global.cg); everything else takes the read-only path, whose L1 merges the 64-byte row pieces
+        // (all loads through L2 cost 12 % of the step)
+        if (slab && (fa < F || fb >= a.H + F)) forward_load<true>(splane + (size_t)fa * a.pitch, splane + (size_t)fb * a.pitch, col0, a.pitch, lane16, v);
+        else forward_load<false>(splane + (size_t)fa * a.pitch, splane + (size_t)fb * a.pitch, col0, a.pitch, lane16, v);
     };
     // prologue: blocks 0..4 (40 rows) by all 16 groups
 #pragma unroll 1
@@ -377,7 +447,7 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
     const bool lenia = a.mode == B200CA_MODE_LENIA;
     // CTAs that own cells with periodic images (first / last columns, first / last rows of a torus) or a partial last band
     const bool edge = strip == 0 || col0 - HALO + N - HALO > a.W - F || y0 + 2 * a.Lp > a.H ||
-                      (a.row_wrap && (y0 < F || y0 + 2 * a.Lp > a.H - F));
+                      ((a.row_wrap || a.peer_up_out || a.peer_dn_out) && (y0 < F || y0 + 2 * a.Lp > a.H - F));
 #pragma unroll 1
     for (int it = 0; it < a.niter; ++it) {
 #pragma unroll 1
@@ -431,6 +501,8 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
             e.w2 = 2.f * wt;
             e.wn = -wt;
             e.dt = a.dt;
+            e.peer_up = a.final_src && a.peer_up_out ? a.peer_up_out + dplane : nullptr;
+            e.peer_dn = a.final_src && a.peer_dn_out ? a.peer_dn_out + dplane : nullptr;
             const bool euler = a.final_src && lenia;
             float2 st[FT];
 #if MARCH_PREFETCH
@@ -466,6 +538,15 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
                     else { if (edge) epilogue<true, true, false>(e, st); else epilogue<false, true, false>(e, st); }
                 }
             }
+        }
+    }
+    // row slab: this CTA's share of the halo is in the neighbours' memory -> release it and bump their arrival counters
+    if (a.final_src && (a.sig_up || a.sig_dn) && (band == 0 || band == a.nbands - 1)) {
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            if (band == 0 && a.sig_up) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(a.sig_up) : "memory");
+            if (band == a.nbands - 1 && a.sig_dn) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(a.sig_dn) : "memory");
         }
     }
 }
@@ -575,18 +656,15 @@ extern "C" int b200ca_lenia_march_prepare_kernel(const float *K, float *Kf, int 
     return 0;
 }
 
-extern "C" int b200ca_lenia_step_march(const float *state_in, float *state_out, const float *Kf, const float *mu, const float *sigma,
-                                       const float *weights, int B, int C, int k_mult, int H, int W, float dt, int mode, int row_wrap,
-                                       int band_begin, int band_end, void *stream) {
-    B200CA_REQUIRE(state_in && state_out && Kf && mu && sigma && weights, "lenia_step_march: null pointer");
-    B200CA_REQUIRE(state_in != state_out, "lenia_step_march: in-place update is not supported");
-    B200CA_REQUIRE(mode == B200CA_MODE_LENIA || mode == B200CA_MODE_AFF, "lenia_step_march: bad mode %d", mode);
+static int march_launch(march::Args a, int B, int C, int k_mult, int H, int W, int band_begin, int band_end, cudaStream_t st) {
+    B200CA_REQUIRE(a.state_in && a.out && a.kf && a.mu && a.sigma && a.weights, "lenia_step_march: null pointer");
+    B200CA_REQUIRE(a.state_in != a.out, "lenia_step_march: in-place update is not supported");
+    B200CA_REQUIRE(a.mode == B200CA_MODE_LENIA || a.mode == B200CA_MODE_AFF, "lenia_step_march: bad mode %d", a.mode);
     B200CA_REQUIRE(B >= 1 && B <= 65535 && C >= 1 && k_mult >= 1, "lenia_step_march: bad B/C/k_mult");
     if (!b200ca_lenia_march_supported(H, W)) {
         set_error("lenia_step_march: world %dx%d not supported (H, W >= 32)", H, W);
         return B200CA_E_UNSUPPORTED;
     }
-    cudaStream_t st = as_stream(stream);
     static bool attr_done[64] = {false};
     int dev = 0;
     B200CA_CUDA(cudaGetDevice(&dev));
@@ -595,13 +673,6 @@ extern "C" int b200ca_lenia_step_march(const float *state_in, float *state_out, 
         B200CA_CUDA(cudaFuncSetAttribute(march::lenia_march_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march::SMEM));
         attr_done[dev & 63] = true;
     }
-    march::Args a;
-    a.state_in = state_in;
-    a.out = state_out;
-    a.kf = reinterpret_cast<const float2 *>(Kf);
-    a.mu = mu;
-    a.sigma = sigma;
-    a.weights = weights;
     a.B = B;
     a.C = C;
     a.NS = C * k_mult;
@@ -611,13 +682,10 @@ extern "C" int b200ca_lenia_step_march(const float *state_in, float *state_out, 
     a.pitch = b200ca_frame_pitch(W);
     a.Lp = march::choose_lp(H, W, B, C);
     a.niter = a.Lp / march::FT;
-    a.dt = dt;
-    a.mode = mode;
-    a.row_wrap = row_wrap;
-    const int nbands = ceil_div(H, 2 * a.Lp);
-    if (band_begin == 0 && band_end == 0) band_end = nbands;
-    B200CA_REQUIRE(band_begin >= 0 && band_end <= nbands && band_begin <= band_end, "lenia_step_march: band range [%d,%d) outside [0,%d)",
-                   band_begin, band_end, nbands);
+    a.nbands = ceil_div(H, 2 * a.Lp);
+    if (band_begin == 0 && band_end == 0) band_end = a.nbands;
+    B200CA_REQUIRE(band_begin >= 0 && band_end <= a.nbands && band_begin <= band_end, "lenia_step_march: band range [%d,%d) outside [0,%d)",
+                   band_begin, band_end, a.nbands);
     if (band_begin == band_end) return 0;
     a.band0 = band_begin;
     dim3 grid(ceil_div(W, march::V), band_end - band_begin, B);
@@ -629,6 +697,54 @@ extern "C" int b200ca_lenia_step_march(const float *state_in, float *state_out, 
         else B200CA_CUDA(launch_pdl(march::lenia_march_kernel<false>, grid, dim3(march::THREADS), march::SMEM, st, a));
     }
     B200CA_LAUNCH_CHECK("lenia_march_kernel");
-    note_variant("lenia_march<%s,Lp=%d>x%d", C == 1 ? "single" : "multi", a.Lp, a.NS);
+    note_variant("lenia_march<%s,Lp=%d%s>x%d", C == 1 ? "single" : "multi", a.Lp, (a.sig_up || a.sig_dn) ? ",p2p-halo" : "", a.NS);
     return 0;
+}
+
+extern "C" int b200ca_lenia_step_march(const float *state_in, float *state_out, const float *Kf, const float *mu, const float *sigma,
+                                       const float *weights, int B, int C, int k_mult, int H, int W, float dt, int mode, int row_wrap,
+                                       int band_begin, int band_end, void *stream) {
+    march::Args a = {};
+    a.state_in = state_in;
+    a.out = state_out;
+    a.kf = reinterpret_cast<const float2 *>(Kf);
+    a.mu = mu;
+    a.sigma = sigma;
+    a.weights = weights;
+    a.dt = dt;
+    a.mode = mode;
+    a.row_wrap = row_wrap;
+    return march_launch(a, B, C, k_mult, H, W, band_begin, band_end, as_stream(stream));
+}
+
+extern "C" int b200ca_lenia_march_slab_ctas(int H, int W, int B, int C) {
+    (void)H;
+    return ceil_div(W, march::V) * B;
+}
+
+extern "C" int b200ca_lenia_step_march_slab(const float *state_in, float *state_out, const float *Kf, const float *mu, const float *sigma,
+                                            const float *weights, int B, int C, int k_mult, int H, int W, float dt, int mode,
+                                            float *peer_up_out, float *peer_dn_out, uint32_t *sig_up, uint32_t *sig_dn,
+                                            const uint32_t *wait_top, const uint32_t *wait_bot, uint32_t wait_target, uint32_t *err_flag,
+                                            void *stream) {
+    B200CA_REQUIRE(peer_up_out && peer_dn_out && sig_up && sig_dn && wait_top && wait_bot, "lenia_step_march_slab: null peer pointer");
+    march::Args a = {};
+    a.state_in = state_in;
+    a.out = state_out;
+    a.kf = reinterpret_cast<const float2 *>(Kf);
+    a.mu = mu;
+    a.sigma = sigma;
+    a.weights = weights;
+    a.dt = dt;
+    a.mode = mode;
+    a.row_wrap = 0;
+    a.peer_up_out = peer_up_out;
+    a.peer_dn_out = peer_dn_out;
+    a.sig_up = sig_up;
+    a.sig_dn = sig_dn;
+    a.wait_top = wait_top;
+    a.wait_bot = wait_bot;
+    a.wait_target = wait_target;
+    a.err_flag = err_flag;
+    return march_launch(a, B, C, k_mult, H, W, 0, 0, as_stream(stream));
 }

@@ -355,6 +355,107 @@ class LeniaSlabCUDA(LeniaSlab):
         self.cur ^= 1
 
 
+class LeniaSlabP2P(LeniaSlab):
+    """Lenia row slab whose halo exchange happens INSIDE the step kernel (option B): the marching kernel
+    (csrc/lenia_march.cu) stores the slab's first / last 16 rows straight into the neighbours' ghost rows over NVLink and bumps
+    their arrival counters; the next step's boundary CTAs wait on this rank's counters.  The host issues ONE launch per step and
+    source channel -- no send/recv, no side stream, no stream hand-off.  Buffers and counters live in symmetric memory
+    (torch.distributed._symmetric_memory: every rank maps every peer's allocation); boundary bands are scheduled first, so the
+    halo travels while the interior bands compute (Lenia.step semantics, lenia.py:430-451, on rows [r0, r1) of the torus).
+
+    Needs P2P access between the GPUs (NVLink / NVSwitch) and a process group; `LeniaSlabCUDA` (NCCL send/recv) is the
+    fallback.  Every rank must call `step()` the same number of times."""
+
+    def __init__(self, lenia_params, C, H, W, rank, world, device="cuda", dt=0.1, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _lib
+        from .lenia_params import compute_kernel
+
+        L = _lib.lib()
+        B = lenia_params["weights"].shape[0]
+        self.device = torch.device(device)
+        self.group = group if group is not None else dist.group.WORLD
+        # the base class allocates two private framed buffers: replaced below by views of one symmetric allocation
+        super().__init__(B, C, H, W, rank, world, _lib.FRAME, L.b200ca_frame_pitch(W), "meta")
+        if not L.b200ca_lenia_march_supported(self.hl, W):
+            raise _lib.B200CAError(f"a {self.hl}x{W} slab is not supported by the marching kernel")
+        n = B * C * self.rows * self.pitch
+        self._n = n
+        self._sym = symm.empty(2 * n + 64, dtype=torch.float32, device=self.device)
+        self._sym.zero_()
+        self._hdl = symm.rendezvous(self._sym, self.group)
+        self.bufs = [self._sym[i * n:(i + 1) * n].view(B, C, self.rows, self.pitch) for i in range(2)]
+        self._counters = self._sym[2 * n:2 * n + 64].view(torch.int32)   # [0] top-ghost arrivals, [1] bottom-ghost arrivals, [2] error
+        ptrs = list(self._hdl.buffer_ptrs)
+        up, down = ring_neighbours(rank, world)
+        cnt = 2 * n * 4
+        self._peer_out = [(ptrs[up] + i * n * 4, ptrs[down] + i * n * 4) for i in range(2)]
+        self._sig_up = ptrs[up] + cnt + 4       # the up neighbour's BOTTOM ghost rows are my first rows
+        self._sig_dn = ptrs[down] + cnt         # the down neighbour's TOP ghost rows are my last rows
+        self._wait_top, self._wait_bot, self._err = ptrs[rank] + cnt, ptrs[rank] + cnt + 4, ptrs[rank] + cnt + 8
+        self.dt = dt
+        p = lenia_params.to(device).param_dict
+        self.k_mult = p.get("k_mult", 1)
+        self.mu = p["mu"].float().contiguous()
+        self.sigma = p["sigma"].float().contiguous()
+        self.weights = p["weights"].float().contiguous()
+        self.k = compute_kernel(lenia_params, C).float().contiguous()
+        self._kmarch = torch.empty(L.b200ca_lenia_march_kernel_elems(B, C, self.k_mult), dtype=torch.float32, device=device)
+        with torch.cuda.device(self.device):
+            _lib.call("b200ca_lenia_march_prepare_kernel", _lib.ptr(self.k), _lib.ptr(self._kmarch), B, C, self.k_mult, int(p["k_size"]),
+                      _lib.current_stream(self.device))
+        self._ctas = L.b200ca_lenia_march_slab_ctas(self.hl, W, B, C)
+        self.step_index = 0
+        self.use_fft = True
+        self.overlap = True
+        self.launches_per_step = C * self.k_mult
+        self._step_fn = L.b200ca_lenia_step_march_slab
+
+    def set_interior(self, dense: torch.Tensor, group=None):
+        """dense: (B,C,hl,W) rows [r0,r1) of the global state.  Collective: every rank calls it (the first ghost rows travel by
+        send/recv, the arrival counters restart from zero)."""
+        from . import _lib
+
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)                      # nobody is still stepping into this rank's buffers
+        self.interior().copy_(dense)
+        with torch.cuda.device(self.device):
+            _lib.call("b200ca_frame_refresh", _lib.ptr(self.buf), self.B, self.C, self.hl, self.W, 0, _lib.current_stream(self.device))
+        self._counters.zero_()
+        self.step_index = 0
+        self.exchange(self.buf, self.group)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)
+
+    def step(self, group=None):
+        from . import _lib
+
+        nxt = self.cur ^ 1
+        pu, pd = self._peer_out[nxt]
+        with _lib.device_guard(self.device):
+            rc = self._step_fn(self.bufs[self.cur].data_ptr(), self.bufs[nxt].data_ptr(), self._kmarch.data_ptr(), self.mu.data_ptr(),
+                               self.sigma.data_ptr(), self.weights.data_ptr(), self.B, self.C, self.k_mult, self.hl, self.W,
+                               float(self.dt), 0, pu, pd, self._sig_up, self._sig_dn, self._wait_top, self._wait_bot,
+                               (self.step_index * self._ctas) & 0xFFFFFFFF, self._err, torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            _lib.check(rc, "b200ca_lenia_step_march_slab")
+        self.cur = nxt
+        self.step_index += 1
+
+    def timed_out(self) -> bool:
+        """True if a boundary CTA gave up waiting for a neighbour (the results are then invalid)."""
+        return bool(self._counters[2].item())
+
+    def close(self):
+        """Collective: no rank may free its buffers while a neighbour's kernel can still store into them."""
+        if getattr(self, "_sym", None) is not None:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(self.group)
+            self.bufs = []
+            self._counters = self._hdl = self._sym = None
+
+
 class MaceSlabCUDA(LeniaSlabCUDA):
     """MaCE-Lenia (and the cross-channel variant) on a row slab.  The redistribution reads the affinity on a
     2-row halo and the state on a 1-row halo, so a step has TWO exchanges: affinity rows after the convolution, state rows

@@ -76,6 +76,34 @@ def main():
         print(f"[rank {rank}] Lenia direct hl={hl} (tile rows {sl.tile_rows}, boundary {sl.n_boundary}/{sl.n_boundary_bot}) "
               f"overlap={sl.overlap}: max |slab - torus| = {err:.2e}", flush=True)
         ok &= err <= 1e-6
+    # ---- halo exchange inside the step kernel (LeniaSlabP2P: P2P stores + arrival counters over NVLink, one launch per step)
+    from pyca_b200.slab import LeniaSlabP2P
+
+    for C, hl, Ww, steps in ((1, 256, 480, 6), (3, 128, 320, 5), (1, 1024, 1200, 7)):
+        dd = {k: (v[:, :C, :C].clone() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+        Hh = hl * world
+        g = torch.Generator().manual_seed(100 + C + hl)
+        full = torch.rand(1, C, Hh, Ww, generator=g)
+        single = pyca_b200.Lenia((Hh, Ww), num_channels=C, params=dict(dd), state_init=full, device=dev, conv_path="fft")
+        params = pyca_b200.LeniaParams(param_dict=dict(dd), channels=C)
+        try:
+            sl = LeniaSlabP2P(params, C, Hh, Ww, rank, world, device=dev)
+        except Exception as e:  # no P2P / symmetric memory on this box: reported, not hidden
+            print(f"[rank {rank}] LeniaSlabP2P unavailable: {e!r}", flush=True)
+            ok = False
+            break
+        sl.set_interior(full[:, :, sl.r0:sl.r1].to(dev))
+        for _ in range(steps):
+            single.step()
+            sl.step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        err = (sl.interior() - single.state[:, :, sl.r0:sl.r1]).abs().max().item()
+        to = sl.timed_out()
+        print(f"[rank {rank}] Lenia P2P-halo slab C={C} hl={hl} W={Ww} {steps} steps: max |slab - torus| = {err:.2e}, timed out: {to}, "
+              f"kernels {pyca_b200._lib.variants()[-1:]}", flush=True)
+        ok &= err <= 2e-6 and not to
+        sl.close()
     # ---- MaCE-Lenia XChan slabs (two exchanges per step: affinity rows, then state rows), 3 steps, mass conserved
     from pyca_b200.slab import MaceSlabCUDA
 
