@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
         // ghost rows (the frame rows of a slab) are written by a peer GPU while this kernel may already run: they are read
         // through L2 (ld.global.cg); everything else takes the read-only path, whose L1 merges the 64-byte row pieces
         // (all loads through L2 cost 12 % of the step)
-        if (slab && (fa < F || fb >= a.H + F)) forward_load<true>(splane + (size_t)fa * a.pitch, splane + (size_t)fb * a.pitch, col0, a.pitch, lane16, v);
+        if (slab && (fa < F || fa >= a.H + F || fb >= a.H + F)) forward_load<true>(splane + (size_t)fa * a.pitch, splane + (size_t)fb * a.pitch, col0, a.pitch, lane16, v);
         else forward_load<false>(splane + (size_t)fa * a.pitch, splane + (size_t)fb * a.pitch, col0, a.pitch, lane16, v);
     };
     // prologue: blocks 0..4 (40 rows) by all 16 groups
@@ -588,10 +588,13 @@ static int choose_lp(int H, int W, int B, int C) {
     double best_cost = 1e30;
     for (int lp = MARCH_MAXLP; lp >= FT; lp >>= 1) {
         const long long ctas = strips * ceil_div(H, 2 * lp) * B;
-        const double waves = (double)ceil_div64(ctas, slots);
-        // per CTA: lp + 32 forward transforms, lp x C x (FIR + inverse + epilogue ~ 2.5 forward transforms each)
+        // Fitted to B200 timings of 1024^2 ... 16384^2 worlds with band heights 8 ... 256 (profiles/r02_conv_paths.md): a
+        // launch behaves like (waves + 1.5) rounds of CTAs -- co-resident CTAs of a short launch run their phases in lockstep and
+        // overlap less than the staggered CTAs of a long one -- and a CTA costs lp + 32 forward transforms plus lp x C x
+        // (FIR + inverse + epilogue ~ 2.5 forward transforms each).
+        const double waves = (double)ceil_div64(ctas, slots) + 1.5;
         const double cost = waves * ((lp + 32) + 2.5 * C * lp);
-        if (cost < best_cost * 0.97) {
+        if (cost < best_cost * 0.98) {   // near ties go to the taller band
             best_cost = cost;
             best = lp;
         }

@@ -4,7 +4,7 @@ line (`config.kernels`), so a change of the dispatch rules shows up here first."
 
 EXPECT = {
     # Lenia 1024^2 (BASELINE configs[1] and its C=3 form)
-    "lenia1_1k_fft": ["lenia_march<single,Lp=16>x1"],
+    "lenia1_1k_fft": ["lenia_march<single,Lp=8>x1"],
     "lenia3_1k_fft": ["lenia_march<multi,Lp="],
     "lenia1_1k_fft_rows": ["lenia_fft_rows<1,1024,split>", "lenia_fft_firinv<8,single,1,512>"],
     "lenia3_1k_fft_rows": ["lenia_fft_rows<2,1024,split>", "lenia_fft_firinv<4,multi,2,256>"],
