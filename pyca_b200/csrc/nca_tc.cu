@@ -62,11 +62,13 @@ constexpr int TMEM_COLS = 512;  // 128 columns per group: D1 = [0,128), D2 = [0,
 constexpr int D2_COL = 0;
 constexpr int H2CHUNK = 16;     // hidden columns per GEMM-2 chunk (two K=8 steps)
 
-// tf32 split: hi = x rounded to 10 explicit mantissa bits (low 13 bits zero, so the tensor core's truncation is exact);
-// lo = x - hi (exact in fp32; the tensor core keeps its top 11 bits: error <= 2^-22 |x|)
+// tf32 split: hi = x truncated to 10 explicit mantissa bits (low 13 bits zero, so the tensor core reads it exactly);
+// lo = x - hi (exact in fp32, |lo| < 2^-10 |x|; the tensor core keeps its top 11 bits: error < 2^-20 |x|, and the dropped
+// lo*lo product is < 2^-20 |a||b| -- both far inside the 1e-5 parity bound, measured 5e-7).  Truncation instead of
+// round-to-nearest saves the add of the rounding form: one LOP3 + one FADD per element (cvt.rna.tf32.f32 expands to ~6
+// SASS instructions on sm_100); the WEIGHT images keep the rounded split (prepared once).
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-    // (cvt.rna.tf32.f32 expands to ~6 SASS instructions on sm_100; the add-and-mask form is 2)
-    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
     lo = x - hi;
 }
 
@@ -91,6 +93,36 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
         "}\n" ::"r"(d_tmem),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// one MMA with the A / B descriptors given as (constant high word, low word): the low word carries the 16-byte-granular
+// shared-memory address, so stepping through an operand is one integer add
+template <bool ACC>
+__device__ __forceinline__ void mma_tf32_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi, uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "n"(ACC ? 1 : 0)
+        : "memory");
+}
+// true in exactly one lane of a converged warp (elect.sync): the code under it is provably single-lane, so ptxas moves the
+// MMA operands to uniform registers directly instead of wrapping every tcgen05.mma in a lane-election loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rx;\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -163,6 +195,12 @@ __global__ void __launch_bounds__(128 * NG, 1) nca_update_tc_kernel(const NcaArg
     // descriptor strides: A operands [chunk][128 rows][16 B], B1 [chunk][128 n][16 B], B2 [chunk][16 n][16 B]
     constexpr uint32_t lboA = 128 * 16, lboB1 = 128 * 16, lboB2 = 16 * 16, sboA = 128, sboB1 = 128, sboB2 = 128;
     constexpr uint32_t IDESC1 = make_idesc(128), IDESC2 = make_idesc(16);
+    // descriptor words: low = (address >> 4) | (LBO >> 4) << 16, high = (SBO >> 4) | version bit (see make_desc)
+    constexpr uint32_t DHI_A = (sboA >> 4) | (1u << 14), DHI_B1 = (sboB1 >> 4) | (1u << 14), DHI_B2 = (sboB2 >> 4) | (1u << 14);
+    const uint32_t dA1hi = ((sA1hi >> 4) & 0x3fffu) | ((lboA >> 4) << 16), dA1lo = ((sA1lo >> 4) & 0x3fffu) | ((lboA >> 4) << 16);
+    const uint32_t dB1hi = ((sB1hi >> 4) & 0x3fffu) | ((lboB1 >> 4) << 16), dB1lo = ((sB1lo >> 4) & 0x3fffu) | ((lboB1 >> 4) << 16);
+    const uint32_t dA2 = ((sA2 >> 4) & 0x3fffu) | ((lboA >> 4) << 16);
+    const uint32_t dB2hi = ((sB2hi >> 4) & 0x3fffu) | ((lboB2 >> 4) << 16), dB2lo = ((sB2lo >> 4) & 0x3fffu) | ((lboB2 >> 4) << 16);
 
     const size_t plane = (size_t)a.H * a.W;
     const int ntiles = tiles_x * tiles_y * a.B;
@@ -244,18 +282,21 @@ __global__ void __launch_bounds__(128 * NG, 1) nca_update_tc_kernel(const NcaArg
         group_sync(gid);
 
         // ---- GEMM 1: D1 = [P | 1 | 0] * [W1f | b1 | 0]^T, K = 40 = 5 k-steps x (hi*hi + hi*lo + lo*hi)
-        if (tid == 0) {
-            tc_fence_after();
+        if (warp == 0) {
+            if (elect_one()) {
+                tc_fence_after();
 #pragma unroll
-            for (int ks = 0; ks < K1P / 8; ++ks) {
-                const uint32_t offA = ks * 2 * 128 * 16, offB = ks * 2 * 128 * 16;
-                const uint64_t ah = make_desc(sA1hi + offA, lboA, sboA), al = make_desc(sA1lo + offA, lboA, sboA);
-                const uint64_t bh = make_desc(sB1hi + offB, lboB1, sboB1), bl = make_desc(sB1lo + offB, lboB1, sboB1);
-                mma_tf32(tmem, ah, bh, IDESC1, ks > 0);
-                mma_tf32(tmem, ah, bl, IDESC1, 1);
-                mma_tf32(tmem, al, bh, IDESC1, 1);
+                for (int ks = 0; ks < K1P / 8; ++ks) {
+                    constexpr uint32_t step = (2 * 128 * 16) >> 4;   // two 16-byte K chunks of 128 rows per k-step
+                    const uint32_t ah = dA1hi + ks * step, al = dA1lo + ks * step, bh = dB1hi + ks * step, bl = dB1lo + ks * step;
+                    if (ks == 0) mma_tf32_lo<false>(tmem, ah, bh, DHI_A, DHI_B1, IDESC1);
+                    else mma_tf32_lo<true>(tmem, ah, bh, DHI_A, DHI_B1, IDESC1);
+                    mma_tf32_lo<true>(tmem, ah, bl, DHI_A, DHI_B1, IDESC1);
+                    mma_tf32_lo<true>(tmem, al, bh, DHI_A, DHI_B1, IDESC1);
+                }
+                mma_commit(bar1);
             }
-            mma_commit(bar1);
+            __syncwarp();
         }
         mbar_wait(bar1, ph1);
         ph1 ^= 1;
@@ -284,20 +325,23 @@ __global__ void __launch_bounds__(128 * NG, 1) nca_update_tc_kernel(const NcaArg
             fence_proxy_async();
             tc_fence_before();
             group_sync(gid);
-            if (tid == 0) {
-                tc_fence_after();
-                const uint32_t sA2hi = sA2 + bsel * A2_BUF, sA2lo = sA2hi + A2_BUF / 2;
+            if (warp == 0) {
+                if (elect_one()) {
+                    tc_fence_after();
+                    const uint32_t a2hi = dA2 + ((bsel * A2_BUF) >> 4), a2lo = a2hi + ((A2_BUF / 2) >> 4);
 #pragma unroll
-                for (int s = 0; s < H2CHUNK / 8; ++s) {
-                    const uint32_t offA = s * 2 * 128 * 16;
-                    const uint32_t offB = (c * (H2CHUNK / 4) + s * 2) * 16 * 16;
-                    const uint64_t ah = make_desc(sA2hi + offA, lboA, sboA), al = make_desc(sA2lo + offA, lboA, sboA);
-                    const uint64_t bh = make_desc(sB2hi + offB, lboB2, sboB2), bl = make_desc(sB2lo + offB, lboB2, sboB2);
-                    mma_tf32(tmem + D2_COL, ah, bh, IDESC2, (c | s) != 0);
-                    mma_tf32(tmem + D2_COL, ah, bl, IDESC2, 1);
-                    mma_tf32(tmem + D2_COL, al, bh, IDESC2, 1);
+                    for (int s = 0; s < H2CHUNK / 8; ++s) {
+                        const uint32_t offA = (s * 2 * 128 * 16) >> 4;
+                        const uint32_t offB = ((c * (H2CHUNK / 4) + s * 2) * 16 * 16) >> 4;
+                        const uint32_t ah = a2hi + offA, al = a2lo + offA, bh = dB2hi + offB, bl = dB2lo + offB;
+                        if (s == 0 && c == 0) mma_tf32_lo<false>(tmem + D2_COL, ah, bh, DHI_A, DHI_B2, IDESC2);
+                        else mma_tf32_lo<true>(tmem + D2_COL, ah, bh, DHI_A, DHI_B2, IDESC2);
+                        mma_tf32_lo<true>(tmem + D2_COL, ah, bl, DHI_A, DHI_B2, IDESC2);
+                        mma_tf32_lo<true>(tmem + D2_COL, al, bh, DHI_A, DHI_B2, IDESC2);
+                    }
+                    mma_commit(bar2 + bsel);
                 }
-                mma_commit(bar2 + bsel);
+                __syncwarp();
             }
         }
         // chunks 6 and 7 are still outstanding
