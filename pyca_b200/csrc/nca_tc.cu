@@ -53,8 +53,9 @@ constexpr int SM_A2 = SM_A1HI;            // buffer b at SM_A2 + b * 16 KB: hi t
 constexpr int A2_BUF = 16 * 1024;
 constexpr int NG = 4;                                     // 128-thread groups per CTA
 constexpr int SM_GROUP = 40 * 1024;                       // per-group A region (A1hi + A1lo; A2 buffers alias it)
-constexpr int SM_BAR = SM_A1HI + NG * SM_GROUP;           // mbarriers (3 per group) + tmem address
-constexpr int SM_TOTAL = SM_BAR + 128;                    // 217 KB + 128: one CTA per SM
+constexpr int SM_BAR = SM_A1HI + NG * SM_GROUP;           // mbarriers (6 per group) + tmem address
+constexpr int SM_TOTAL = SM_BAR + 256;                    // 217 KB + 256: one CTA per SM
+constexpr int NTHREADS = 128 * NG + 32 * NG;              // four worker groups + one MMA-issue warp per group
 static_assert(SM_TOTAL + 1024 <= 227 * 1024, "CTA must fit in one SM");
 static_assert(TC_WBYTES <= SM_A1HI, "weights overflow their smem region");
 
@@ -152,27 +153,41 @@ __device__ __forceinline__ float sigmoid_rn(float x) {
 
 __device__ __forceinline__ void group_sync(int gid) { asm volatile("bar.sync %0, 128;" ::"r"(gid + 1) : "memory"); }
 
-__global__ void __launch_bounds__(128 * NG, 1) nca_update_tc_kernel(const NcaArgs a, int tiles_x, int tiles_y) {
+// Roles: 16 worker warps (four 128-thread groups, one tile each: perception, ReLU / splits, output) and one MMA-issue warp
+// PER GROUP.  Hand-offs are mbarriers in both directions -- workers arrive on full1 / full2[b] (128 arrivals) when an A
+// operand is in shared memory, the group's MMA warp waits for it, issues the tcgen05.mma burst and commits to bar1 /
+// bar2[b], which the workers wait on -- so no worker warp ever issues an MMA or waits at a group-wide bar.sync: with the
+// issue inside worker warp 0 (round 1) 27 % of the warp samples sat at the group barrier after every operand store and at
+// the re-convergence behind the issuing lane.  (ONE issue warp polling all four groups was 1.8x slower: a tcgen05.commit
+// tracks every earlier MMA of the issuing thread, so each group's hand-off waited for the other groups' GEMMs.)
+__global__ void __launch_bounds__(NTHREADS, 1) nca_update_tc_kernel(const NcaArgs a, int tiles_x, int tiles_y) {
     extern __shared__ __align__(1024) unsigned char smem_all[];
-    const int gid = threadIdx.x >> 7;           // group of this thread
+    const bool mma_warp = threadIdx.x >= 128 * NG;
+    const int gid = mma_warp ? (threadIdx.x - 128 * NG) >> 5 : threadIdx.x >> 7;   // group of this thread
     const int tid = threadIdx.x & 127;          // thread within the group = tile row = TMEM lane
     const int lane = tid & 31, warp = tid >> 5;
     unsigned char *smem = smem_all + gid * SM_GROUP;  // group view: the SM_A* offsets below land in this group's region
     float *sw = reinterpret_cast<float *>(smem_all + SM_W);
-    uint64_t *bar1 = reinterpret_cast<uint64_t *>(smem_all + SM_BAR) + 3 * gid;  // GEMM 1 done
-    uint64_t *bar2 = bar1 + 1;                                                   // bar2[b]: GEMM 2 chunk using A2 buffer b done
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_all + SM_BAR + 3 * NG * 8);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_all + SM_BAR);
+    uint64_t *bar1 = bars + 6 * gid;   // GEMM 1 done (MMA warp -> workers)
+    uint64_t *bar2 = bar1 + 1;         // bar2[b]: GEMM 2 chunk using A2 buffer b done
+    uint64_t *full1 = bar1 + 3;        // A1 written by all 128 workers (workers -> MMA warp)
+    uint64_t *full2 = bar1 + 4;        // full2[b]: A2 buffer b written
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_all + SM_BAR + 6 * NG * 8);
 
     // ---- one-time setup: weights -> smem, barriers, TMEM
     {
         const float4 *src = reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(a.wp) + WP_TC_OFF);
         float4 *dst = reinterpret_cast<float4 *>(sw);
-        for (int t = threadIdx.x; t < TC_WBYTES / 16; t += 128 * NG) dst[t] = __ldg(src + t);
+        for (int t = threadIdx.x; t < TC_WBYTES / 16; t += NTHREADS) dst[t] = __ldg(src + t);
     }
-    if (tid == 0) {
+    if (tid == 0 && !mma_warp) {
         mbar_init(bar1, 1);
         mbar_init(bar2, 1);
         mbar_init(bar2 + 1, 1);
+        mbar_init(full1, 128);
+        mbar_init(full2, 128);
+        mbar_init(full2 + 1, 128);
         mbar_fence_init();
     }
     if (threadIdx.x < 32) {
@@ -206,6 +221,51 @@ __global__ void __launch_bounds__(128 * NG, 1) nca_update_tc_kernel(const NcaArg
     const int ntiles = tiles_x * tiles_y * a.B;
     uint32_t ph1 = 0, ph2[2] = {0, 0};
 
+    if (mma_warp) {
+        // ---- MMA-issue warp of group `gid`: per tile the requests are [GEMM 1, chunk 0, ..., chunk 7]
+        uint32_t pf1 = 0, pf2[2] = {0, 0};
+        const uint32_t tm = tmem;
+        for (int tile = blockIdx.x * NG + gid; tile < ntiles; tile += gridDim.x * NG) {
+            mbar_wait(full1, pf1);
+            pf1 ^= 1;
+            if (elect_one()) {
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < K1P / 8; ++ks) {
+                    constexpr uint32_t step = (2 * 128 * 16) >> 4;   // two 16-byte K chunks of 128 rows per k-step
+                    const uint32_t ah = dA1hi + ks * step, al = dA1lo + ks * step, bh = dB1hi + ks * step, bl = dB1lo + ks * step;
+                    if (ks == 0) mma_tf32_lo<false>(tm, ah, bh, DHI_A, DHI_B1, IDESC1);
+                    else mma_tf32_lo<true>(tm, ah, bh, DHI_A, DHI_B1, IDESC1);
+                    mma_tf32_lo<true>(tm, ah, bl, DHI_A, DHI_B1, IDESC1);
+                    mma_tf32_lo<true>(tm, al, bh, DHI_A, DHI_B1, IDESC1);
+                }
+                mma_commit(bar1);
+            }
+            __syncwarp();
+#pragma unroll 2
+            for (int c = 0; c < NCA_HID / H2CHUNK; ++c) {
+                const int bsel = c & 1;
+                mbar_wait(full2 + bsel, pf2[bsel]);
+                pf2[bsel] ^= 1;
+                if (elect_one()) {
+                    tc_fence_after();
+                    const uint32_t a2hi = dA2 + ((bsel * A2_BUF) >> 4), a2lo = a2hi + ((A2_BUF / 2) >> 4);
+#pragma unroll
+                    for (int s2 = 0; s2 < H2CHUNK / 8; ++s2) {
+                        const uint32_t offA = (s2 * 2 * 128 * 16) >> 4;
+                        const uint32_t offB = ((c * (H2CHUNK / 4) + s2 * 2) * 16 * 16) >> 4;
+                        const uint32_t ah = a2hi + offA, al = a2lo + offA, bh = dB2hi + offB, bl = dB2lo + offB;
+                        if (s2 == 0 && c == 0) mma_tf32_lo<false>(tm + D2_COL, ah, bh, DHI_A, DHI_B2, IDESC2);
+                        else mma_tf32_lo<true>(tm + D2_COL, ah, bh, DHI_A, DHI_B2, IDESC2);
+                        mma_tf32_lo<true>(tm + D2_COL, ah, bl, DHI_A, DHI_B2, IDESC2);
+                        mma_tf32_lo<true>(tm + D2_COL, al, bh, DHI_A, DHI_B2, IDESC2);
+                    }
+                    mma_commit(bar2 + bsel);
+                }
+                __syncwarp();
+            }
+        }
+    } else
     for (int tile = blockIdx.x * NG + gid; tile < ntiles; tile += gridDim.x * NG) {
         const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
         const int x = tx * 32 + lane, y = ty * 4 + warp;
@@ -279,25 +339,7 @@ __global__ void __launch_bounds__(128 * NG, 1) nca_update_tc_kernel(const NcaArg
         }
         fence_proxy_async();
         tc_fence_before();
-        group_sync(gid);
-
-        // ---- GEMM 1: D1 = [P | 1 | 0] * [W1f | b1 | 0]^T, K = 40 = 5 k-steps x (hi*hi + hi*lo + lo*hi)
-        if (warp == 0) {
-            if (elect_one()) {
-                tc_fence_after();
-#pragma unroll
-                for (int ks = 0; ks < K1P / 8; ++ks) {
-                    constexpr uint32_t step = (2 * 128 * 16) >> 4;   // two 16-byte K chunks of 128 rows per k-step
-                    const uint32_t ah = dA1hi + ks * step, al = dA1lo + ks * step, bh = dB1hi + ks * step, bl = dB1lo + ks * step;
-                    if (ks == 0) mma_tf32_lo<false>(tmem, ah, bh, DHI_A, DHI_B1, IDESC1);
-                    else mma_tf32_lo<true>(tmem, ah, bh, DHI_A, DHI_B1, IDESC1);
-                    mma_tf32_lo<true>(tmem, ah, bl, DHI_A, DHI_B1, IDESC1);
-                    mma_tf32_lo<true>(tmem, al, bh, DHI_A, DHI_B1, IDESC1);
-                }
-                mma_commit(bar1);
-            }
-            __syncwarp();
-        }
+        mbar_arrive(full1);   // -> the MMA warp issues GEMM 1: D1 = [P | 1 | 0] * [W1f | b1 | 0]^T, K = 40 = 5 k-steps x (hi*hi + hi*lo + lo*hi)
         mbar_wait(bar1, ph1);
         ph1 ^= 1;
         tc_fence_after();
@@ -324,25 +366,7 @@ __global__ void __launch_bounds__(128 * NG, 1) nca_update_tc_kernel(const NcaArg
             }
             fence_proxy_async();
             tc_fence_before();
-            group_sync(gid);
-            if (warp == 0) {
-                if (elect_one()) {
-                    tc_fence_after();
-                    const uint32_t a2hi = dA2 + ((bsel * A2_BUF) >> 4), a2lo = a2hi + ((A2_BUF / 2) >> 4);
-#pragma unroll
-                    for (int s = 0; s < H2CHUNK / 8; ++s) {
-                        const uint32_t offA = (s * 2 * 128 * 16) >> 4;
-                        const uint32_t offB = ((c * (H2CHUNK / 4) + s * 2) * 16 * 16) >> 4;
-                        const uint32_t ah = a2hi + offA, al = a2lo + offA, bh = dB2hi + offB, bl = dB2lo + offB;
-                        if (s == 0 && c == 0) mma_tf32_lo<false>(tmem + D2_COL, ah, bh, DHI_A, DHI_B2, IDESC2);
-                        else mma_tf32_lo<true>(tmem + D2_COL, ah, bh, DHI_A, DHI_B2, IDESC2);
-                        mma_tf32_lo<true>(tmem + D2_COL, ah, bl, DHI_A, DHI_B2, IDESC2);
-                        mma_tf32_lo<true>(tmem + D2_COL, al, bh, DHI_A, DHI_B2, IDESC2);
-                    }
-                    mma_commit(bar2 + bsel);
-                }
-                __syncwarp();
-            }
+            mbar_arrive(full2 + bsel);   // -> the MMA warp issues this chunk's six MMAs into D2
         }
         // chunks 6 and 7 are still outstanding
         mbar_wait(bar2, ph2[0]);
@@ -372,9 +396,9 @@ __global__ void __launch_bounds__(128 * NG, 1) nca_update_tc_kernel(const NcaArg
                 for (int ch = 0; ch < NCA_N; ++ch) ob[(size_t)ch * plane] = keep ? sigmoid_rn(o[ch] + bias2[ch]) : 0.f;
             }
         }
-        // all TMEM reads of this tile are done before the next tile's MMAs overwrite D1/D2
+        // all TMEM reads of this thread are done before it arrives on full1 for the next tile, and the next GEMM 1 is issued
+        // only after all 128 arrivals: nothing overwrites D1 / D2 early
         tc_fence_before();
-        group_sync(gid);
     }
 
     __syncthreads();
@@ -431,7 +455,7 @@ int nca_step_tc(const NcaArgs &a, cudaStream_t st) {
     const int tiles_x = ceil_div(a.W, 32), tiles_y = ceil_div(a.H, 4);
     const long long ntiles = (long long)tiles_x * tiles_y * a.B;
     const int grid = (int)std::min<long long>(ceil_div64(ntiles, NG), (long long)num_sms());
-    nca_update_tc_kernel<<<grid, 128 * NG, SM_TOTAL, st>>>(a, tiles_x, tiles_y);
+    nca_update_tc_kernel<<<grid, NTHREADS, SM_TOTAL, st>>>(a, tiles_x, tiles_y);
     B200CA_LAUNCH_CHECK("nca_update_tc_kernel");
     note_variant("nca_update_tc<grid=%d>", grid);
     return 0;
