@@ -170,13 +170,18 @@ class ClockSampler:
 # workload descriptions shared by BOTH arms (the reference arm prints the same `config` without importing pyca_b200)
 # ------------------------------------------------------------------------------------------------
 SHAPES = {
-    "lenia_1k": ("lenia", 1, 1024, 1024), "lenia3_1k": ("lenia", 3, 1024, 1024), "lenia_4k": ("lenia", 1, 4096, 4096),
+    "lenia_1k": ("lenia", 1, 1024, 1024), "lenia_1k_single": ("lenia", 1, 1024, 1024), "lenia3_1k": ("lenia", 3, 1024, 1024), "lenia_4k": ("lenia", 1, 4096, 4096),
     "lenia_seg": ("lenia", 1, 4096, 3976), "lenia_16k": ("lenia", 1, 16384, 16384),
     "gol_64k": ("gol", 0, 65536, 65536), "gol_16k": ("gol", 0, 16384, 16384), "gol_250": ("gol", 0, 250, 250),
     "mace_xchan_4k": ("xchan", 3, 4096, 4096), "mace_xchan_1k": ("xchan", 3, 1024, 1024),
     "nca_256": ("nca", 16, 128, 128), "flow_lenia_1k": ("flow", 3, 1024, 1024), "flow_lenia_4k": ("flow", 3, 4096, 4096),
 }
-REPLICA_WORKLOADS = ("lenia_1k",)          # one independent world per GPU at N > 1
+REPLICA_WORKLOADS = ("lenia_1k",)          # independent worlds on every GPU at N > 1 (weak scaling, no communication)
+# The headline workload steps a BATCH of independent 1024^2 worlds per GPU through the batch dimension of the Automaton API
+# (`Lenia(size=(B,H,W))`, lenia.py:19-29, parameters by `LeniaParams.expand(B)`, batch_params.py:217-236): 24 worlds = 201 MB
+# of state (in + out), i.e. inputs larger than L2 by construction, and enough CTAs to fill the machine -- a single 1024^2
+# world is a latency measurement (one wave of CTAs, ~20 us per step whatever the kernel does; reported as `single_world`).
+LENIA1K_BATCH = 24
 SLAB_WORKLOADS = ("lenia_16k", "lenia_4k", "gol_64k", "gol_16k")
 GOL_GHOST = 64
 L2_BYTES = 126 << 20
@@ -194,6 +199,12 @@ def static_config(name, n):
     fam, C, H, W = SHAPES[name]
     if fam == "lenia":
         per_rank = H * W * C * 8 // (1 if name in REPLICA_WORKLOADS else n)
+        if name in REPLICA_WORKLOADS:
+            return {"workload": name, "shape": [LENIA1K_BATCH, C, H, W], "k_size": 31,
+                    "params": "demo_lenia/abominable_mongolic" + (f" sliced to C={C}" if C != 3 else "") + f", expanded to {LENIA1K_BATCH} worlds",
+                    "partition": (f"{LENIA1K_BATCH} independent {H}x{W} worlds per GPU stepped together through the batch dimension of the "
+                                  f"Automaton API (size=(B,H,W)), {n} GPU(s), no communication"),
+                    "l2": f"inputs larger than L2: {LENIA1K_BATCH * H * W * C * 8 >> 20} MB of state read + written per step, no flush"}
         cfg = {"workload": name, "shape": [1, C, H, W], "k_size": 31,
                "params": "demo_lenia/abominable_mongolic" + (f" sliced to C={C}" if C != 3 else ""),
                "partition": "single GPU" if n == 1 else (f"{n} independent worlds, one per GPU, no communication"
@@ -234,7 +245,7 @@ class RefArm:
         self.fam, self.C, H, W = SHAPES[name]
         cap = {"lenia": 4096, "gol": 4096, "xchan": 1024, "flow": 1024, "nca": 128}[self.fam]
         self.H, self.W = min(H, cap), min(W, cap)
-        self.B = 16 if self.fam == "nca" else 1
+        self.B = 16 if self.fam == "nca" else (LENIA1K_BATCH if name in REPLICA_WORKLOADS else 1)
         self.kind = "reference"
         try:
             sys.path.insert(0, os.path.join(ROOT, "baseline"))
@@ -276,19 +287,32 @@ class RefArm:
             if C != 3:
                 d = {k: (v[:, :C, :C].clone() if isinstance(v, torch.Tensor) else v) for k, v in P.param_dict.items()}
                 P = R.LeniaParams(param_dict=d, channels=C)
-            s0 = torch.rand(1, C, self.H, self.W, generator=g) * (1.5 if self.fam == "flow" else 1.0)
             cls = {"lenia": R.Lenia, "xchan": R.MaCELeniaXChan, "flow": R.FlowLenia}[self.fam]
-            kw = dict(num_channels=C, params=P, state_init=s0, device="cpu")
+            kw = dict(num_channels=C, params=P, device="cpu")
             if self.fam == "lenia":
                 kw["dt"] = 0.1
-            self.auto = cls((self.H, self.W), **kw)
+            if self.B > 1:
+                # The batch of worlds, stepped ONE WORLD AT A TIME: on the host that is the reference's faster mode -- one
+                # (B,H,W) automaton with expanded parameters works on 24 x 8 MB spectra at once, falls out of the caches and
+                # ran 4x slower per cell here (0.056 vs 0.23 GCUPS on 8 cores) -- so the CPU arm gets its best case.
+                self.autos = [cls((self.H, self.W), state_init=torch.rand(1, C, self.H, self.W, generator=g), **kw) for _ in range(self.B)]
+
+                def step_all():
+                    for a in self.autos:
+                        a.step()
+
+                self.step = step_all
+                return
+            s0 = torch.rand(1, C, self.H, self.W, generator=g) * (1.5 if self.fam == "flow" else 1.0)
+            self.auto = cls((self.H, self.W), state_init=s0, **kw)
         self.step = self.auto.step
 
     def cells_per_step(self):
         return self.B * self.H * self.W
 
     def sample(self):
-        what = {"lenia": f"Lenia C={self.C} {self.H}x{self.W} Lenia.step() (lenia.py:430-469)",
+        what = {"lenia": (f"{self.B} worlds, one Lenia.step() each (world by world: the host's faster mode) of " if self.B > 1 else "") +
+                         f"Lenia C={self.C} {self.H}x{self.W} Lenia.step() (lenia.py:430-469)",
                 "xchan": f"MaCE-XChan C=3 {self.H}x{self.W} MaCELeniaXChan.step() (mace_lenia_xchan.py:59-76, macelenia.py:89-159)",
                 "flow": f"FlowLenia C=3 {self.H}x{self.W} FlowLenia.step() (flow_lenia.py:246-253)",
                 "gol": f"GoL {self.H}x{self.W} int32 CA2D.step() (ca2d.py:195-209)",
@@ -547,6 +571,73 @@ class LeniaWL(Workload):
 
     def cpu_sample(self):
         return f"Lenia C={self.C} {self.cH}x{self.cW} oracle step (torch fft2 path of lenia.py:430-469)"
+
+
+class LeniaBatchWL(LeniaWL):
+    """The headline workload (BASELINE configs[1]): LENIA1K_BATCH independent 1024x1024 single-channel worlds per GPU, stepped
+    together through the batch dimension of the Automaton API -- `Lenia(size=(B,H,W), params=params.expand(B))`, the
+    reference's own way of running several worlds (lenia.py:19-29, batch_params.py:217-236).  One step = one generation of
+    every world = one kernel launch; 201 MB of state are read + written per step (inputs larger than L2)."""
+
+    def __init__(self, rank, world, device, H, W, C=1, name="lenia_1k"):
+        super().__init__(rank, world, device, H, W, C, name, replicas=True)
+        self.replicas = world > 1
+        self.Bw = LENIA1K_BATCH
+
+    def setup(self):
+        import pyca_b200
+
+        self.params = self._params()
+        g = torch.Generator().manual_seed(self.rank)
+        st = torch.rand(self.Bw, self.C, self.H, self.W, generator=g)
+        self.h_state = st[:1].clone().pin_memory()
+        self.auto = pyca_b200.Lenia((self.Bw, self.H, self.W), num_channels=self.C, params=self.params.expand(self.Bw), state_init=st,
+                                    device=self.device, conv_path=os.environ.get("B200CA_LENIA_PATH", "auto"))
+        self.auto.step()
+        self.slab = None
+        self.rotating = True      # (inputs exceed L2 by construction: no flush)
+        self.graph = None
+
+    def step(self):
+        self.auto.step()
+
+    def run(self, k):
+        for _ in range(k):
+            self.auto.step()
+
+    def issue_note(self):
+        return "one launch per step (ctypes call from Python), all worlds of the batch in the same launch"
+
+    def cells_per_step(self):
+        return self.Bw * self.H * self.W * self.world
+
+    def launches_per_step(self):
+        return 1 if self.auto.conv_algo in ("march", "direct") else self._fft_kernels()
+
+    def dominant(self):
+        cells = self.Bw * self.H * self.W
+        k = {"march": "lenia_march_kernel", "fft_rows": "lenia_fft_rows + lenia_fft_firinv (whole step)", "direct": "lenia_conv_kernel"}
+        return {"kernel": k[self.auto.conv_algo], "bytes": cells * self.C * 8, "fma": 0}
+
+    def e2e_setup(self):
+        import pyca_b200
+
+        # end to end is per WORLD: each 1024^2 world travels host -> device -> step -> host on its own (LeniaHostPipe lanes)
+        self.auto1 = pyca_b200.Lenia((self.H, self.W), num_channels=self.C, params=self.params, state_init=self.h_state, device=self.device)
+        self.h_out = torch.empty(1, self.C, self.H, self.W).pin_memory()
+        _pipe_setup(self, self.auto1, (1, self.C, self.H, self.W))
+
+    def e2e_cells(self):
+        return self.H * self.W * self.world
+
+    def e2e_step_sync(self):
+        a = self.auto1
+        a.state = self.h_state.to(self.device, non_blocking=True)
+        a.step()
+        self.h_out.copy_(a.state, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        n = self.h_state.numel() * 4
+        return n, n
 
 
 class GolWL(Workload):
@@ -940,7 +1031,9 @@ class NcaWL(Workload):
 
 def make_workload(name, rank, world, device):
     if name == "lenia_1k":
-        return LeniaWL(rank, world, device, 1024, 1024, 1, name, replicas=True)
+        return LeniaBatchWL(rank, world, device, 1024, 1024, 1, name)
+    if name == "lenia_1k_single":
+        return LeniaWL(rank, world, device, 1024, 1024, 1, name)
     if name == "lenia3_1k":
         return LeniaWL(rank, world, device, 1024, 1024, 3, name)
     if name == "lenia_4k":
@@ -1246,7 +1339,7 @@ def main():
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
         extras = {}
-        for other in ["lenia3_1k", "gol_250", "gol_64k", "mace_xchan_4k", "nca_256", "flow_lenia_4k"]:
+        for other in ["lenia_1k_single", "lenia3_1k", "gol_250", "gol_64k", "mace_xchan_4k", "nca_256", "flow_lenia_4k"]:
             if other == name:
                 continue
             try:

@@ -61,6 +61,16 @@ class LeniaParams:
                 self.param_dict[k] = v.to(device)
         return self
 
+    def expand(self, batch_size):
+        """Parameters with batch size 1 repeated to `batch_size` worlds (the reference's BatchParams.expand,
+        automata/utils/batch_params.py:217-236): how PyCA steps several worlds with one parameter set, `size=(B,H,W)`."""
+        assert self.batch_size == 1, f"Batch size must be 1 to expand, here is {self.batch_size}"
+        new = {}
+        for key, v in self.param_dict.items():
+            new[key] = v.repeat(batch_size, *([1] * (v.dim() - 1))) if isinstance(v, torch.Tensor) else v
+        channels = self.param_dict["weights"].shape[-1]
+        return type(self)(param_dict=new, channels=channels, device=getattr(self, "device", "cpu"))
+
     def __getitem__(self, k):
         return self.param_dict[k]
 
