@@ -166,7 +166,8 @@ int b200ca_lenia_step_fft_phase(const float *state_in, float *state_out, const f
 #define B200CA_ALGO_MARCH 2
 /* which of the three convolution paths conv_path='auto' takes for B worlds of HxW with NS = C*k_mult source kernels per
  * destination plane (a rule fitted to B200 measurements; Gaussian growth -- Fourier growth functions are direct-only) */
-int b200ca_lenia_pick_algo(int B, int NS, int H, int W);
+int b200ca_lenia_pick_algo(int B, int NS, int H, int W);                 /* k_size 31 */
+int b200ca_lenia_pick_algo_ks(int B, int NS, int H, int W, int k_size);  /* per kernel size (lenia.py:143-168 k_size_override) */
 int b200ca_lenia_march_supported(int H, int W);
 int64_t b200ca_lenia_march_kernel_elems(int B, int C, int k_mult);
 int b200ca_lenia_march_prepare_kernel(const float *K, float *Kf, int B, int C, int k_mult, int ks, void *stream);

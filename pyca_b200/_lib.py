@@ -49,6 +49,7 @@ SIGNATURES = {
     "b200ca_lenia_step_fft_phase": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                             c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p]),
     "b200ca_lenia_pick_algo": (c_int, [c_int, c_int, c_int, c_int]),
+    "b200ca_lenia_pick_algo_ks": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "b200ca_lenia_march_supported": (c_int, [c_int, c_int]),
     "b200ca_lenia_march_kernel_elems": (c_int64, [c_int, c_int, c_int]),
     "b200ca_lenia_march_prepare_kernel": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

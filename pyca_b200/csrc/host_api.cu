@@ -156,7 +156,7 @@ extern "C" int b200ca_lenia_pipe_create(void **pipe, const float *K, const float
     p->dev = dev;
     p->B = B, p->C = C, p->km = k_mult, p->H = H, p->W = W, p->family = family, p->depth = depth;
     p->dt = dt, p->beta = beta, p->alpha = alpha;
-    p->algo = b200ca_lenia_pick_algo(B, C * k_mult, H, W);
+    p->algo = b200ca_lenia_pick_algo_ks(B, C * k_mult, H, W, ks);
     p->fft = p->algo == B200CA_ALGO_FFT_ROWS;
     p->dbytes = (size_t)B * C * H * W * sizeof(float);
     const int rc = pipe_build(p, K, mu, sigma, weights, ks);

@@ -16,9 +16,27 @@
 //     periodic frame of the output buffer so the next step needs no wrap logic.
 // Algorithmic traffic 8 B/cell/channel; the kernel is bound by the fp32 FMA pipe (496 FMA per
 // cell and channel pair), not by HBM -- see DESIGN.md.
+#include <mutex>
+#include <unordered_map>
+
 #include "tma.cuh"
 
 namespace b200ca {
+
+// Kernel radius class of a prepared tap table, remembered per (device pointer) by b200ca_lenia_prepare_kernel so that the step
+// entry point keeps its signature: the taps are embedded in 31 x 31 either way, the class only selects how much of that
+// footprint the kernel evaluates (3, 5, 7, 9 or 15).  Unknown pointers (tables prepared elsewhere) take the full radius.
+static std::mutex g_rk_mutex;
+static std::unordered_map<const void *, int> g_rk_of;
+static int radius_class(int ks) {
+    const int r = ks / 2;
+    return r <= 3 ? 3 : r <= 5 ? 5 : r <= 7 ? 7 : r <= 9 ? 9 : 15;
+}
+static int radius_of_table(const void *kprep) {
+    std::lock_guard<std::mutex> lk(g_rk_mutex);
+    auto it = g_rk_of.find(kprep);
+    return it == g_rk_of.end() ? 15 : it->second;
+}
 
 constexpr int F = B200CA_FRAME;
 constexpr int R = 15;            // kernel radius handled by the direct path (k_size <= 31)
@@ -86,7 +104,9 @@ __device__ __forceinline__ void store_mirrors(float *__restrict__ plane, int H, 
 
 // GARBI = true: the growth of a pair is its Fourier series (g_arbi); kept out of the Gaussian instantiation, whose register
 // allocation and code are what the direct path was tuned with.
-template <int NW, bool GARBI>
+// RK: radius of the kernel actually evaluated (k_size <= 2 RK + 1; the prepared taps are embedded in 31 x 31, zero outside): the
+// folded rows dy = 0..RK and the taps dx = -RK..RK only -- (RK+1)(2RK+1) FMAs per cell and kernel pair instead of 16 x 31.
+template <int NW, bool GARBI, int RK = R>
 __global__ void __launch_bounds__(32 * NW) lenia_conv_kernel(const CUtensorMap *__restrict__ tmap, const LeniaArgs a) {
     constexpr int TH = 8 * NW;
     constexpr int TROWS = TH + 2 * R;
@@ -142,13 +162,17 @@ __global__ void __launch_bounds__(32 * NW) lenia_conv_kernel(const CUtensorMap *
 #pragma unroll
         for (int k = 0; k < STRIP; ++k) acc[k] = 0.f;
 
+        // columns of the row segment / taps that a radius-RK kernel touches (float4 granularity)
+        constexpr int D0 = R - RK, D1 = R + RK;                                  // tap columns dx
+        constexpr int Q0 = (D0 + XOFF) / 4, Q1 = (STRIP - 1 + D1 + XOFF) / 4;     // float4s of the input segment
+        constexpr int T0 = D0 / 4, T1 = D1 / 4;                                   // float4s of the tap row
 #pragma unroll 1
-        for (int dy = 0; dy <= R; ++dy) {
+        for (int dy = 0; dy <= RK; ++dy) {
             float sv[NLD * 4];
             {
                 const float4 *rp = reinterpret_cast<const float4 *>(tl + dy * SROW);
 #pragma unroll
-                for (int q = 0; q < NLD; ++q) {
+                for (int q = Q0; q <= Q1; ++q) {
                     float4 v = rp[q];
                     sv[4 * q] = v.x; sv[4 * q + 1] = v.y; sv[4 * q + 2] = v.z; sv[4 * q + 3] = v.w;
                 }
@@ -156,7 +180,7 @@ __global__ void __launch_bounds__(32 * NW) lenia_conv_kernel(const CUtensorMap *
             if (dy > 0) {
                 const float4 *rm = reinterpret_cast<const float4 *>(tl - dy * SROW);
 #pragma unroll
-                for (int q = 0; q < NLD; ++q) {
+                for (int q = Q0; q <= Q1; ++q) {
                     float4 v = rm[q];
                     sv[4 * q] += v.x; sv[4 * q + 1] += v.y; sv[4 * q + 2] += v.z; sv[4 * q + 3] += v.w;
                 }
@@ -165,16 +189,16 @@ __global__ void __launch_bounds__(32 * NW) lenia_conv_kernel(const CUtensorMap *
             {
                 const float4 *kp = reinterpret_cast<const float4 *>(tp + dy * KPITCH);
 #pragma unroll
-                for (int q = 0; q < KPITCH / 4; ++q) {
+                for (int q = T0; q <= T1; ++q) {
                     float4 v = kp[q];
                     tv[4 * q] = v.x; tv[4 * q + 1] = v.y; tv[4 * q + 2] = v.z; tv[4 * q + 3] = v.w;
                 }
             }
             float p[STRIP];
 #pragma unroll
-            for (int k = 0; k < STRIP; ++k) p[k] = tv[0] * sv[k + XOFF];
+            for (int k = 0; k < STRIP; ++k) p[k] = tv[D0] * sv[k + D0 + XOFF];
 #pragma unroll
-            for (int dx = 1; dx < KW; ++dx) {
+            for (int dx = D0 + 1; dx <= D1; ++dx) {
 #pragma unroll
                 for (int k = 0; k < STRIP; ++k) p[k] = fmaf(tv[dx], sv[k + dx + XOFF], p[k]);
             }
@@ -319,7 +343,7 @@ __global__ void garbi_stats_init_kernel(float *stats, int n) {
     }
 }
 
-template <int NW, bool GARBI>
+template <int NW, bool GARBI, int RK = R>
 static int launch_conv(const CUtensorMap *tm, const LeniaArgs &a, int tiles_y, cudaStream_t st) {
     constexpr int TH = 8 * NW;
     constexpr size_t smem = (size_t)2 * (((TH + 2 * R) * SROW + 31) / 32 * 32) * 4 + 2 * KPREP * 4 + 64;
@@ -327,13 +351,13 @@ static int launch_conv(const CUtensorMap *tm, const LeniaArgs &a, int tiles_y, c
     int dev = 0;
     B200CA_CUDA(cudaGetDevice(&dev));
     if (!attr_set[dev & 63]) {
-        B200CA_CUDA(cudaFuncSetAttribute(lenia_conv_kernel<NW, GARBI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200CA_CUDA(cudaFuncSetAttribute(lenia_conv_kernel<NW, GARBI, RK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[dev & 63] = true;
     }
     dim3 grid(ceil_div(a.W, TW), tiles_y, a.B * a.C);
-    lenia_conv_kernel<NW, GARBI><<<grid, 32 * NW, smem, st>>>(tm, a);
+    lenia_conv_kernel<NW, GARBI, RK><<<grid, 32 * NW, smem, st>>>(tm, a);
     B200CA_LAUNCH_CHECK("lenia_conv_kernel");
-    note_variant("lenia_conv<%d,%s>", NW, GARBI ? "garbi" : "gauss");
+    note_variant("lenia_conv<%d,%s,R=%d>", NW, GARBI ? "garbi" : "gauss", RK);
     return 0;
 }
 
@@ -389,6 +413,10 @@ extern "C" int b200ca_lenia_prepare_kernel(const float *K, float *Kprep, int B, 
         set_error("lenia_prepare_kernel: kernel is not symmetric under row reversal; the folded direct path needs K[dy]==K[-dy]");
         return B200CA_E_UNSUPPORTED;
     }
+    {
+        std::lock_guard<std::mutex> lk(g_rk_mutex);
+        g_rk_of[Kprep] = radius_class(ks);
+    }
     return 0;
 }
 
@@ -423,11 +451,21 @@ static int lenia_step_impl(LeniaArgs a, int B, int C, int k_mult, int H, int W, 
     if (rc) return rc;
     const int ty = tile_row_end - tile_row_begin;
     cudaStream_t st = as_stream(stream);
+    const int rk = radius_of_table(a.kprep);
     if (a.gmode == G_GAUSS) {
         switch (nw) {
-            case 2: return launch_conv<2, false>(tm, a, ty, st);
-            case 4: return launch_conv<4, false>(tm, a, ty, st);
-            default: return launch_conv<8, false>(tm, a, ty, st);
+#define B200CA_CONV_RK(NWV)                                                   \
+    switch (rk) {                                                             \
+        case 3: return launch_conv<NWV, false, 3>(tm, a, ty, st);             \
+        case 5: return launch_conv<NWV, false, 5>(tm, a, ty, st);             \
+        case 7: return launch_conv<NWV, false, 7>(tm, a, ty, st);             \
+        case 9: return launch_conv<NWV, false, 9>(tm, a, ty, st);             \
+        default: return launch_conv<NWV, false, R>(tm, a, ty, st);            \
+    }
+            case 2: B200CA_CONV_RK(2)
+            case 4: B200CA_CONV_RK(4)
+            default: B200CA_CONV_RK(8)
+#undef B200CA_CONV_RK
         }
     }
     switch (nw) {

@@ -609,14 +609,19 @@ using namespace b200ca;
 
 extern "C" int b200ca_lenia_march_supported(int H, int W) { return (H >= 2 * march::F && W >= 2 * march::F) ? 1 : 0; }
 
-// conv_path = 'auto' (profiles/r02_conv_paths.md has the measurements behind the rule):
-//   one source kernel per destination: the two-kernel hybrid for small worlds (a single wave of CTAs: shorter serial chain),
-//   the marching kernel otherwise;  several sources: the hybrid (its fused kernel sums the sources in registers; the marching
-//   kernel accumulates through the output planes, one launch per source);  whatever the preferred path cannot do falls to the
-//   next one, the direct convolution last.
-extern "C" int b200ca_lenia_pick_algo(int B, int NS, int H, int W) {
+// conv_path = 'auto' (profiles/r02_conv_paths.md has the measurements behind the rule), by kernel size, sources and world size:
+//   k_size <= 7: the direct kernel (evaluates the 7 x 7 footprint only: 28 folded FMAs per cell and pair instead of 496);
+//   k_size <= 11: direct, except for big single-source worlds (marching kernel) and small multi-source ones (hybrid);
+//   larger kernels (all of demo_data is k_size 31) take an FFT path, whose cost does not depend on the radius:
+//     one source kernel per destination: the two-kernel hybrid for small worlds (a single wave of CTAs: shorter serial
+//     chain), the marching kernel otherwise;  several sources: the hybrid (its fused kernel sums the sources in registers;
+//     the marching kernel accumulates through the output planes, one launch per source);
+//   whatever the preferred path cannot do falls to the next one, the direct convolution last.
+extern "C" int b200ca_lenia_pick_algo_ks(int B, int NS, int H, int W, int ks) {
     const bool march_ok = b200ca_lenia_march_supported(H, W) != 0, rows_ok = b200ca_lenia_fft_length(H, W) > 0;
     const bool small = (long long)B * H * W <= 1536LL * 1536LL;
+    if (ks <= 7) return B200CA_ALGO_DIRECT;
+    if (ks <= 11 && !(NS == 1 && !small && march_ok) && !(NS > 1 && small && rows_ok)) return B200CA_ALGO_DIRECT;
     if (NS == 1) {
         if (rows_ok && small) return B200CA_ALGO_FFT_ROWS;
         return march_ok ? B200CA_ALGO_MARCH : (rows_ok ? B200CA_ALGO_FFT_ROWS : B200CA_ALGO_DIRECT);
@@ -624,6 +629,7 @@ extern "C" int b200ca_lenia_pick_algo(int B, int NS, int H, int W) {
     if (rows_ok) return B200CA_ALGO_FFT_ROWS;
     return march_ok ? B200CA_ALGO_MARCH : B200CA_ALGO_DIRECT;
 }
+extern "C" int b200ca_lenia_pick_algo(int B, int NS, int H, int W) { return b200ca_lenia_pick_algo_ks(B, NS, H, W, 31); }
 
 extern "C" int64_t b200ca_lenia_march_kernel_elems(int B, int C, int k_mult) {
     return (int64_t)B * C * k_mult * C * march::KROWS * march::ROW4 * 2;

@@ -112,7 +112,7 @@ class _LeniaEngine:
                       _lib.current_stream(dev))
             rows_ok = self.L.b200ca_lenia_fft_length(fs.H, fs.W) > 0 and self.garbi is None
             march_ok = self.L.b200ca_lenia_march_supported(fs.H, fs.W) > 0 and self.garbi is None
-            self.algo = "direct" if self.garbi is not None else pick_conv_algo(fs.B, fs.C * self.k_mult, fs.H, fs.W, march_ok, rows_ok)
+            self.algo = "direct" if self.garbi is not None else pick_conv_algo(fs.B, fs.C * self.k_mult, fs.H, fs.W, march_ok, rows_ok, ks)
             self.use_fft = self.algo != "direct"
             if self.algo == "fft_rows":
                 self.kfft = torch.empty(self.L.b200ca_lenia_fft_kernel_elems(fs.B, fs.C, self.k_mult, fs.H, fs.W), dtype=torch.float32,

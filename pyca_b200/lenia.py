@@ -51,7 +51,7 @@ def garbi_tables(p, B, C, k_mult):
             "stats": torch.zeros((n, 2), dtype=torch.float32, device=co.device)}
 
 
-def pick_conv_algo(B, NS, H, W, march_ok=True, rows_ok=True):
+def pick_conv_algo(B, NS, H, W, march_ok=True, rows_ok=True, k_size=31):
     """conv_path='auto': which convolution kernel steps a (B, C, H, W) world with NS = C * k_mult source kernels per
     destination.  Measured on B200 (profiles/r02_conv_paths.md; all paths agree with the oracle to <= 1e-5):
       * one source (C = 1): the marching kernel (lenia_march.cu) wins from 4096^2 up (118 vs 140 us at 4096^2, 1.26 vs 1.58 ms
@@ -59,10 +59,11 @@ def pick_conv_algo(B, NS, H, W, march_ok=True, rows_ok=True):
         two-kernel hybrid (lenia_fft.cu, 512-thread small-world variant) has the shorter serial chain: 19.6 vs 22.1 us;
       * several sources: the hybrid's fused kernel keeps the per-destination sum over sources in registers, the marching kernel
         accumulates it through the output planes, one launch per source (843 vs 932 us at 4096^2, C = 3);
-      * the direct convolution (lenia.cu) is FMA-bound at R = 15 and serves what the FFT paths do not (Fourier growth
-        functions, worlds narrower than 32)."""
+      * the direct convolution (lenia.cu) is FMA-bound at R = 15 (385 us at 4096^2) but evaluates only the radius class of the
+        kernel: k_size <= 7 runs in 104 us at 4096^2 and beats both FFT paths, whose cost does not depend on the radius; it also
+        serves what the FFT paths do not (Fourier growth functions, worlds narrower than 32)."""
     del march_ok, rows_ok   # (the library applies the same support checks)
-    return ("direct", "fft_rows", "march")[_lib.lib().b200ca_lenia_pick_algo(int(B), int(NS), int(H), int(W))]
+    return ("direct", "fft_rows", "march")[_lib.lib().b200ca_lenia_pick_algo_ks(int(B), int(NS), int(H), int(W), int(k_size))]
 
 
 def conv_garbi(fs, dst, kprep, weights, g, k_mult, dt, mode):
@@ -274,7 +275,7 @@ class Lenia(Automaton):
         if self.g_arbi:
             self.conv_algo = "direct"
         elif self.conv_path == "auto":
-            self.conv_algo = pick_conv_algo(self.batch, self.C * self.k_mult, self.h, self.w, march_ok, rows_ok)
+            self.conv_algo = pick_conv_algo(self.batch, self.C * self.k_mult, self.h, self.w, march_ok, rows_ok, self.k_size)
         else:
             self.conv_algo = {"fft": "march", "fft_rows": "fft_rows", "direct": "direct"}[self.conv_path]
         self.use_fft = self.conv_algo != "direct"

@@ -412,3 +412,31 @@ def test_constructors_without_params_or_state():
     m0 = float(m.total_mass())
     m.step()
     assert abs(float(m.total_mass()) - m0) <= 1e-5 * m0
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("ks", [5, 7, 13, 21, 27])
+def test_lenia_kernel_sizes_vs_oracle(ks, path):
+    """k_size below 31 (Lenia.update_params(k_size_override), lenia.py:143-168): the direct kernel evaluates only the radius
+    class of the kernel (3, 5, 7, 9, 15), the FFT paths embed it in their 31-tap footprint; all against the oracle."""
+    import pyca_b200
+
+    d, _, mu, sg, w = _oracle_params()
+    d = dict(d)
+    d["k_size"] = ks
+    K = orc.lenia_kernel(d["beta"], d["mu_k"], d["sigma_k"], ks)
+    g = torch.Generator().manual_seed(ks)
+    shape = (96, 300)
+    s0 = torch.rand(1, 3, *shape, generator=g)
+    a = pyca_b200.Lenia(shape, params=d, state_init=s0, device="cuda", conv_path=path)
+    assert a.k.shape[-1] == ks
+    from pyca_b200 import _lib
+    _lib.variants(reset=True)
+    a.step()
+    got = _lib.variants(reset=True)
+    if path == "direct":
+        rk = 3 if ks <= 7 else 5 if ks <= 11 else 7 if ks <= 15 else 9 if ks <= 19 else 15
+        assert any(f"R={rk}>" in v for v in got), got
+    ref = orc.lenia_step(s0, K, mu, sg, w, 0.1)
+    err = (a.state.cpu() - ref).abs().max().item()
+    assert err <= TOL, f"ks={ks} {path}: {err:.2e}"
