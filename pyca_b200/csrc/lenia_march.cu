@@ -446,10 +446,13 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
     const bool col_ok = tid >= HALO && tid < N - HALO && xw < a.W;
     const bool lenia = a.mode == B200CA_MODE_LENIA;
     // CTAs that own cells with periodic images (first / last columns, first / last rows of a torus) or a partial last band
-    const bool edge = strip == 0 || col0 - HALO + N - HALO > a.W - F || y0 + 2 * a.Lp > a.H ||
-                      ((a.row_wrap || a.peer_up_out || a.peer_dn_out) && (y0 < F || y0 + 2 * a.Lp > a.H - F));
+    // (decided per block of 8 row pairs: in a 256-row band only the first / last 16 rows of the world take the slow path)
+    const bool edge_x = strip == 0 || col0 - HALO + N - HALO > a.W - F;
+    const bool edge_rows = a.row_wrap || a.peer_up_out || a.peer_dn_out;
 #pragma unroll 1
     for (int it = 0; it < a.niter; ++it) {
+        const int ra0 = y0 + FT * it, rb0 = ra0 + a.Lp;   // first rows of the two halves of this block
+        const bool edge = edge_x || rb0 + FT > a.H || (edge_rows && (ra0 < F || rb0 + FT > a.H - F || (ra0 + FT > a.H - F) || rb0 < F));
 #pragma unroll 1
         for (int j = 0; j < (SINGLE ? 1 : a.C); ++j) {
             const int pidx = (b * a.NS + a.src) * a.C + j;
