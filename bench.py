@@ -664,7 +664,18 @@ class GolWL(Workload):
             self.pw.random_fill(seed=2024)
             self.slab = None
         else:
-            self.slab = GolSlabCUDA(self.H, self.W, self.rank, self.world, self.ghost, self.device)
+            # ghost rows pushed by one P2P kernel per exchange (symmetric memory); NCCL send/recv slabs as the fallback
+            from pyca_b200.slab import GolSlabP2P
+
+            self.halo = "p2p"
+            try:
+                if os.environ.get("B200CA_SLAB_HALO", "p2p") != "p2p":
+                    raise RuntimeError("forced")
+                self.slab = GolSlabP2P(self.H, self.W, self.rank, self.world, self.ghost, self.device)
+            except Exception as e:
+                log(f"P2P-halo GoL slabs unavailable ({e!r}): NCCL send/recv slabs")
+                self.halo = "nccl"
+                self.slab = GolSlabCUDA(self.H, self.W, self.rank, self.world, self.ghost, self.device)
             self.slab.random_fill(seed=2024)
 
     def step(self):
@@ -1445,8 +1456,8 @@ def main():
                 ent["gcups"] = sw.cells_per_step() / (ms_n * 1e-3) / 1e9
                 ent["config"] = sw.config()
                 if hasattr(sw, "halo"):
-                    ent["halo"] = ("P2P stores + arrival counters from inside the step kernel, one launch per step" if sw.halo == "p2p"
-                                   else "NCCL send/recv per step on a side stream")
+                    ent["halo"] = ("P2P stores + arrival counters over NVLink (symmetric memory), no host-side exchange" if sw.halo == "p2p"
+                                   else "NCCL send/recv on a side stream")
                 b200lib.variants(reset=True)
                 sw.step()
                 ent["kernels"] = b200lib.variants(reset=True)

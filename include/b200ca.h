@@ -191,6 +191,17 @@ int b200ca_lenia_step_march_slab(const float *state_in, float *state_out, const 
                                  const uint32_t *wait_top, const uint32_t *wait_bot, uint32_t wait_target, uint32_t *err_flag,
                                  void *stream);
 
+/* One halo exchange of a row slab as one kernel per rank (csrc/halo.cu): copies `nbytes` (multiple of 16) from src_up / src_dn
+ * (this rank's first / last owned rows) into dst_up / dst_dn (the up neighbour's bottom ghost rows / the down neighbour's top
+ * ghost rows, peer-mapped) and synchronises with both neighbours through counters in peer-mapped memory: `up_ready` / `dn_ready`
+ * and `up_arrived` / `dn_arrived` are slots in the NEIGHBOURS' counter blocks that this rank bumps, `my_ready[2]` / `my_arrived[2]`
+ * this rank's own ([0] written by the up neighbour, [1] by the down neighbour); `epoch` = 1, 2, ... counts the exchanges, every
+ * rank issues the same sequence.  When the kernel ends this rank's ghost rows are current.  `ticket`: 4 zeroed bytes of local
+ * scratch; a wait longer than ~4 s sets *err_flag. */
+int b200ca_halo_push(const void *src_up, void *dst_up, const void *src_dn, void *dst_dn, int64_t nbytes, uint32_t *up_ready,
+                     uint32_t *dn_ready, const uint32_t *my_ready, uint32_t *up_arrived, uint32_t *dn_arrived,
+                     const uint32_t *my_arrived, uint32_t epoch, uint32_t *ticket, uint32_t *err_flag, void *stream);
+
 /* Mass-conserving redistribution (+ optional cross-channel mixing).  Replaces
  * MaCELenia._mace_step (macelenia.py:89-120) after the affinity, and
  * MaCELeniaXChan._cross_chan_step (mace_lenia_xchan.py:68-76) when alpha_on != 0:

@@ -244,6 +244,55 @@ class GolSlabCUDA(GolSlab):
         return int(cnt.item())
 
 
+class GolSlabP2P(GolSlabCUDA):
+    """GolSlabCUDA whose ghost-row exchange is ONE kernel per rank (csrc/halo.cu): the boundary rows are stored straight into the
+    neighbours' ghost rows over NVLink and the ranks synchronise through counters in symmetric memory -- no NCCL send/recv, no
+    host synchronisation between the generations of consecutive batches."""
+
+    def __init__(self, H, W, rank, world, ghost=16, device="cuda", s_mask=0b1100, b_mask=0b1000, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        super().__init__(H, W, rank, world, ghost, "meta", s_mask, b_mask)
+        self.device = torch.device(device)
+        self.group = group if group is not None else dist.group.WORLD
+        n = self.rows * self.stride
+        self._n = n
+        self._sym = symm.empty(2 * n + 64, dtype=torch.int32, device=self.device)
+        self._sym.zero_()
+        self._hdl = symm.rendezvous(self._sym, self.group)
+        self.bufs = [self._sym[i * n:(i + 1) * n].view(self.rows, self.stride) for i in range(2)]
+        self._ptrs = [b.data_ptr() for b in self.bufs]
+        self._counters = self._sym[2 * n:2 * n + 64]   # [0:2] ready, [2:4] arrived, [4] ticket, [5] error
+        base = list(self._hdl.buffer_ptrs)
+        self._base = base
+        self._up, self._down = ring_neighbours(rank, world)
+        self._cnt = 2 * n * 4
+        self.epoch = 0
+
+    def exchange(self, group=None):
+        from . import _lib
+
+        g, hl, row = self.g, self.hl, self.stride * 4
+        me, up, dn = self._base[self.rank], self._base[self._up], self._base[self._down]
+        buf = self.cur * self._n * 4
+        self.epoch += 1
+        with _lib.device_guard(self.device):
+            _lib.call("b200ca_halo_push", me + buf + g * row, up + buf + (hl + g) * row, me + buf + hl * row, dn + buf, g * row,
+                      up + self._cnt + 4, dn + self._cnt, me + self._cnt, up + self._cnt + 12, dn + self._cnt + 8, me + self._cnt + 8,
+                      self.epoch & 0xFFFFFFFF, me + self._cnt + 16, me + self._cnt + 20, _lib.current_stream(self.device))
+        self.fresh = g
+
+    def timed_out(self) -> bool:
+        return bool(self._counters[5].item())
+
+    def close(self):
+        if getattr(self, "_sym", None) is not None:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(self.group)
+            self.bufs = []
+            self._counters = self._hdl = self._sym = None
+
+
 class LeniaSlabCUDA(LeniaSlab):
     """Lenia row slab on one GPU: boundary tile rows first, halo exchange on a side stream overlapped with
     the interior tiles (Lenia.step semantics, lenia.py:430-451, on rows [r0, r1) of the global torus)."""

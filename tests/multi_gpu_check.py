@@ -35,6 +35,23 @@ def main():
     ok &= same and int(pop.item()) == ref.population()
     print(f"[rank {rank}] GoL slab == torus: {same}; population {int(pop.item())} vs {ref.population()}", flush=True)
 
+    # ---- the same with the ghost rows pushed by one P2P kernel per exchange (GolSlabP2P, csrc/halo.cu)
+    from pyca_b200.slab import GolSlabP2P
+
+    try:
+        ps = GolSlabP2P(H, W, rank, world, ghost=4, device=dev)
+        ps.random_fill(seed=77)
+        ps.run(steps)
+        torch.cuda.synchronize()
+        dist.barrier()
+        same = torch.equal(ps.owned()[:, :ref.wpr], ref.bits[ps.r0:ps.r1, :ref.wpr]) and not ps.timed_out()
+        print(f"[rank {rank}] GoL P2P-halo slab == torus: {same} ({ps.epoch} exchanges)", flush=True)
+        ok &= same
+        ps.close()
+    except Exception as e:
+        print(f"[rank {rank}] GolSlabP2P unavailable: {e!r}", flush=True)
+        ok = False
+
     # ---- Lenia: C=1 and C=3, 3 steps, overlap on and off
     p = load_npz("params_lenia_abominable_mongolic.npz")
     d = {k: t(p[k]) for k in ["mu", "sigma", "beta", "mu_k", "sigma_k", "weights"]}
