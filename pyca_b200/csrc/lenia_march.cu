@@ -18,6 +18,12 @@
 // HBM traffic per cell and step: the state once (+14 % strip halo, + (Lp+30)/Lp band halo, mostly L2 hits), the Euler
 // operand (an L2 hit: the same CTA loaded that row <= 38 rows earlier) and the output: ~1.1-1.3x the algorithmic 8 B.
 // tools/march_proto.py is the numpy model of the index arithmetic below.
+// Code size: everything below is inlined into the kernel (12.8 K instructions = 204 KB for the single-destination variant), and
+// the short CTAs of small worlds pay for it in instruction-cache misses (ncu `no_instruction` 2.1 of 7 stall cycles per issue on
+// the 24 x 1024^2 batch, 0.2 at 16384^2).  Shrinking it to 3.8 K instructions -- one shared forward routine called from a
+// prologue folded into the marching loop, no per-edge-case epilogue instantiations, a separate out-of-line pass for the frame
+// images -- measured 20 % SLOWER at every size (1.58 vs 1.30 ms at 16384^2): the out-of-line calls cost registers and spills
+// around every call site, real `__noinline__` transforms 50 %.  Not kept.
 #include "common.cuh"
 
 // A/B switches of the developer builds (tools/march_ab.sh); the defaults are what ships

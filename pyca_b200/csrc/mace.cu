@@ -161,11 +161,11 @@ __global__ void __launch_bounds__(128) mace_fast_kernel(const MaceArgs a) {
     const float *stp = a.state_in + (size_t)b * C * pstride + fx;
     float *outp = a.out + (size_t)b * C * pstride;
 
-    float E[C][3], rE[C][3], rG[C][3], AF[C][3];  // index 0: oldest row
+    float E[C][3], rE[C][3], rG[C][3];  // index 0: oldest row
 #pragma unroll
     for (int c = 0; c < C; ++c)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) E[c][k] = rE[c][k] = rG[c][k] = AF[c][k] = 0.f;
+        for (int k = 0; k < 3; ++k) E[c][k] = rE[c][k] = rG[c][k] = 0.f;
 
     const int rend = min(y0 + MROWS, a.H) + 2;  // last input row + 1
     // software pipeline: the loads of input row r+1 are issued before row r is processed
@@ -199,7 +199,6 @@ __global__ void __launch_bounds__(128) mace_fast_kernel(const MaceArgs a) {
             const float re = __shfl_up_sync(0xffffffffu, e, 1) + e + __shfl_down_sync(0xffffffffu, e, 1);
             // shift windows
             E[c][0] = E[c][1]; E[c][1] = E[c][2]; E[c][2] = e;
-            AF[c][0] = AF[c][1]; AF[c][1] = AF[c][2]; AF[c][2] = af;
             rE[c][0] = rE[c][1]; rE[c][1] = rE[c][2]; rE[c][2] = re;
             const float z = rE[c][0] + rE[c][1] + rE[c][2];           // Z(r-1)
             const float gq = __fdividef(st, z);                        // G(r-1)
@@ -210,21 +209,17 @@ __global__ void __launch_bounds__(128) mace_fast_kernel(const MaceArgs a) {
         const int yo = r - 2;
         if (yo < y0 || !out_lane) continue;   // window still filling / halo lane
         if (a.alpha_on) {
-            float mx = AF[0][0], tot = outv[0];
+            // softmax_c(beta * Aff_c) = E_c / sum_c E_c with the E = exp(beta * Aff) of row r-2 already in the window (the
+            // reference subtracts the maximum first, mace_lenia_xchan.py:68-76; |beta * Aff| <= 8 needs no such guard in fp32)
+            float tot = outv[0], den = E[0][0];
 #pragma unroll
             for (int c = 1; c < C; ++c) {
-                mx = fmaxf(mx, AF[c][0]);
                 tot += outv[c];
+                den += E[c][0];
             }
-            float num[C], den = 0.f;
+            const float inv = __fdividef(tot, den);
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                num[c] = exp2f(bl2 * (AF[c][0] - mx));
-                den += num[c];
-            }
-            const float inv = __fdividef(1.f, den);
-#pragma unroll
-            for (int c = 0; c < C; ++c) outv[c] = outv[c] - (outv[c] - tot * (num[c] * inv)) * a.alpha;
+            for (int c = 0; c < C; ++c) outv[c] = outv[c] - (outv[c] - E[c][0] * inv) * a.alpha;
         }
         const bool edge = (x < F) || (x >= a.W - F) || (a.row_wrap && (yo < F || yo >= a.H - F));
 #pragma unroll
