@@ -36,6 +36,9 @@
 #ifndef MARCH_PREFETCH
 #define MARCH_PREFETCH 0     // forward-row loads issued before the FIR, Euler operands before the transforms
 #endif
+#ifndef MARCH_PREFETCH_EPI
+#define MARCH_PREFETCH_EPI 0 // Euler operands issued before the transforms (16 registers held across them)
+#endif
 #ifndef MARCH_MAXLP
 #define MARCH_MAXLP 128      // rows pairs per band at most (taller bands: fewer redundant forward transforms, but too few CTAs)
 #endif
@@ -514,7 +517,7 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
             e.peer_dn = a.final_src && a.peer_dn_out ? a.peer_dn_out + dplane : nullptr;
             const bool euler = a.final_src && lenia;
             float2 st[FT];
-#if MARCH_PREFETCH
+#if MARCH_PREFETCH_EPI
             if (col_ok && euler) {
                 if (edge) epilogue_prefetch<true>(e, st);
                 else epilogue_prefetch<false>(e, st);
@@ -531,7 +534,7 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
                 forward_compute(vf, ring + (zf % RING) * ROWP4, tw, lane16);
             }
             __syncthreads();
-#if !MARCH_PREFETCH
+#if !MARCH_PREFETCH_EPI
             if (col_ok && euler) {
                 if (edge) epilogue_prefetch<true>(e, st);
                 else epilogue_prefetch<false>(e, st);
