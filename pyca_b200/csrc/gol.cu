@@ -12,6 +12,8 @@
 //     4 count bit-planes (2 LOP3 for Life, a mux tree for arbitrary 9-bit S/B masks).
 // Algorithmic traffic: 1 bit read + 1 bit written per cell (0.25 B/cell/step).
 #include <algorithm>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200ca {
@@ -601,6 +603,9 @@ static int launch_fast(const uint32_t *in, uint32_t *out, const GolGeom &g, uint
             rpt = cand[c];
         }
     }
+#ifdef B200CA_DEV
+    if (const char *e = getenv("B200CA_GOL_RPT")) rpt = atoi(e) == 16 ? 16 : (atoi(e) == 8 ? 8 : 4);
+#endif
 #define B200CA_GOL_DISPATCH(LIFE_, OPEN_)                                                        \
     (rpt == 16 ? launch_fast_t<LIFE_, OPEN_, 16>(in, out, g, s, b, st)                           \
                : (rpt == 8 ? launch_fast_t<LIFE_, OPEN_, 8>(in, out, g, s, b, st) : launch_fast_t<LIFE_, OPEN_, 4>(in, out, g, s, b, st)))
