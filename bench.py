@@ -19,7 +19,7 @@ reference from baseline/_ref (baseline/install_ref.py; cpu_baseline.kind "refere
 only if that install is absent (kind "port").  That arm imports neither pyca_b200 nor the CUDA library.
 
 Timing: W warm-up steps, then R blocks of EXACTLY K steps, each block between its own pair of CUDA events (barrier +
-synchronize around the whole timed region); R is chosen so that the region lasts >= 50 ms whatever K is, and
+synchronize around the whole timed region); R is chosen so that the region lasts >= 250 ms whatever K is, and
 ms_per_step = median block time (max over ranks per block) / K.  `timing` in the JSON line says what really ran.
 """
 from __future__ import annotations
@@ -1200,10 +1200,11 @@ def run_reference(args, rank, world):
     arm = RefArm(name)
     arm.setup()
     # one "step" of this arm = a bounded sample of `reps` consecutive CPU steps (>= 50 ms of work), so that K steps are not
-    # dominated by start-up effects; a 4 s untimed spin-up precedes the W warm-up steps (thread pools, first-touch pages)
+    # dominated by start-up effects; an 8 s untimed spin-up precedes the W warm-up steps (thread pools, first-touch pages, host
+    # clock ramp: the step time of a fresh process keeps falling for several seconds on the box)
     t0 = time.perf_counter()
     n0 = 0
-    while time.perf_counter() - t0 < 4.0 or n0 < 1:
+    while time.perf_counter() - t0 < 8.0 or n0 < 1:
         arm.step()
         n0 += 1
     t_one = (time.perf_counter() - t0) / n0
@@ -1269,7 +1270,7 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms_per_step, timing = timed_blocks(wl, args.steps, args.warmup, world, flush, device)
+    ms_per_step, timing = timed_blocks(wl, args.steps, args.warmup, world, flush, device, min_ms=250.0)   # (long enough for >= 3 clock samples)
     clocks = sampler.stop() if sampler else None
     value = wl.cells_per_step() / (ms_per_step * 1e-3) / 1e9
 
