@@ -356,16 +356,22 @@ __device__ __forceinline__ void epilogue(const EpiArgs &e, const float2 (&st)[FT
             e.oa[(size_t)r * e.pitch] = v.x;
             e.oa[e.half + (size_t)r * e.pitch] = v.y;
         } else {
+            // x images (first / last strip of every row: 2 of 5 strips of a 1024-wide world) are two predicated stores; only the
+            // first / last 16 rows of a torus take the general out-of-line path
             const int ya = e.ya0 + r, yb = ya + e.Lp;
-            const bool xe = (e.xw < F) || (e.xw >= e.W - F);
+            const int xoff = e.xw < F ? e.W : (e.xw >= e.W - F ? -e.W : 0);
             if (ya < e.H) {
-                e.oa[(size_t)r * e.pitch] = v.x;
-                if (xe || (e.row_wrap && (ya < F || ya >= e.H - F))) store_mirrors(e.oplane, e.H, e.W, e.pitch, ya, e.xw, v.x, e.row_wrap != 0);
+                float *p = e.oa + (size_t)r * e.pitch;
+                *p = v.x;
+                if (e.row_wrap && (ya < F || ya >= e.H - F)) store_mirrors(e.oplane, e.H, e.W, e.pitch, ya, e.xw, v.x, true);
+                else if (xoff) p[xoff] = v.x;
                 store_peer(e, ya, v.x);
             }
             if (yb < e.H) {
-                e.oa[e.half + (size_t)r * e.pitch] = v.y;
-                if (xe || (e.row_wrap && (yb < F || yb >= e.H - F))) store_mirrors(e.oplane, e.H, e.W, e.pitch, yb, e.xw, v.y, e.row_wrap != 0);
+                float *p = e.oa + e.half + (size_t)r * e.pitch;
+                *p = v.y;
+                if (e.row_wrap && (yb < F || yb >= e.H - F)) store_mirrors(e.oplane, e.H, e.W, e.pitch, yb, e.xw, v.y, true);
+                else if (xoff) p[xoff] = v.y;
                 store_peer(e, yb, v.y);
             }
         }
