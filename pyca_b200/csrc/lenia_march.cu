@@ -39,6 +39,9 @@
 #ifndef MARCH_PREFETCH_EPI
 #define MARCH_PREFETCH_EPI 0 // Euler operands issued before the transforms (16 registers held across them)
 #endif
+#ifndef MARCH_ONE_FORWARD
+#define MARCH_ONE_FORWARD 1  // the prologue runs as extra rounds of the marching loop: ONE inlined copy of the forward transform
+#endif
 #ifndef MARCH_MAXLP
 #define MARCH_MAXLP 128      // rows pairs per band at most (taller bands: fewer redundant forward transforms, but too few CTAs)
 #endif
@@ -449,6 +452,7 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
         if (slab && (fa < F || fa >= a.H + F || fb >= a.H + F)) forward_load<true>(splane + (size_t)fa * a.pitch, splane + (size_t)fb * a.pitch, col0, a.pitch, lane16, v);
         else forward_load<false>(splane + (size_t)fa * a.pitch, splane + (size_t)fb * a.pitch, col0, a.pitch, lane16, v);
     };
+#if !MARCH_ONE_FORWARD
     // prologue: blocks 0..4 (40 rows) by all 16 groups
 #pragma unroll 1
     for (int z = grp; z < RING; z += 16) {
@@ -456,6 +460,7 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
         forward_fetch(z, v);
         forward_compute(v, ring + (z % RING) * ROWP4, tw, lane16);
     }
+#endif
 
     const int xw = col0 - HALO + tid;                    // world column of this thread's sample n = tid (epilogue)
     const bool col_ok = tid >= HALO && tid < N - HALO && xw < a.W;
@@ -464,29 +469,34 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
     // (decided per block of 8 row pairs: in a 256-row band only the first / last 16 rows of the world take the slow path)
     const bool edge_x = strip == 0 || col0 - HALO + N - HALO > a.W - F;
     const bool edge_rows = a.row_wrap || a.peer_up_out || a.peer_dn_out;
+    // MARCH_ONE_FORWARD: rounds it = -3, -2, -1 are the prologue -- all 16 groups run forward transforms (blocks 0..4 of the ring,
+    // 40 rows) through the SAME inlined code the marching rounds use (a second copy in a separate prologue loop costs 18 KB of
+    // instruction-cache footprint, which short CTAs pay for: ncu `no_instruction` 25 % of the stall samples on the 24 x 1024^2 batch)
+    constexpr int PRO = MARCH_ONE_FORWARD ? (RING + 15) / 16 : 0;
 #pragma unroll 1
-    for (int it = 0; it < a.niter; ++it) {
+    for (int it = -PRO; it < a.niter; ++it) {
+        const bool pro = it < 0;
         const int ra0 = y0 + FT * it, rb0 = ra0 + a.Lp;   // first rows of the two halves of this block
         const bool edge = edge_x || rb0 + FT > a.H || (edge_rows && (ra0 < F || rb0 + FT > a.H - F || (ra0 + FT > a.H - F) || rb0 < F));
 #pragma unroll 1
-        for (int j = 0; j < (SINGLE ? 1 : a.C); ++j) {
+        for (int j = (SINGLE || !pro) ? 0 : a.C - 1; j < (SINGLE ? 1 : a.C); ++j) {
             const int pidx = (b * a.NS + a.src) * a.C + j;
-            if (!SINGLE) {
+            if (!SINGLE && !pro) {
                 const float2 *kfj = kf0 + (size_t)j * KROWS * ROW4;
 #pragma unroll
                 for (int dy = 0; dy < KROWS; ++dy) kt[dy] = __ldg(kfj + dy * ROW4);
             }
             // the forward transform this group runs after the FIR (groups 8-15, last destination): its 32 loads are issued
             // now and stay in flight behind the FIR
-            const bool do_fwd = grp >= FT && j == (SINGLE ? 0 : a.C - 1) && it + 1 < a.niter;
-            const int zf = FT * (it + NBLK) + (grp - FT);
+            const int zf = pro ? grp + 16 * (it + PRO) : FT * (it + NBLK) + (grp - FT);
+            const bool do_fwd = pro ? zf < RING : (grp >= FT && j == (SINGLE ? 0 : a.C - 1) && it + 1 < a.niter);
             float2 vf[16];
 #if MARCH_PREFETCH
             if (do_fwd) forward_fetch(zf, vf);
 #endif
-            __syncthreads();  // ring rows of this iteration are complete; the previous epilogue is done with `filt`
+            if (!pro) __syncthreads();  // ring rows of this iteration are complete; the previous epilogue is done with `filt`
             // ---- FIR: output pairs 4h .. 4h+3 of this block from ring rows (8 it + 4h) .. (+33), two frequencies per thread
-            {
+            if (!pro) {
                 const float4 *blk[NBLK];
                 int bb = it % NBLK;
 #pragma unroll
@@ -529,9 +539,10 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
                 else epilogue_prefetch<false>(e, st);
             }
 #endif
-            __syncthreads();
-            // ---- inverse transforms (groups 0-7) | forward transforms of the block needed next (groups 8-15, last destination)
-            if (grp < FT) {
+            if (!pro) __syncthreads();
+            // ---- inverse transforms (groups 0-7) | forward transforms of the block needed next (groups 8-15, last destination);
+            //      prologue rounds: forward transforms on all 16 groups
+            if (!pro && grp < FT) {
                 inverse_row(filt + grp * ROWP4, tw, lane16);
             } else if (do_fwd) {
 #if !MARCH_PREFETCH
@@ -539,6 +550,7 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
 #endif
                 forward_compute(vf, ring + (zf % RING) * ROWP4, tw, lane16);
             }
+            if (pro) continue;
             __syncthreads();
 #if !MARCH_PREFETCH_EPI
             if (col_ok && euler) {
