@@ -86,3 +86,67 @@ def test_reference_arm_of_bench_is_free_of_the_product():
             assert "pyca_b200" not in seg and "b200ca" not in seg.replace("B200CA", ""), node.name
             wanted.discard(node.name)
     assert not wanted, f"not found in bench.py: {wanted}"
+
+
+def test_conv_path_rule_and_band_heights_without_a_gpu():
+    """b200ca_lenia_pick_algo_ks / b200ca_lenia_march_band_rows are host-side rules (profiles/r02_conv_paths.md): no device needed."""
+    from pyca_b200 import _lib
+
+    L = _lib.lib()
+    DIRECT, ROWS, MARCH = 0, 1, 2
+    assert L.b200ca_lenia_pick_algo_ks(1, 1, 1024, 1024, 31) == ROWS          # one small world: two-kernel hybrid
+    assert L.b200ca_lenia_pick_algo_ks(24, 1, 1024, 1024, 31) == MARCH        # the headline batch
+    assert L.b200ca_lenia_pick_algo_ks(1, 1, 16384, 16384, 31) == MARCH
+    assert L.b200ca_lenia_pick_algo_ks(1, 3, 4096, 4096, 31) == ROWS          # several source channels
+    assert L.b200ca_lenia_pick_algo_ks(1, 3, 4097, 4096, 31) == MARCH         # odd height: the hybrid cannot, the marching kernel can
+    assert L.b200ca_lenia_pick_algo_ks(1, 1, 4096, 4096, 7) == DIRECT         # small kernels: direct, whatever the world
+    assert L.b200ca_lenia_pick_algo_ks(1, 3, 4096, 4096, 5) == DIRECT
+    assert L.b200ca_lenia_pick_algo_ks(1, 1, 4096, 4096, 11) == MARCH and L.b200ca_lenia_pick_algo_ks(1, 1, 1024, 1024, 11) == DIRECT
+    assert L.b200ca_lenia_pick_algo_ks(1, 1, 24, 24, 31) == DIRECT            # too small for the FFT paths
+    assert L.b200ca_lenia_pick_algo(1, 1, 1024, 1024) == ROWS
+    assert L.b200ca_lenia_march_supported(33, 449) == 1 and L.b200ca_lenia_march_supported(16, 64) == 0
+    for H, W, B in [(1024, 1024, 1), (1024, 1024, 24), (4096, 4096, 1), (16384, 16384, 1), (2048, 16384, 1)]:
+        rows = L.b200ca_lenia_march_band_rows(H, W, B, 1)
+        assert rows % 16 == 0 and 16 <= rows <= 256, (H, W, B, rows)
+    assert L.b200ca_lenia_march_band_rows(16384, 16384, 1, 1) > L.b200ca_lenia_march_band_rows(1024, 1024, 1, 1)
+
+
+def test_lenia_params_expand_matches_the_reference_semantics():
+    """LeniaParams.expand (batch_params.py:217-236): batch-1 tensors repeated along dim 0, scalars kept."""
+    import torch
+
+    import pyca_b200
+    from tests.util import load_npz, t
+
+    p = load_npz("params_lenia_abominable_mongolic.npz")
+    d = {k: t(p[k]) for k in ["mu", "sigma", "beta", "mu_k", "sigma_k", "weights"]}
+    d["k_size"] = int(p["k_size"])
+    P = pyca_b200.LeniaParams(param_dict=d)
+    E = P.expand(5)
+    assert E.batch_size == 5 and E["k_size"] == P["k_size"]
+    for k in ["mu", "sigma", "beta", "mu_k", "sigma_k", "weights"]:
+        assert E[k].shape[0] == 5 and torch.allclose(E[k][3], P[k][0], atol=1e-6)   # (the constructor re-sanitises, as the reference does)
+    import pytest
+    with pytest.raises(AssertionError):
+        E.expand(2)
+
+
+def test_both_bench_arms_print_the_same_config():
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "bench.py")).read()
+    ns = {}
+    # the static description is a pure function of (workload name, GPU count): evaluate it in isolation
+    import ast
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if (isinstance(n, ast.FunctionDef) and n.name in ("static_config", "lenia_ring_worlds")) or
+            (isinstance(n, ast.Assign) and any(getattr(tg, "id", "") in ("SHAPES", "REPLICA_WORKLOADS", "SLAB_WORKLOADS", "GOL_GHOST", "L2_BYTES",
+                                                                           "LENIA1K_BATCH", "L2_FLUSH_BYTES") for tg in n.targets))]
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "bench_static", "exec"), ns)
+    for name in ns["SHAPES"]:
+        for n in (1, 2, 8):
+            c = ns["static_config"](name, n)
+            assert c["workload"] == name and "l2" in c and "partition" in c
+    assert ns["static_config"]("lenia_1k", 1)["shape"] == [ns["LENIA1K_BATCH"], 1, 1024, 1024]
