@@ -37,7 +37,7 @@
 #define MARCH_PREFETCH 0     // forward-row loads issued before the FIR, Euler operands before the transforms
 #endif
 #ifndef MARCH_PREFETCH_EPI
-#define MARCH_PREFETCH_EPI 0 // Euler operands issued before the transforms (16 registers held across them)
+#define MARCH_PREFETCH_EPI 1 // Euler operands issued before the transforms (16 registers held across them)
 #endif
 #ifndef MARCH_ONE_FORWARD
 #define MARCH_ONE_FORWARD 1  // the prologue runs as extra rounds of the marching loop: ONE inlined copy of the forward transform
@@ -47,6 +47,18 @@
 #endif
 #ifndef MARCH_FORCELP
 #define MARCH_FORCELP 0      // != 0: fixed band height (A/B runs)
+#endif
+#ifndef MARCH_RELOAD_TAPS
+#define MARCH_RELOAD_TAPS 1  // 1: the single-destination kernel reloads its 16 tap pairs before every FIR (32 registers free elsewhere)
+#endif
+#ifndef MARCH_MULTI_XEDGE
+#define MARCH_MULTI_XEDGE 1
+#endif
+#ifndef MARCH_PRO_UNITS
+#define MARCH_PRO_UNITS 4
+#endif
+#ifndef MARCH_JOB_WAVES
+#define MARCH_JOB_WAVES 1    // balanced launches: grid = this many waves of CTAs (0: fixed-height bands for every launch)
 #endif
 
 namespace b200ca {
@@ -70,6 +82,7 @@ constexpr int ROW4 = N / 2;       // float4 of a spectra row (tap-table stride)
 //   sample layout    float2 index n               (inverse output: (row a, row b) of sample n)
 constexpr int ROWP4 = 144;        // float4 per padded row (2304 B >= 16*17 float2)
 constexpr int THREADS = 256;
+constexpr int PRO_UNITS = MARCH_PRO_UNITS;      // cost of a band's prologue (40 forward transforms on all 16 groups) in rounds of the marching loop
 constexpr size_t SMEM = (size_t)(RING + FT) * ROWP4 * sizeof(float4) + 16 * 17 * sizeof(float2);
 
 struct Args {
@@ -78,8 +91,11 @@ struct Args {
     const float2 *kf;   // (B, NS, C, KROWS, 128) tap pairs in FIR-thread order (march_prepare_kernel)
     const float *mu, *sigma, *weights;
     int B, C, NS, k_mult, H, W, pitch;
-    int Lp, niter;      // row pairs per band (multiple of FT), Lp / FT
-    int band0;          // first band of this launch (row slabs issue their boundary bands first)
+    int Lp, niter;      // banded launches: row pairs per band (multiple of FT), Lp / FT
+    int band0;          // banded launches: first band of this launch (a caller that overlaps an exchange issues its boundary bands first)
+    int jobs;           // 1: balanced launch -- the grid is ONE wave of CTAs that share the (world, strip, 16-row unit) space evenly
+    int units, strips;  // 16-row units per column of bands (ceil(H / 16)), strips per world
+    int split_k;        // balanced launches: != 0: every column is cut into split_k equal bands, one CTA each (no run crosses a column)
     int src;            // source-kernel index i*k_mult + m of this launch
     int acc_in;         // 1: add to the partial sums already in `out` (sources after the first)
     int final_src;      // 1: last source -> Euler step / clamp (LENIA) or plain sum (AFF)
@@ -97,6 +113,7 @@ struct Args {
     unsigned wait_target;                        // arrivals expected before this step may read its ghost rows
     int nbands;                                  // bands of the whole slab (blockIdx.y is permuted: boundary bands first)
     unsigned *err_flag;                          // set if a wait timed out (no hang: the step then reads stale ghost rows)
+    unsigned stagger_ns;                         // developer builds: the second half of the grid starts this much later (phase experiment)
 };
 
 // Every fp32 instruction with three register operands -- scalar or packed -- occupies the FMA pipe for two cycles per warp
@@ -294,14 +311,20 @@ __device__ __forceinline__ void fir_half(const float4 *const (&blk)[NBLK], const
 
 struct EpiArgs {
     const float2 *u;       // this thread's sample of output pair 0 (stride 2*ROWP4 float2 per pair)
-    const float *sa;       // state, row pair 0 (EULER)
-    float *oa;             // output, row pair 0
+    // Row addresses are byte pointers + r * pitchB with a 32-bit product: ONE IMAD.WIDE per address (element-indexed 64-bit
+    // arithmetic cost four integer instructions per row: 128 of the ~1000 instructions of a marching round).
+    const char *sa, *sb;   // state, first row of the first / second half of this block of 8 row pairs (EULER)
+    char *oa, *ob;         // output, same rows
     float *oplane;
-    long long half;        // Lp * pitch: distance of the second row of a pair
+    int pitchB;            // row pitch in bytes
     int pitch, H, W, ya0, Lp, xw, row_wrap;
+    int xoff;              // distance to this column's periodic x image (+-W for the 16 columns next to the world edge, else 0)
     float mu, nc2, w2, wn, dt;   // growth(u) * weight = exp2((u - mu)^2 * nc2) * w2 + wn
     float *peer_up, *peer_dn;    // destination plane in the neighbours' out buffers (row slabs), or null
 };
+
+__device__ __forceinline__ const float *row_ptr(const char *base, int r, int pitchB) { return reinterpret_cast<const float *>(base + (long long)(r * pitchB)); }
+__device__ __forceinline__ float *row_ptr(char *base, int r, int pitchB) { return reinterpret_cast<float *>(base + (long long)(r * pitchB)); }
 
 // a row slab's first / last F rows go to the neighbour's bottom / top ghost rows as well (with their periodic x images)
 __device__ __forceinline__ void store_peer(const EpiArgs &e, int y, float v) {
@@ -321,26 +344,29 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 // the Euler operands (state rows a and b of 8 row pairs), issued long before they are needed
-template <bool EDGE>
+template <int EDGE>
 __device__ __forceinline__ void epilogue_prefetch(const EpiArgs &e, float2 (&st)[FT]) {
 #pragma unroll
     for (int r = 0; r < FT; ++r) {
-        const bool oka = !EDGE || e.ya0 + r < e.H, okb = !EDGE || e.ya0 + e.Lp + r < e.H;
-        st[r] = make_float2(oka ? __ldg(e.sa + (size_t)r * e.pitch) : 0.f, okb ? __ldg(e.sa + e.half + (size_t)r * e.pitch) : 0.f);
+        const bool oka = EDGE < 2 || e.ya0 + r < e.H, okb = EDGE < 2 || e.ya0 + e.Lp + r < e.H;
+        st[r] = make_float2(oka ? __ldg(row_ptr(e.sa, r, e.pitchB)) : 0.f, okb ? __ldg(row_ptr(e.sb, r, e.pitchB)) : 0.f);
     }
 }
 
 // growth + weighted source sum (+ partial sums of earlier sources) (+ Euler step / clamp) and the stores of 8 row pairs;
 // the two rows of a pair are the two halves of packed fp32x2 operations.
-// EDGE = false: a CTA whose cells have no periodic images and whose rows all lie inside the world.
-template <bool EDGE, bool ACC, bool EULER>
+// EDGE = 0: a block of 8 row pairs whose cells have no periodic images and whose rows all lie inside the world;  1: the same rows in
+// the first / last strip of a world (2 of the 5 strips of a 1024-wide world): the cells within 16 columns of the world edge store
+// their periodic x image as well (one predicated store per row -- as cheap as EDGE = 0, which matters because a balanced launch
+// ends when its slowest CTA does);  2: the general path (first / last 16 rows of a torus or a slab, rows beyond the world).
+template <int EDGE, bool ACC, bool EULER>
 __device__ __forceinline__ void epilogue(const EpiArgs &e, const float2 (&st)[FT]) {
     float2 pv[FT];
     if (ACC) {
 #pragma unroll
         for (int r = 0; r < FT; ++r) {
-            const bool oka = !EDGE || e.ya0 + r < e.H, okb = !EDGE || e.ya0 + e.Lp + r < e.H;
-            pv[r] = make_float2(oka ? e.oa[(size_t)r * e.pitch] : 0.f, okb ? e.oa[e.half + (size_t)r * e.pitch] : 0.f);
+            const bool oka = EDGE < 2 || e.ya0 + r < e.H, okb = EDGE < 2 || e.ya0 + e.Lp + r < e.H;
+            pv[r] = make_float2(oka ? *row_ptr(e.oa, r, e.pitchB) : 0.f, okb ? *row_ptr(e.ob, r, e.pitchB) : 0.f);
         }
     }
     const float2 nmu = make_float2(-e.mu, -e.mu), nc2 = make_float2(e.nc2, e.nc2), w2 = make_float2(e.w2, e.w2), wn = make_float2(e.wn, e.wn),
@@ -355,23 +381,31 @@ __device__ __forceinline__ void epilogue(const EpiArgs &e, const float2 (&st)[FT
             v = __ffma2_rn(dt2, v, st[r]);
             v = make_float2(fminf(fmaxf(v.x, 0.f), 1.f), fminf(fmaxf(v.y, 0.f), 1.f));
         }
-        if (!EDGE) {
-            e.oa[(size_t)r * e.pitch] = v.x;
-            e.oa[e.half + (size_t)r * e.pitch] = v.y;
+        if (EDGE == 0) {
+            *row_ptr(e.oa, r, e.pitchB) = v.x;
+            *row_ptr(e.ob, r, e.pitchB) = v.y;
+        } else if (EDGE == 1) {
+            float *pa = row_ptr(e.oa, r, e.pitchB), *pb = row_ptr(e.ob, r, e.pitchB);
+            *pa = v.x;
+            *pb = v.y;
+            if (e.xoff) {
+                pa[e.xoff] = v.x;
+                pb[e.xoff] = v.y;
+            }
         } else {
             // x images (first / last strip of every row: 2 of 5 strips of a 1024-wide world) are two predicated stores; only the
             // first / last 16 rows of a torus take the general out-of-line path
             const int ya = e.ya0 + r, yb = ya + e.Lp;
-            const int xoff = e.xw < F ? e.W : (e.xw >= e.W - F ? -e.W : 0);
+            const int xoff = e.xoff;
             if (ya < e.H) {
-                float *p = e.oa + (size_t)r * e.pitch;
+                float *p = row_ptr(e.oa, r, e.pitchB);
                 *p = v.x;
                 if (e.row_wrap && (ya < F || ya >= e.H - F)) store_mirrors(e.oplane, e.H, e.W, e.pitch, ya, e.xw, v.x, true);
                 else if (xoff) p[xoff] = v.x;
                 store_peer(e, ya, v.x);
             }
             if (yb < e.H) {
-                float *p = e.oa + e.half + (size_t)r * e.pitch;
+                float *p = row_ptr(e.ob, r, e.pitchB);
                 *p = v.y;
                 if (e.row_wrap && (yb < F || yb >= e.H - F)) store_mirrors(e.oplane, e.H, e.W, e.pitch, yb, e.xw, v.y, true);
                 else if (xoff) p[xoff] = v.y;
@@ -381,7 +415,15 @@ __device__ __forceinline__ void epilogue(const EpiArgs &e, const float2 (&st)[FT
     }
 }
 
-// grid (strips, bands of this launch, B), block 256.  SINGLE: one destination plane (C == 1): taps stay in registers.
+// block 256.  SINGLE: one destination plane (C == 1): taps stay in registers.
+// Two ways to hand out the bands:
+//   * balanced (a.jobs, every whole-world / whole-slab step): grid = ONE wave of CTAs (2 per SM).  The columns of bands -- (world,
+//     strip) pairs, each ceil(H / 16) units of 16 rows tall -- are laid end to end and cut into gridDim.x equal runs of units; a CTA
+//     marches down its run, starting a new band (prologue: 32 extra forward transforms) only at its first unit and where the run
+//     crosses into the next column.  Fixed-height bands had to choose between tall bands that leave the last wave of CTAs mostly
+//     empty and short ones that double the forward transforms (24 x 1024^2: 1920 CTAs of 64 rows = 6.5 waves, 2x the forward
+//     work); now every SM is busy for the same time with ~1.1x.
+//   * banded (band_begin / band_end of b200ca_lenia_step_march): grid (strips, bands of this launch, B), fixed band height.
 template <bool SINGLE>
 __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
     extern __shared__ __align__(16) float4 msm[];
@@ -389,22 +431,11 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
     float4 *filt = msm + RING * ROWP4;                   // FT rows: filtered spectra -> inverse exchange -> outputs
     float2 *tw = reinterpret_cast<float2 *>(filt + FT * ROWP4);  // W256^{t r} at [17 t + r]
     const int tid = threadIdx.x, lane16 = tid & 15, grp = tid >> 4;  // 16 groups of 16 lanes
-    const int strip = blockIdx.x, b = blockIdx.z;
-    // row slabs: boundary bands first (blockIdx.y = 0 -> first band, 1 -> last band), so that the neighbours' ghost rows are on
-    // their way while the interior bands run
-    int band = a.band0 + blockIdx.y;
-#ifndef MARCH_NOPERM
-    if (a.nbands > 1 && (a.sig_up || a.sig_dn)) band = blockIdx.y == 0 ? 0 : (blockIdx.y == 1 ? a.nbands - 1 : (int)blockIdx.y - 1);
-#endif
-    const int y0 = band * 2 * a.Lp;
-    const int col0 = strip * V;                          // framed column of sample n = 0 (world column strip*V - HALO)
-    const int src_plane = b * a.C + a.src / a.k_mult;
     const size_t plane_elems = (size_t)(a.H + 2 * F) * a.pitch;
-    const float *splane = a.state_in + (size_t)src_plane * plane_elems;
     const int max_frow = a.H + 2 * F - 1;
     const bool slab = a.wait_top != nullptr || a.wait_bot != nullptr;
 
-    // input-independent prologue: twiddle table, taps of the first destination
+    // input-independent prologue: twiddle table
     {
         const int t = tid >> 4, r = tid & 15;
         float sn, cs;
@@ -413,170 +444,269 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
     }
     const int f = tid & 127, h = tid >> 7;
     const int fslot = 9 * (f >> 3) + (f & 7);            // this FIR thread's float4 in a padded spectra row
-    float2 kt[KROWS];
-    const float2 *kf0 = a.kf + (size_t)((b * a.NS + a.src) * a.C) * KROWS * ROW4 + f;
-#pragma unroll
-    for (int dy = 0; dy < KROWS; ++dy) kt[dy] = __ldg(kf0 + dy * ROW4);
-    pdl_wait_then_release();  // the state is the previous step's output
-    if (tid == 0 && (a.wait_top || a.wait_bot)) {
-        // ghost rows written by the neighbours' previous step: wait for their arrival counters (bounded: a lost neighbour must
-        // not hang the GPU -- after ~4 s the error flag is raised and the step goes on)
-        unsigned long long t0;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        for (int side = 0; side < 2; ++side) {
-            const unsigned *cnt = side == 0 ? a.wait_top : a.wait_bot;
-            const bool mine = side == 0 ? band == 0 : band == a.nbands - 1;
-            if (!cnt || !mine) continue;
-            for (;;) {
-                unsigned v;
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
-                if ((int)(v - a.wait_target) >= 0) break;
-                unsigned long long t1;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                if (t1 - t0 > 4000000000ull) {
-                    if (a.err_flag) atomicExch(a.err_flag, 1u);
-                    break;
-                }
-                __nanosleep(200);
-            }
-        }
-    }
-    __syncthreads();          // twiddle table, ghost rows
-
-    // spectra row z of the band <- image rows (y0 + z - R, y0 + Lp + z - R), clamped into the framed plane
-    auto forward_fetch = [&](int z, float2 (&v)[16]) {
-        const int fa = min(y0 + z - R + F, max_frow), fb = min(y0 + a.Lp + z - R + F, max_frow);
-        // ghost rows (the frame rows of a slab) are written by a peer GPU while this kernel may already run: they are read
-        // through L2 (ld.global.cg); everything else takes the read-only path, whose L1 merges the 64-byte row pieces
-        // (all loads through L2 cost 12 % of the step)
-        if (slab && (fa < F || fa >= a.H + F || fb >= a.H + F)) forward_load<true>(splane + (size_t)fa * a.pitch, splane + (size_t)fb * a.pitch, col0, a.pitch, lane16, v);
-        else forward_load<false>(splane + (size_t)fa * a.pitch, splane + (size_t)fb * a.pitch, col0, a.pitch, lane16, v);
-    };
-#if !MARCH_ONE_FORWARD
-    // prologue: blocks 0..4 (40 rows) by all 16 groups
-#pragma unroll 1
-    for (int z = grp; z < RING; z += 16) {
-        float2 v[16];
-        forward_fetch(z, v);
-        forward_compute(v, ring + (z % RING) * ROWP4, tw, lane16);
-    }
-#endif
-
-    const int xw = col0 - HALO + tid;                    // world column of this thread's sample n = tid (epilogue)
-    const bool col_ok = tid >= HALO && tid < N - HALO && xw < a.W;
     const bool lenia = a.mode == B200CA_MODE_LENIA;
-    // CTAs that own cells with periodic images (first / last columns, first / last rows of a torus) or a partial last band
-    // (decided per block of 8 row pairs: in a 256-row band only the first / last 16 rows of the world take the slow path)
-    const bool edge_x = strip == 0 || col0 - HALO + N - HALO > a.W - F;
     const bool edge_rows = a.row_wrap || a.peer_up_out || a.peer_dn_out;
-    // MARCH_ONE_FORWARD: rounds it = -3, -2, -1 are the prologue -- all 16 groups run forward transforms (blocks 0..4 of the ring,
-    // 40 rows) through the SAME inlined code the marching rounds use (a second copy in a separate prologue loop costs 18 KB of
-    // instruction-cache footprint, which short CTAs pay for: ncu `no_instruction` 25 % of the stall samples on the 24 x 1024^2 batch)
-    constexpr int PRO = MARCH_ONE_FORWARD ? (RING + 15) / 16 : 0;
-#pragma unroll 1
-    for (int it = -PRO; it < a.niter; ++it) {
-        const bool pro = it < 0;
-        const int ra0 = y0 + FT * it, rb0 = ra0 + a.Lp;   // first rows of the two halves of this block
-        const bool edge = edge_x || rb0 + FT > a.H || (edge_rows && (ra0 < F || rb0 + FT > a.H - F || (ra0 + FT > a.H - F) || rb0 < F));
-#pragma unroll 1
-        for (int j = (SINGLE || !pro) ? 0 : a.C - 1; j < (SINGLE ? 1 : a.C); ++j) {
-            const int pidx = (b * a.NS + a.src) * a.C + j;
-            if (!SINGLE && !pro) {
-                const float2 *kfj = kf0 + (size_t)j * KROWS * ROW4;
-#pragma unroll
-                for (int dy = 0; dy < KROWS; ++dy) kt[dy] = __ldg(kfj + dy * ROW4);
-            }
-            // the forward transform this group runs after the FIR (groups 8-15, last destination): its 32 loads are issued
-            // now and stay in flight behind the FIR
-            const int zf = pro ? grp + 16 * (it + PRO) : FT * (it + NBLK) + (grp - FT);
-            const bool do_fwd = pro ? zf < RING : (grp >= FT && j == (SINGLE ? 0 : a.C - 1) && it + 1 < a.niter);
-            float2 vf[16];
-#if MARCH_PREFETCH
-            if (do_fwd) forward_fetch(zf, vf);
+    pdl_wait_then_release();  // the state is the previous step's output
+#ifdef B200CA_DEV
+    if (a.stagger_ns && blockIdx.x >= gridDim.x / 2 && tid == 0) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        } while (t1 - t0 < a.stagger_ns);
+    }
 #endif
-            if (!pro) __syncthreads();  // ring rows of this iteration are complete; the previous epilogue is done with `filt`
-            // ---- FIR: output pairs 4h .. 4h+3 of this block from ring rows (8 it + 4h) .. (+33), two frequencies per thread
-            if (!pro) {
-                const float4 *blk[NBLK];
-                int bb = it % NBLK;
+    __syncthreads();          // twiddle table
+
+    int done = 0;             // balanced launches: units of this CTA's run that are finished
+#pragma unroll 1
+    for (;;) {
+        // ---- the next band of this CTA
+        int strip, b, y0, Lp, niter;
+        if (a.jobs && a.split_k) {
+            // every column of bands cut into split_k equal bands (chosen by the host when that leaves no CTA with more rows than
+            // the runs below would: e.g. 74 columns on 296 CTAs)
+            if (done) break;
+            done = 1;
+            const int col = blockIdx.x / a.split_k, part = blockIdx.x - col * a.split_k;
+            const int u0 = (int)((long long)a.units * part / a.split_k);
+            niter = (int)((long long)a.units * (part + 1) / a.split_k) - u0;
+            strip = col % a.strips;
+            b = col / a.strips;
+            y0 = 2 * FT * u0;
+            Lp = FT * niter;
+        } else if (a.jobs) {
+            // Runs are equal in COST: a column is `units` rounds of the marching loop plus PRO_UNITS rounds' worth of prologue, so a
+            // run that crosses into the next column (a second prologue) gets fewer rows than one that does not.
+            const int vunits = a.units + PRO_UNITS;
+            const long long total = (long long)vunits * a.strips * a.B;
+            const long long v = total * blockIdx.x / gridDim.x + done, v_end = total * (blockIdx.x + 1) / gridDim.x;
+            if (v >= v_end) break;
+            const int col = (int)(v / vunits), v0 = (int)(v - (long long)col * vunits);
+            const int nv = (int)min((long long)(vunits - v0), v_end - v);
+            done += nv;
+            const int u0 = max(v0 - PRO_UNITS, 0);
+            niter = max(v0 + nv - PRO_UNITS, 0) - u0;
+            if (niter == 0) continue;
+            strip = col % a.strips;
+            b = col / a.strips;
+            y0 = 2 * FT * u0;
+            Lp = FT * niter;
+        } else {
+            if (done) break;
+            done = 1;
+            strip = blockIdx.x;
+            b = blockIdx.z;
+            // callers that overlap a halo exchange: boundary bands first (blockIdx.y = 0 -> first band, 1 -> last band)
+            int band = a.band0 + blockIdx.y;
+#ifndef MARCH_NOPERM
+            if (a.nbands > 1 && (a.sig_up || a.sig_dn)) band = blockIdx.y == 0 ? 0 : (blockIdx.y == 1 ? a.nbands - 1 : (int)blockIdx.y - 1);
+#endif
+            Lp = a.Lp;
+            niter = a.niter;
+            y0 = band * 2 * Lp;
+        }
+        const bool top = y0 == 0, bot = y0 + 2 * Lp >= a.H;   // this band holds the first / last rows of the world (slab)
+        const int col0 = strip * V;                          // framed column of sample n = 0 (world column strip*V - HALO)
+        const int src_plane = b * a.C + a.src / a.k_mult;
+        const float *splane = a.state_in + (size_t)src_plane * plane_elems;
+
+        // taps of the first destination
+        float2 kt[KROWS];
+        const float2 *kf0 = a.kf + (size_t)((b * a.NS + a.src) * a.C) * KROWS * ROW4 + f;
+        if (SINGLE && !MARCH_RELOAD_TAPS) {
 #pragma unroll
-                for (int i = 0; i < NBLK; ++i) {
-                    blk[i] = ring + bb * FT * ROWP4 + fslot;
-                    bb = bb + 1 == NBLK ? 0 : bb + 1;
+            for (int dy = 0; dy < KROWS; ++dy) kt[dy] = __ldg(kf0 + dy * ROW4);
+        }
+        if (slab && (top || bot)) {
+            if (tid == 0) {
+                // ghost rows written by the neighbours' previous step: wait for their arrival counters (bounded: a lost neighbour must
+                // not hang the GPU -- after ~4 s the error flag is raised and the step goes on)
+                unsigned long long t0;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                for (int side = 0; side < 2; ++side) {
+                    const unsigned *cnt = side == 0 ? a.wait_top : a.wait_bot;
+                    const bool mine = side == 0 ? top : bot;
+                    if (!cnt || !mine) continue;
+                    for (;;) {
+                        unsigned v;
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+                        if ((int)(v - a.wait_target) >= 0) break;
+                        unsigned long long t1;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                        if (t1 - t0 > 4000000000ull) {
+                            if (a.err_flag) atomicExch(a.err_flag, 1u);
+                            break;
+                        }
+                        __nanosleep(200);
+                    }
                 }
-                if (h == 0) fir_half<0>(blk, kt, filt + fslot);
-                else fir_half<1>(blk, kt, filt + 4 * ROWP4 + fslot);
             }
-            // Euler operands of the epilogue: in flight behind the transforms
-            const float mu = __ldg(a.mu + pidx), sg = __ldg(a.sigma + pidx), wt = __ldg(a.weights + pidx);
-            const size_t dplane = (size_t)(b * a.C + j) * plane_elems;
-            const size_t o0 = (size_t)(y0 + FT * it + F) * a.pitch + F + xw;
-            EpiArgs e;
-            e.u = reinterpret_cast<const float2 *>(filt) + tid;
-            e.sa = a.state_in + dplane + o0;
-            e.oplane = a.out + dplane;
-            e.oa = e.oplane + o0;
-            e.half = (long long)a.Lp * a.pitch;
-            e.pitch = a.pitch;
-            e.H = a.H;
-            e.W = a.W;
-            e.ya0 = y0 + FT * it;
-            e.Lp = a.Lp;
-            e.xw = xw;
-            e.row_wrap = a.row_wrap;
-            e.mu = mu;
-            e.nc2 = -1.4426950408889634f / (2.f * sg * sg);   // growth = 2 exp(-(u-mu)^2 / (2 sigma^2)) - 1  (lenia.py:423-426)
-            e.w2 = 2.f * wt;
-            e.wn = -wt;
-            e.dt = a.dt;
-            e.peer_up = a.final_src && a.peer_up_out ? a.peer_up_out + dplane : nullptr;
-            e.peer_dn = a.final_src && a.peer_dn_out ? a.peer_dn_out + dplane : nullptr;
-            const bool euler = a.final_src && lenia;
-            float2 st[FT];
+            __syncthreads();      // ghost rows
+        }
+
+        // spectra row z of the band <- image rows (y0 + z - R, y0 + Lp + z - R), clamped into the framed plane
+        auto forward_fetch = [&](int z, float2 (&v)[16]) {
+            const int fa = min(y0 + z - R + F, max_frow), fb = min(y0 + Lp + z - R + F, max_frow);
+            // ghost rows (the frame rows of a slab) are written by a peer GPU while this kernel may already run: they are read
+            // through L2 (ld.global.cg); everything else takes the read-only path, whose L1 merges the 64-byte row pieces
+            // (all loads through L2 cost 12 % of the step)
+            if (slab && (fa < F || fa >= a.H + F || fb >= a.H + F)) forward_load<true>(splane + (size_t)fa * a.pitch, splane + (size_t)fb * a.pitch, col0, a.pitch, lane16, v);
+            else forward_load<false>(splane + (size_t)fa * a.pitch, splane + (size_t)fb * a.pitch, col0, a.pitch, lane16, v);
+        };
+#if !MARCH_ONE_FORWARD
+        // prologue: blocks 0..4 (40 rows) by all 16 groups
+#pragma unroll 1
+        for (int z = grp; z < RING; z += 16) {
+            float2 v[16];
+            forward_fetch(z, v);
+            forward_compute(v, ring + (z % RING) * ROWP4, tw, lane16);
+        }
+#endif
+
+        // growth(u) * weight = exp2((u - mu)^2 * nc2) * w2 + wn  (lenia.py:423-426: 2 exp(-(u-mu)^2 / (2 sigma^2)) - 1); one destination:
+        // constant for the whole band
+        float g_mu = 0.f, g_nc2 = 0.f, g_w2 = 0.f, g_wn = 0.f;
+        if (SINGLE) {
+            const int pidx = (b * a.NS + a.src) * a.C;
+            const float sg = __ldg(a.sigma + pidx), wt = __ldg(a.weights + pidx);
+            g_mu = __ldg(a.mu + pidx);
+            g_nc2 = -1.4426950408889634f / (2.f * sg * sg);
+            g_w2 = 2.f * wt;
+            g_wn = -wt;
+        }
+        const int xw = col0 - HALO + tid;                    // world column of this thread's sample n = tid (epilogue)
+        const bool col_ok = tid >= HALO && tid < N - HALO && xw < a.W;
+        // CTAs that own cells with periodic images (first / last columns, first / last rows of a torus) or a partial last band
+        // (decided per block of 8 row pairs: in a 256-row band only the first / last 16 rows of the world take the slow path)
+        const bool edge_x = strip == 0 || col0 - HALO + N - HALO > a.W - F;
+        // MARCH_ONE_FORWARD: rounds it = -3, -2, -1 are the prologue -- all 16 groups run forward transforms (blocks 0..4 of the ring,
+        // 40 rows) through the SAME inlined code the marching rounds use (a second copy in a separate prologue loop costs 18 KB of
+        // instruction-cache footprint, which short CTAs pay for: ncu `no_instruction` 25 % of the stall samples on the 24 x 1024^2 batch)
+        constexpr int PRO = MARCH_ONE_FORWARD ? (RING + 15) / 16 : 0;
+#pragma unroll 1
+        for (int it = -PRO; it < niter; ++it) {
+            const bool pro = it < 0;
+            const int ra0 = y0 + FT * it, rb0 = ra0 + Lp;   // first rows of the two halves of this block
+            const bool edge_y = rb0 + FT > a.H || (edge_rows && (ra0 < F || rb0 + FT > a.H - F || (ra0 + FT > a.H - F) || rb0 < F));
+            const int edge = edge_y ? 2 : (edge_x ? (SINGLE || MARCH_MULTI_XEDGE ? 1 : 2) : 0);
+#pragma unroll 1
+            for (int j = (SINGLE || !pro) ? 0 : a.C - 1; j < (SINGLE ? 1 : a.C); ++j) {
+                const int pidx = (b * a.NS + a.src) * a.C + j;
+                if ((!SINGLE || MARCH_RELOAD_TAPS) && !pro) {
+                    const float2 *kfj = kf0 + (size_t)j * KROWS * ROW4;
+#pragma unroll
+                    for (int dy = 0; dy < KROWS; ++dy) kt[dy] = __ldg(kfj + dy * ROW4);
+                }
+                // the forward transform this group runs after the FIR (groups 8-15, last destination): its 32 loads are issued
+                // now and stay in flight behind the FIR
+                const int zf = pro ? grp + 16 * (it + PRO) : FT * (it + NBLK) + (grp - FT);
+                const bool do_fwd = pro ? zf < RING : (grp >= FT && j == (SINGLE ? 0 : a.C - 1) && it + 1 < niter);
+                float2 vf[16];
+#if MARCH_PREFETCH
+                if (do_fwd) forward_fetch(zf, vf);
+#endif
+                if (!pro) __syncthreads();  // ring rows of this iteration are complete; the previous epilogue is done with `filt`
+                // ---- FIR: output pairs 4h .. 4h+3 of this block from ring rows (8 it + 4h) .. (+33), two frequencies per thread
+                if (!pro) {
+                    const float4 *blk[NBLK];
+                    int bb = it % NBLK;
+#pragma unroll
+                    for (int i = 0; i < NBLK; ++i) {
+                        blk[i] = ring + bb * FT * ROWP4 + fslot;
+                        bb = bb + 1 == NBLK ? 0 : bb + 1;
+                    }
+                    if (h == 0) fir_half<0>(blk, kt, filt + fslot);
+                    else fir_half<1>(blk, kt, filt + 4 * ROWP4 + fslot);
+                }
+                // growth constants and row pointers of the epilogue
+                if (!SINGLE) {
+                    const float sg = __ldg(a.sigma + pidx), wt = __ldg(a.weights + pidx);
+                    g_mu = __ldg(a.mu + pidx);
+                    g_nc2 = -1.4426950408889634f / (2.f * sg * sg);
+                    g_w2 = 2.f * wt;
+                    g_wn = -wt;
+                }
+                const size_t dplane = (size_t)(b * a.C + j) * plane_elems;
+                const int pitchB = a.pitch * 4;
+                const long long o0B = (long long)(y0 + FT * it + F) * pitchB + (long long)((F + xw) * 4);
+                EpiArgs e;
+                e.u = reinterpret_cast<const float2 *>(filt) + tid;
+                e.sa = reinterpret_cast<const char *>(a.state_in + dplane) + o0B;
+                e.sb = e.sa + (long long)Lp * pitchB;
+                e.oplane = a.out + dplane;
+                e.oa = reinterpret_cast<char *>(e.oplane) + o0B;
+                e.ob = e.oa + (long long)Lp * pitchB;
+                e.pitchB = pitchB;
+                e.pitch = a.pitch;
+                e.H = a.H;
+                e.W = a.W;
+                e.ya0 = y0 + FT * it;
+                e.Lp = Lp;
+                e.xw = xw;
+                e.xoff = xw < F ? a.W : (xw >= a.W - F ? -a.W : 0);
+                e.row_wrap = a.row_wrap;
+                e.mu = g_mu;
+                e.nc2 = g_nc2;
+                e.w2 = g_w2;
+                e.wn = g_wn;
+                e.dt = a.dt;
+                e.peer_up = a.final_src && a.peer_up_out ? a.peer_up_out + dplane : nullptr;
+                e.peer_dn = a.final_src && a.peer_dn_out ? a.peer_dn_out + dplane : nullptr;
+                const bool euler = a.final_src && lenia;
+                float2 st[FT];
 #if MARCH_PREFETCH_EPI
-            if (col_ok && euler) {
-                if (edge) epilogue_prefetch<true>(e, st);
-                else epilogue_prefetch<false>(e, st);
-            }
+                if (!pro && col_ok && euler) {
+                    if (edge == 2) epilogue_prefetch<2>(e, st);
+                    else epilogue_prefetch<0>(e, st);
+                }
 #endif
-            if (!pro) __syncthreads();
-            // ---- inverse transforms (groups 0-7) | forward transforms of the block needed next (groups 8-15, last destination);
-            //      prologue rounds: forward transforms on all 16 groups
-            if (!pro && grp < FT) {
-                inverse_row(filt + grp * ROWP4, tw, lane16);
-            } else if (do_fwd) {
+                if (!pro) __syncthreads();
+                // ---- inverse transforms (groups 0-7) | forward transforms of the block needed next (groups 8-15, last destination);
+                //      prologue rounds: forward transforms on all 16 groups
+                if (!pro && grp < FT) {
+                    inverse_row(filt + grp * ROWP4, tw, lane16);
+                } else if (do_fwd) {
 #if !MARCH_PREFETCH
-                forward_fetch(zf, vf);
+                    forward_fetch(zf, vf);
 #endif
-                forward_compute(vf, ring + (zf % RING) * ROWP4, tw, lane16);
-            }
-            if (pro) continue;
-            __syncthreads();
+                    forward_compute(vf, ring + (zf % RING) * ROWP4, tw, lane16);
+                }
+                if (pro) continue;
+                __syncthreads();
 #if !MARCH_PREFETCH_EPI
-            if (col_ok && euler) {
-                if (edge) epilogue_prefetch<true>(e, st);
-                else epilogue_prefetch<false>(e, st);
-            }
+                if (col_ok && euler) {
+                    if (edge == 2) epilogue_prefetch<2>(e, st);
+                    else epilogue_prefetch<0>(e, st);
+                }
 #endif
-            // ---- epilogue: growth + weighted source sum (+ Euler / clamp), sample n = tid of the 8 row pairs
-            if (col_ok) {
-                if (SINGLE || !a.acc_in) {
-                    if (euler) { if (edge) epilogue<true, false, true>(e, st); else epilogue<false, false, true>(e, st); }
-                    else { if (edge) epilogue<true, false, false>(e, st); else epilogue<false, false, false>(e, st); }
-                } else {
-                    if (euler) { if (edge) epilogue<true, true, true>(e, st); else epilogue<false, true, true>(e, st); }
-                    else { if (edge) epilogue<true, true, false>(e, st); else epilogue<false, true, false>(e, st); }
+                // ---- epilogue: growth + weighted source sum (+ Euler / clamp), sample n = tid of the 8 row pairs
+                if (col_ok) {
+#define MARCH_EPI(ACC, EUL)                                   \
+    do {                                                      \
+        if (edge == 2) epilogue<2, ACC, EUL>(e, st);          \
+        else if (edge == 1) epilogue<1, ACC, EUL>(e, st);     \
+        else epilogue<0, ACC, EUL>(e, st);                    \
+    } while (0)
+                    if (SINGLE || !a.acc_in) {
+                        if (euler) MARCH_EPI(false, true);
+                        else MARCH_EPI(false, false);
+                    } else {
+                        if (euler) MARCH_EPI(true, true);
+                        else MARCH_EPI(true, false);
+                    }
+#undef MARCH_EPI
                 }
             }
         }
-    }
-    // row slab: this CTA's share of the halo is in the neighbours' memory -> release it and bump their arrival counters
-    if (a.final_src && (a.sig_up || a.sig_dn) && (band == 0 || band == a.nbands - 1)) {
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            if (band == 0 && a.sig_up) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(a.sig_up) : "memory");
-            if (band == a.nbands - 1 && a.sig_dn) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(a.sig_dn) : "memory");
+        // row slab: this band's share of the halo is in the neighbours' memory -> release it and bump their arrival counters
+        if (a.final_src && (a.sig_up || a.sig_dn) && (top || bot)) {
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) {
+                if (top && a.sig_up) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(a.sig_up) : "memory");
+                if (bot && a.sig_dn) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(a.sig_dn) : "memory");
+            }
         }
     }
 }
@@ -722,12 +852,38 @@ static int march_launch(march::Args a, int B, int C, int k_mult, int H, int W, i
     a.Lp = march::choose_lp(H, W, B, C);
     a.niter = a.Lp / march::FT;
     a.nbands = ceil_div(H, 2 * a.Lp);
-    if (band_begin == 0 && band_end == 0) band_end = a.nbands;
-    B200CA_REQUIRE(band_begin >= 0 && band_end <= a.nbands && band_begin <= band_end, "lenia_step_march: band range [%d,%d) outside [0,%d)",
-                   band_begin, band_end, a.nbands);
-    if (band_begin == band_end) return 0;
-    a.band0 = band_begin;
-    dim3 grid(ceil_div(W, march::V), band_end - band_begin, B);
+    int job_waves = MARCH_JOB_WAVES;
+#ifdef B200CA_DEV
+    if (const char *e = getenv("B200CA_MARCH_WAVES")) job_waves = atoi(e);
+    if (const char *e = getenv("B200CA_MARCH_STAGGER")) a.stagger_ns = (unsigned)atoi(e);
+#endif
+    dim3 grid;
+    if (band_begin == 0 && band_end == 0 && job_waves > 0) {
+        // balanced launch: the whole world / slab, cut into equal runs of 16-row units for one wave of CTAs (see the kernel)
+        a.jobs = 1;
+        a.units = ceil_div(H, 2 * march::FT);
+        a.strips = ceil_div(W, march::V);
+        const long long ncols = (long long)a.strips * B, total = a.units * ncols;
+        const long long G = std::min<long long>(total, 2LL * num_sms() * job_waves);
+        grid = dim3((unsigned)G, 1, 1);
+        // equal runs of the whole (column, unit) space, or every column cut into k equal bands: whichever leaves the busiest CTA
+        // with fewer rounds (a run pays march::PRO_UNITS rounds for every column it enters)
+        if (ncols <= G) {
+            const long long k = std::min<long long>(G / ncols, a.units);
+            const long long rounds_split = ceil_div64(a.units, k), rounds_runs = ceil_div64((a.units + march::PRO_UNITS) * ncols, G);
+            if (rounds_split <= rounds_runs) {
+                a.split_k = (int)k;
+                grid = dim3((unsigned)(k * ncols), 1, 1);
+            }
+        }
+    } else {
+        if (band_begin == 0 && band_end == 0) band_end = a.nbands;
+        B200CA_REQUIRE(band_begin >= 0 && band_end <= a.nbands && band_begin <= band_end, "lenia_step_march: band range [%d,%d) outside [0,%d)",
+                       band_begin, band_end, a.nbands);
+        if (band_begin == band_end) return 0;
+        a.band0 = band_begin;
+        grid = dim3(ceil_div(W, march::V), band_end - band_begin, B);
+    }
     for (int s = 0; s < a.NS; ++s) {
         a.src = s;
         a.acc_in = s > 0;
@@ -736,7 +892,8 @@ static int march_launch(march::Args a, int B, int C, int k_mult, int H, int W, i
         else B200CA_CUDA(launch_pdl(march::lenia_march_kernel<false>, grid, dim3(march::THREADS), march::SMEM, st, a));
     }
     B200CA_LAUNCH_CHECK("lenia_march_kernel");
-    note_variant("lenia_march<%s,Lp=%d%s>x%d", C == 1 ? "single" : "multi", a.Lp, (a.sig_up || a.sig_dn) ? ",p2p-halo" : "", a.NS);
+    if (a.jobs) note_variant("lenia_march<%s,balanced:%u%s%s>x%d", C == 1 ? "single" : "multi", grid.x, a.split_k ? ",split" : "", (a.sig_up || a.sig_dn) ? ",p2p-halo" : "", a.NS);
+    else note_variant("lenia_march<%s,Lp=%d%s>x%d", C == 1 ? "single" : "multi", a.Lp, (a.sig_up || a.sig_dn) ? ",p2p-halo" : "", a.NS);
     return 0;
 }
 

@@ -440,3 +440,41 @@ def test_lenia_kernel_sizes_vs_oracle(ks, path):
     ref = orc.lenia_step(s0, K, mu, sg, w, 0.1)
     err = (a.state.cpu() - ref).abs().max().item()
     assert err <= TOL, f"ks={ks} {path}: {err:.2e}"
+
+
+@pytest.mark.parametrize("C,B,shape", [(1, 5, (1000, 500)), (1, 3, (1024, 1024)), (3, 4, (600, 460)), (1, 2, (2056, 230)), (1, 9, (40, 300))])
+def test_march_balanced_runs_cross_columns(C, B, shape):
+    """The marching kernel's balanced launch cuts the (world, strip, 16-row unit) space into equal runs, one per CTA
+    (csrc/lenia_march.cu): a run starts and ends anywhere in a column of bands and may cross into the next strip or the next
+    world.  Batches of worlds with their own parameters (lenia.py:19-29) and heights that are not multiples of 16, so that the
+    runs hit every kind of seam; two steps, the second from the kernel's own framed output."""
+    import pyca_b200
+
+    sets = []
+    for name in ("abominable_mongolic", "bedfast_laplace"):
+        dd = params_dict(load_npz(f"params_lenia_{name}.npz"))
+        if C != 3:
+            dd = sliced(dd, C)
+        pd = pyca_b200.LeniaParams(param_dict=dd, channels=C).param_dict   # sanitised as the constructor does (leniaparams.py)
+        pd = {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in pd.items()}
+        sets.append((pd, orc.lenia_kernel(pd["beta"], pd["mu_k"], pd["sigma_k"], 31), pd["mu"], pd["sigma"], pd["weights"]))
+    pick = [sets[i % 2] for i in range(B)]
+    d = {k: torch.cat([p[0][k] for p in pick], 0) for k in ["mu", "sigma", "beta", "mu_k", "sigma_k", "weights"]}
+    d["k_size"] = 31
+    g = torch.Generator().manual_seed(B * 100 + C)
+    s0 = torch.rand(B, C, *shape, generator=g)
+    a = pyca_b200.Lenia((B, *shape), num_channels=C, params=d, state_init=s0, device="cuda", conv_path="fft")
+    pyca_b200._lib.variants(reset=True)
+    a.step()
+    got = pyca_b200._lib.variants(reset=True)
+    assert any(v.startswith(f"lenia_march<{'single' if C == 1 else 'multi'},balanced:") for v in got), got
+
+    def ref_step(s):
+        return torch.cat([orc.lenia_step(s[i:i + 1], p[1], p[2], p[3], p[4], 0.1) for i, p in enumerate(pick)], 0)
+
+    ref = ref_step(s0)
+    err = (a.state.cpu() - ref).abs().max().item()
+    assert err <= TOL, f"step 1: {err:.2e}"
+    a.step()
+    err2 = (a.state.cpu() - ref_step(ref)).abs().max().item()
+    assert err2 <= 3 * TOL, f"step 2: {err2:.2e}"
