@@ -264,23 +264,6 @@ __device__ __forceinline__ void inverse_row(float4 *row4, const float2 *tw, int 
     for (int q = 0; q < 16; ++q) row2[t + 16 * q] = v[q];
 }
 
-// writes the periodic images (not the cell itself) of interior cell (y, x) into the frame; rare, kept out of line
-__device__ __noinline__ void store_mirrors(float *__restrict__ plane, int H, int W, int pitch, int y, int x, float v, bool row_wrap) {
-    const int fy = y + F, fx = x + F;
-    int ys[3], xs[3], ny = 0, nx = 0;
-    ys[ny++] = fy;
-    if (row_wrap) {
-        if (y < F) ys[ny++] = fy + H;
-        if (y >= H - F) ys[ny++] = fy - H;
-    }
-    xs[nx++] = fx;
-    if (x < F) xs[nx++] = fx + W;
-    if (x >= W - F) xs[nx++] = fx - W;
-    for (int a = 0; a < ny; ++a)
-        for (int b = 0; b < nx; ++b)
-            if (a | b) plane[(size_t)ys[a] * pitch + xs[b]] = v;
-}
-
 // Column FIR of 4 output row pairs (4*H4 .. 4*H4+3 of the current block of 8) for the thread's two frequencies.  The 34 input
 // rows start at row 4*H4 of ring block b0 and run through blocks b0 .. b0+4; `blk[i]` points at this thread's float4 of the
 // first row of block (b0 + i) % 5, so every load is pointer + immediate offset (no per-row wrap arithmetic).
@@ -315,7 +298,6 @@ struct EpiArgs {
     // arithmetic cost four integer instructions per row: 128 of the ~1000 instructions of a marching round).
     const char *sa, *sb;   // state, first row of the first / second half of this block of 8 row pairs (EULER)
     char *oa, *ob;         // output, same rows
-    float *oplane;
     int pitchB;            // row pitch in bytes
     int pitch, H, W, ya0, Lp, xw, row_wrap;
     int xoff;              // distance to this column's periodic x image (+-W for the 16 columns next to the world edge, else 0)
@@ -393,22 +375,34 @@ __device__ __forceinline__ void epilogue(const EpiArgs &e, const float2 (&st)[FT
                 pb[e.xoff] = v.y;
             }
         } else {
-            // x images (first / last strip of every row: 2 of 5 strips of a 1024-wide world) are two predicated stores; only the
-            // first / last 16 rows of a torus take the general out-of-line path
+            // rows beyond the world are skipped; the first / last 16 rows of a torus store their periodic y image (and the corner
+            // image) as well, the first / last 16 rows of a slab go to the neighbour's ghost rows.  All inline: a balanced launch
+            // ends with its slowest CTA, and the out-of-line image routine made the four rounds per column that touch these rows
+            // cost as much as eight.
             const int ya = e.ya0 + r, yb = ya + e.Lp;
             const int xoff = e.xoff;
             if (ya < e.H) {
                 float *p = row_ptr(e.oa, r, e.pitchB);
                 *p = v.x;
-                if (e.row_wrap && (ya < F || ya >= e.H - F)) store_mirrors(e.oplane, e.H, e.W, e.pitch, ya, e.xw, v.x, true);
-                else if (xoff) p[xoff] = v.x;
+                if (xoff) p[xoff] = v.x;
+                const int yoff = !e.row_wrap ? 0 : (ya < F ? e.H : (ya >= e.H - F ? -e.H : 0));
+                if (yoff) {
+                    float *q = p + (long long)yoff * e.pitch;
+                    *q = v.x;
+                    if (xoff) q[xoff] = v.x;
+                }
                 store_peer(e, ya, v.x);
             }
             if (yb < e.H) {
                 float *p = row_ptr(e.ob, r, e.pitchB);
                 *p = v.y;
-                if (e.row_wrap && (yb < F || yb >= e.H - F)) store_mirrors(e.oplane, e.H, e.W, e.pitch, yb, e.xw, v.y, true);
-                else if (xoff) p[xoff] = v.y;
+                if (xoff) p[xoff] = v.y;
+                const int yoff = !e.row_wrap ? 0 : (yb < F ? e.H : (yb >= e.H - F ? -e.H : 0));
+                if (yoff) {
+                    float *q = p + (long long)yoff * e.pitch;
+                    *q = v.y;
+                    if (xoff) q[xoff] = v.y;
+                }
                 store_peer(e, yb, v.y);
             }
         }
@@ -634,8 +628,7 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
                 e.u = reinterpret_cast<const float2 *>(filt) + tid;
                 e.sa = reinterpret_cast<const char *>(a.state_in + dplane) + o0B;
                 e.sb = e.sa + (long long)Lp * pitchB;
-                e.oplane = a.out + dplane;
-                e.oa = reinterpret_cast<char *>(e.oplane) + o0B;
+                e.oa = reinterpret_cast<char *>(a.out + dplane) + o0B;
                 e.ob = e.oa + (long long)Lp * pitchB;
                 e.pitchB = pitchB;
                 e.pitch = a.pitch;
