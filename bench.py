@@ -756,8 +756,8 @@ class GolWL(Workload):
 
 
 class MaceSlabWL(Workload):
-    """MaCE-XChan 4096^2 C=3 as ONE torus in row slabs: two NCCL exchanges per step (affinity rows, state
-    rows); `sharded` block of the N > 1 runs."""
+    """MaCE-XChan 4096^2 C=3 as ONE torus in row slabs: two exchanges per step (affinity rows, state rows),
+    each one P2P push kernel per rank (NCCL send/recv as the fallback); `sharded` block of the N > 1 runs."""
     scaling = "strong"
 
     def __init__(self, rank, world, device, H, W, name="mace_xchan_4k"):
@@ -770,11 +770,19 @@ class MaceSlabWL(Workload):
 
     def setup(self):
         import pyca_b200
-        from pyca_b200.slab import MaceSlabCUDA
+        from pyca_b200.slab import MaceSlabCUDA, MaceSlabP2P
 
         d, _ = load_params("params_xchan_arborical_asbestosis.npz")
         self.params = pyca_b200.LeniaParams(param_dict=d)
-        self.slab = MaceSlabCUDA(self.params, 3, self.H, self.W, self.rank, self.world, device=self.device, beta=6.0, alpha=0.03)
+        self.halo = "p2p"
+        try:
+            if os.environ.get("B200CA_SLAB_HALO", "p2p") != "p2p":
+                raise RuntimeError("forced")
+            self.slab = MaceSlabP2P(self.params, 3, self.H, self.W, self.rank, self.world, device=self.device, beta=6.0, alpha=0.03)
+        except Exception as e:
+            log(f"P2P-halo MaCE slabs unavailable ({e!r}): NCCL send/recv slabs")
+            self.halo = "nccl"
+            self.slab = MaceSlabCUDA(self.params, 3, self.H, self.W, self.rank, self.world, device=self.device, beta=6.0, alpha=0.03)
         self.slab.set_interior(self._full_world()[:, :, self.slab.r0:self.slab.r1])
 
     def step(self):
@@ -791,7 +799,7 @@ class MaceSlabWL(Workload):
 
     def config(self):
         c = static_config(self.name, self.world)
-        c["partition"] = f"{self.world} row slabs, two NCCL halo exchanges per step (affinity rows, state rows)"
+        c["partition"] = f"{self.world} row slabs, two halo exchanges per step (2 affinity rows, 16 state rows)"
         return c
 
     def check_against_single_gpu(self, steps=2):
@@ -808,7 +816,8 @@ class MaceSlabWL(Workload):
         mass = self.slab.interior().double().sum().reshape(1)
         torch.distributed.all_reduce(mass)
         self.single = single
-        return {"steps": steps, "max_abs_err": err, "tolerance": 1e-5, "mass": float(mass.item()), "mass_initial": float(full.double().sum().item())}
+        return {"steps": steps, "max_abs_err": err, "tolerance": 1e-5, "mass": float(mass.item()), "mass_initial": float(full.double().sum().item()),
+                "timed_out": bool(self.slab.timed_out()) if hasattr(self.slab, "timed_out") else False}
 
 
 class MaceWL(Workload):

@@ -201,6 +201,12 @@ int b200ca_lenia_step_march_slab(const float *state_in, float *state_out, const 
 int b200ca_halo_push(const void *src_up, void *dst_up, const void *src_dn, void *dst_dn, int64_t nbytes, uint32_t *up_ready,
                      uint32_t *dn_ready, const uint32_t *my_ready, uint32_t *up_arrived, uint32_t *dn_arrived,
                      const uint32_t *my_arrived, uint32_t epoch, uint32_t *ticket, uint32_t *err_flag, void *stream);
+/* The same for `nplanes` row blocks per direction, `plane_stride_bytes` apart in every buffer (the (b, c) planes of a framed Lenia /
+ * MaCE slab: the MaCE slabs exchange affinity rows and state rows this way, slab.py: MaceSlabP2P). */
+int b200ca_halo_push_planes(const void *src_up, void *dst_up, const void *src_dn, void *dst_dn, int64_t nbytes, int nplanes,
+                            int64_t plane_stride_bytes, uint32_t *up_ready, uint32_t *dn_ready, const uint32_t *my_ready,
+                            uint32_t *up_arrived, uint32_t *dn_arrived, const uint32_t *my_arrived, uint32_t epoch, uint32_t *ticket,
+                            uint32_t *err_flag, void *stream);
 
 /* Mass-conserving redistribution (+ optional cross-channel mixing).  Replaces
  * MaCELenia._mace_step (macelenia.py:89-120) after the affinity, and

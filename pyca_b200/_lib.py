@@ -62,6 +62,8 @@ SIGNATURES = {
                                              c_void_p, c_void_p]),
     "b200ca_halo_push": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_uint32, c_void_p, c_void_p, c_void_p]),
+    "b200ca_halo_push_planes": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p]),
     "b200ca_mace_redistribute": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_float,
                                          c_int, c_void_p]),
     "b200ca_lenia_conv_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

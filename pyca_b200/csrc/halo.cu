@@ -21,6 +21,8 @@ struct HaloArgs {
     const int4 *src_up, *src_dn;   // my first / last owned rows
     int4 *dst_up, *dst_dn;         // the up neighbour's bottom ghost rows / the down neighbour's top ghost rows (peer mappings)
     long long n16;                 // 16-byte words per block of rows
+    int nplanes;                   // blocks per direction (the planes of a framed Lenia slab), `stride16` 16-byte words apart
+    long long stride16;
     unsigned *up_ready, *dn_ready;       // neighbours' counters bumped in A
     const unsigned *my_ready;            // [0] bumped by the up neighbour, [1] by the down neighbour
     unsigned *up_arrived, *dn_arrived;   // neighbours' counters bumped in D
@@ -59,9 +61,12 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const HaloArgs a) {
     }
     __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;  // C
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n16; i += stride) {
-        a.dst_up[i] = a.src_up[i];
-        a.dst_dn[i] = a.src_dn[i];
+    for (int p = 0; p < a.nplanes; ++p) {
+        const long long o = p * a.stride16;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n16; i += stride) {
+            a.dst_up[o + i] = a.src_up[o + i];
+            a.dst_dn[o + i] = a.src_dn[o + i];
+        }
     }
     __threadfence_system();  // D
     __syncthreads();
@@ -80,12 +85,15 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const HaloArgs a) {
 
 using namespace b200ca;
 
-extern "C" int b200ca_halo_push(const void *src_up, void *dst_up, const void *src_dn, void *dst_dn, int64_t nbytes, uint32_t *up_ready,
-                                uint32_t *dn_ready, const uint32_t *my_ready, uint32_t *up_arrived, uint32_t *dn_arrived,
-                                const uint32_t *my_arrived, uint32_t epoch, uint32_t *ticket, uint32_t *err_flag, void *stream) {
+extern "C" int b200ca_halo_push_planes(const void *src_up, void *dst_up, const void *src_dn, void *dst_dn, int64_t nbytes, int nplanes,
+                                       int64_t plane_stride_bytes, uint32_t *up_ready, uint32_t *dn_ready, const uint32_t *my_ready,
+                                       uint32_t *up_arrived, uint32_t *dn_arrived, const uint32_t *my_arrived, uint32_t epoch,
+                                       uint32_t *ticket, uint32_t *err_flag, void *stream) {
     B200CA_REQUIRE(src_up && dst_up && src_dn && dst_dn && up_ready && dn_ready && my_ready && up_arrived && dn_arrived && my_arrived && ticket,
                    "halo_push: null pointer");
     B200CA_REQUIRE(nbytes > 0 && nbytes % 16 == 0, "halo_push: the row blocks must be multiples of 16 bytes (got %lld)", (long long)nbytes);
+    B200CA_REQUIRE(nplanes >= 1 && (nplanes == 1 || (plane_stride_bytes >= nbytes && plane_stride_bytes % 16 == 0)),
+                   "halo_push: bad plane count / stride (%d, %lld)", nplanes, (long long)plane_stride_bytes);
     B200CA_REQUIRE((((uintptr_t)src_up | (uintptr_t)dst_up | (uintptr_t)src_dn | (uintptr_t)dst_dn) & 15) == 0, "halo_push: 16-byte alignment");
     HaloArgs a;
     a.src_up = static_cast<const int4 *>(src_up);
@@ -93,6 +101,8 @@ extern "C" int b200ca_halo_push(const void *src_up, void *dst_up, const void *sr
     a.dst_up = static_cast<int4 *>(dst_up);
     a.dst_dn = static_cast<int4 *>(dst_dn);
     a.n16 = nbytes / 16;
+    a.nplanes = nplanes;
+    a.stride16 = plane_stride_bytes / 16;
     a.up_ready = up_ready;
     a.dn_ready = dn_ready;
     a.my_ready = my_ready;
@@ -105,6 +115,13 @@ extern "C" int b200ca_halo_push(const void *src_up, void *dst_up, const void *sr
     const int blocks = (int)std::min<long long>(32, (a.n16 + 255) / 256);
     halo_push_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a);
     B200CA_LAUNCH_CHECK("halo_push_kernel");
-    note_variant("halo_push<blocks=%d>", blocks);
+    note_variant("halo_push<blocks=%d,planes=%d>", blocks, nplanes);
     return 0;
+}
+
+extern "C" int b200ca_halo_push(const void *src_up, void *dst_up, const void *src_dn, void *dst_dn, int64_t nbytes, uint32_t *up_ready,
+                                uint32_t *dn_ready, const uint32_t *my_ready, uint32_t *up_arrived, uint32_t *dn_arrived,
+                                const uint32_t *my_arrived, uint32_t epoch, uint32_t *ticket, uint32_t *err_flag, void *stream) {
+    return b200ca_halo_push_planes(src_up, dst_up, src_dn, dst_dn, nbytes, 1, 0, up_ready, dn_ready, my_ready, up_arrived, dn_arrived, my_arrived,
+                                   epoch, ticket, err_flag, stream);
 }

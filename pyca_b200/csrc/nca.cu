@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) nca_update_simt_kernel(const Nca
 // zeroes the cells that were written non-zero but have no alive (new alpha > 0.1) cell in their 3x3 torus window
 __global__ void nca_life_kernel(float *__restrict__ state, const uint32_t *__restrict__ alive_bits,
                                 const uint32_t *__restrict__ nz_bits, int B, int H, int W, int wpr) {
+    pdl_wait_then_release();   // the bit planes and the state are the update kernel's output
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y, b = blockIdx.z;
     if (x >= W) return;
@@ -245,7 +246,7 @@ extern "C" int b200ca_nca_step_shard(const float *state_in, float *state_out, co
     }
     dim3 g2(ceil_div(W, 128), H, B);
     B200CA_REQUIRE(H <= 65535, "nca_step: H too large for the life pass");
-    nca_life_kernel<<<g2, 128, 0, st>>>(state_out, a.alive_bits, a.nz_bits, B, H, W, a.wpr);
+    B200CA_CUDA(launch_pdl(nca_life_kernel, g2, dim3(128), (size_t)0, st, state_out, (const uint32_t *)a.alive_bits, (const uint32_t *)a.nz_bits, B, H, W, a.wpr));
     B200CA_LAUNCH_CHECK("nca_life_kernel");
     return 0;
 }

@@ -197,6 +197,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) nca_update_tc_kernel(const NcaArg
     }
     fence_proxy_async();  // weight images are read by the tensor core (async proxy)
     tc_fence_before();
+    // programmatic dependent launch: everything above (57 KB of weights into shared memory, barriers, TMEM) overlaps the tail of the
+    // previous step's life pass; the state and the bit planes are only touched below
+    pdl_wait_then_release();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot + gid * 128;                   // this group's 128 columns
@@ -455,7 +458,7 @@ int nca_step_tc(const NcaArgs &a, cudaStream_t st) {
     const int tiles_x = ceil_div(a.W, 32), tiles_y = ceil_div(a.H, 4);
     const long long ntiles = (long long)tiles_x * tiles_y * a.B;
     const int grid = (int)std::min<long long>(ceil_div64(ntiles, NG), (long long)num_sms());
-    nca_update_tc_kernel<<<grid, NTHREADS, SM_TOTAL, st>>>(a, tiles_x, tiles_y);
+    B200CA_CUDA(launch_pdl(nca_update_tc_kernel, dim3(grid), dim3(NTHREADS), (size_t)SM_TOTAL, st, a, tiles_x, tiles_y));
     B200CA_LAUNCH_CHECK("nca_update_tc_kernel");
     note_variant("nca_update_tc<grid=%d>", grid);
     return 0;

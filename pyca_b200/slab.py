@@ -551,3 +551,61 @@ class MaceSlabCUDA(LeniaSlabCUDA):
         self.redistribute_phase()
         if self.world > 1:
             self.exchange(self.buf, group)
+
+
+class MaceSlabP2P(MaceSlabCUDA):
+    """MaceSlabCUDA whose two exchanges per step (affinity rows, state rows) are ONE kernel per rank each (csrc/halo.cu,
+    `b200ca_halo_push_planes`): the rows are stored straight into the neighbours' frame rows over NVLink and the ranks synchronise
+    through counters in symmetric memory.  With NCCL send/recv the two exchanges cost more than the 0.12 ms slab step itself on
+    8 GPUs (efficiency 0.44).  The state buffers and the affinity buffer live in one symmetric allocation.  Collective: every
+    rank calls `step()` / `set_interior()` / `close()` the same number of times."""
+
+    AFF_ROWS = 2   # the redistribution reads the affinity on a 2-row halo (macelenia.py:103-118: 3x3 of a 3x3-normalised field)
+
+    def __init__(self, lenia_params, C, H, W, rank, world, device="cuda", beta=8.0, alpha=None, conv_path="auto", group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        super().__init__(lenia_params, C, H, W, rank, world, device=device, beta=beta, alpha=alpha, conv_path=conv_path)
+        if world < 2:
+            raise ValueError("MaceSlabP2P needs at least two ranks (MaceSlabCUDA runs a single slab)")
+        self.group = group if group is not None else dist.group.WORLD
+        n = self.B * self.C * self.rows * self.pitch
+        self._n = n
+        self._sym = symm.empty(3 * n + 64, dtype=torch.float32, device=self.device)
+        self._sym.zero_()
+        self._hdl = symm.rendezvous(self._sym, self.group)
+        shape = (self.B, self.C, self.rows, self.pitch)
+        self.bufs = [self._sym[i * n:(i + 1) * n].view(shape) for i in range(2)]
+        self.aff = self._sym[2 * n:3 * n].view(shape)
+        self._counters = self._sym[3 * n:3 * n + 64].view(torch.int32)   # [0:2] ready, [2:4] arrived, [4] ticket, [5] error
+        self._base = list(self._hdl.buffer_ptrs)
+        self._up, self._down = ring_neighbours(rank, world)
+        self._cnt = 3 * n * 4
+        self.epoch = 0
+        self.__dict__.pop("_exchange_ops", None)
+
+    def exchange(self, t=None, group=None):
+        from . import _lib
+
+        t = self.buf if t is None else t
+        nrows = self.AFF_ROWS if t.data_ptr() == self.aff.data_ptr() else self.F
+        F, hl, row = self.F, self.hl, self.pitch * 4
+        off = t.data_ptr() - self._sym.data_ptr()
+        me, up, dn = self._base[self.rank] + off, self._base[self._up] + off, self._base[self._down] + off
+        cme, cup, cdn = self._base[self.rank] + self._cnt, self._base[self._up] + self._cnt, self._base[self._down] + self._cnt
+        self.epoch += 1
+        with _lib.device_guard(self.device):
+            # my first rows -> the up neighbour's bottom frame rows; my last rows -> the down neighbour's top frame rows
+            _lib.call("b200ca_halo_push_planes", me + F * row, up + (hl + F) * row, me + (hl + F - nrows) * row, dn + (F - nrows) * row,
+                      nrows * row, self.B * self.C, self.rows * row, cup + 4, cdn, cme, cup + 12, cdn + 8, cme + 8,
+                      self.epoch & 0xFFFFFFFF, cme + 16, cme + 20, _lib.current_stream(self.device))
+
+    def timed_out(self) -> bool:
+        return bool(self._counters[5].item())
+
+    def close(self):
+        if getattr(self, "_sym", None) is not None:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(self.group)
+            self.bufs = []
+            self.aff = self._counters = self._hdl = self._sym = None

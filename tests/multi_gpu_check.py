@@ -130,19 +130,26 @@ def main():
     Hh, Ww = 192 * world, 320
     g = torch.Generator().manual_seed(11)
     full = 1.5 * torch.rand(1, 3, Hh, Ww, generator=g)
-    single = pyca_b200.MaCELeniaXChan((Hh, Ww), params=dict(dx), state_init=full, device=dev)
-    ms = MaceSlabCUDA(pyca_b200.LeniaParams(param_dict=dict(dx)), 3, Hh, Ww, rank, world, device=dev, beta=6.0, alpha=0.03)
-    ms.set_interior(full[:, :, ms.r0:ms.r1].to(dev))
-    for _ in range(3):
-        single.step()
-        ms.step()
-    torch.cuda.synchronize()
-    err = (ms.interior() - single.state[:, :, ms.r0:ms.r1]).abs().max().item()
-    mass = ms.interior().double().sum().reshape(1)
-    dist.all_reduce(mass)
-    m0 = float(full.double().sum())
-    print(f"[rank {rank}] MaCE-XChan slab: max |slab - torus| = {err:.2e}; mass {float(mass.item()):.4f} vs {m0:.4f}", flush=True)
-    ok &= err <= 1e-5 and abs(float(mass.item()) - m0) <= 1e-5 * m0
+    from pyca_b200.slab import MaceSlabP2P
+
+    for cls in (MaceSlabCUDA, MaceSlabP2P):     # NCCL send/recv exchanges, then one P2P push kernel per exchange (csrc/halo.cu)
+        single = pyca_b200.MaCELeniaXChan((Hh, Ww), params=dict(dx), state_init=full, device=dev)
+        ms = cls(pyca_b200.LeniaParams(param_dict=dict(dx)), 3, Hh, Ww, rank, world, device=dev, beta=6.0, alpha=0.03)
+        ms.set_interior(full[:, :, ms.r0:ms.r1].to(dev))
+        for _ in range(5):
+            single.step()
+            ms.step()
+        torch.cuda.synchronize()
+        err = (ms.interior() - single.state[:, :, ms.r0:ms.r1]).abs().max().item()
+        mass = ms.interior().double().sum().reshape(1)
+        dist.all_reduce(mass)
+        m0 = float(full.double().sum())
+        to = ms.timed_out() if hasattr(ms, "timed_out") else False
+        print(f"[rank {rank}] MaCE-XChan slab ({cls.__name__}): max |slab - torus| = {err:.2e}; mass {float(mass.item()):.4f} vs {m0:.4f}; "
+              f"timed out: {to}", flush=True)
+        ok &= err <= 1e-5 and abs(float(mass.item()) - m0) <= 1e-5 * m0 and not to
+        if hasattr(ms, "close"):
+            ms.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()
