@@ -348,12 +348,13 @@ class Workload:
     def cpu_sample(self): ...
 
 
-E2E_DEPTH = 3
+E2E_DEPTH = 8
 
 
 def _pipe_setup(wl, auto, shape):
     """End-to-end path: pyca_b200.LeniaHostPipe (b200ca_lenia_pipe_* in the C ABI) -- E2E_DEPTH lanes on their own streams;
-    every world is copied up from its own pinned host buffer, stepped, and copied down into its own pinned host buffer."""
+    every world is copied up from its own pinned host buffer, stepped, and stored into its own pinned host buffer (by the
+    unframing kernel, over PCIe: b200ca_lenia_pipe_submit)."""
     from pyca_b200.pipeline import LeniaHostPipe
 
     wl.pipe = LeniaHostPipe(auto, depth=E2E_DEPTH)
@@ -1356,7 +1357,8 @@ def main():
         e2e = {"value": cells * n_e2e / el / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": hb, "d2h_bytes_per_step": db,
                "ms_per_step": el / n_e2e * 1e3, "steps": n_e2e, "statistic": "median over >= 5 blocks of `steps` worlds (>= 0.15 s in all)",
                "api": (f"pyca_b200.LeniaHostPipe(auto, depth={E2E_DEPTH}).submit(pinned h_in, pinned h_out) = b200ca_lenia_pipe_submit: per "
-                       "world H2D -> step -> D2H, independent worlds overlapped on separate streams") if piped else
+                       "world H2D (copy engine) -> step -> the unframing kernel stores the result straight into the pinned host buffer over "
+                       "PCIe; independent worlds overlapped on separate streams") if piped else
                       "Automaton.state = <pinned host tensor>; step(); state -> pinned host tensor"}
         if piped:
             el_s, _, _ = run_e2e(wl.e2e_step_sync, max(3, min(args.steps, 20)))

@@ -180,6 +180,21 @@ extern "C" int b200ca_lenia_pipe_submit(void *pipe, const float *h_state_in, flo
     p->next = (p->next + 1) % p->depth;
     if (l.busy) B200CA_CUDA(cudaEventSynchronize(l.done));  // the lane's previous world has landed in its host buffer
     const int B = p->B, C = p->C, km = p->km, H = p->H, W = p->W;
+    // The result goes straight into the host buffer when it is pinned (mapped into the device's address space): the unframing
+    // kernel stores over PCIe (posted writes), which saves the device-to-host copy-engine operation and its stream hop
+    // (1024^2: 129 -> 114 us per world).  Reading the INPUT over PCIe from a kernel is slower than the copy engine (158 us), so
+    // the host-to-device direction stays a cudaMemcpyAsync.  Pageable host buffers take the copy engine both ways.
+    float *out_mapped = nullptr;
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, h_state_out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            out_mapped = static_cast<float *>(at.devicePointer);
+        else
+            (void)cudaGetLastError();
+    }
+#ifdef B200CA_DEV
+    if (const char *e = getenv("B200CA_PIPE_ZEROCOPY")) out_mapped = atoi(e) ? out_mapped : nullptr;
+#endif
     B200CA_CUDA(cudaMemcpyAsync(l.dense, h_state_in, p->dbytes, cudaMemcpyHostToDevice, l.st));
     int rc = b200ca_frame_load(l.dense, l.a, B, C, H, W, 1, l.st);
     float *src = l.a, *dst = l.b;
@@ -197,8 +212,12 @@ extern "C" int b200ca_lenia_pipe_submit(void *pipe, const float *h_state_in, flo
         dst = t;
     }
     if (rc) return rc;
-    if ((rc = b200ca_frame_store(src, l.dense, B, C, H, W, l.st))) return rc;
-    B200CA_CUDA(cudaMemcpyAsync(h_state_out, l.dense, p->dbytes, cudaMemcpyDeviceToHost, l.st));
+    if (out_mapped) {
+        if ((rc = b200ca_frame_store(src, out_mapped, B, C, H, W, l.st))) return rc;
+    } else {
+        if ((rc = b200ca_frame_store(src, l.dense, B, C, H, W, l.st))) return rc;
+        B200CA_CUDA(cudaMemcpyAsync(h_state_out, l.dense, p->dbytes, cudaMemcpyDeviceToHost, l.st));
+    }
     B200CA_CUDA(cudaEventRecord(l.done, l.st));
     l.busy = true;
     return 0;
