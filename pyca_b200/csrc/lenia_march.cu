@@ -763,22 +763,27 @@ using namespace b200ca;
 extern "C" int b200ca_lenia_march_supported(int H, int W) { return (H >= 2 * march::F && W >= 2 * march::F) ? 1 : 0; }
 
 // conv_path = 'auto' (profiles/r02_conv_paths.md has the measurements behind the rule), by kernel size, sources and world size:
-//   k_size <= 7: the direct kernel (evaluates the 7 x 7 footprint only: 28 folded FMAs per cell and pair instead of 496);
-//   k_size <= 11: direct, except for big single-source worlds (marching kernel) and small multi-source ones (hybrid);
-//   larger kernels (all of demo_data is k_size 31) take an FFT path, whose cost does not depend on the radius:
-//     one source kernel per destination: the two-kernel hybrid for small worlds (a single wave of CTAs: shorter serial
-//     chain), the marching kernel otherwise;  several sources: the hybrid (its fused kernel sums the sources in registers;
-//     the marching kernel accumulates through the output planes, one launch per source);
+//   one source kernel per destination (C = 1): big worlds (more than 1536^2 cells in the launch) take the marching kernel
+//     whatever the kernel size (4096^2: 95 us against 104 us for the direct kernel at k_size 5); smaller ones the direct
+//     kernel up to k_size 11 (it evaluates the (k/2+1) x k folded footprint only) and the two-kernel hybrid above (a single
+//     wave of CTAs: the shorter serial chain);
+//   several sources: k_size <= 7 direct; k_size <= 11 direct for big worlds, hybrid for small ones; larger kernels (all of
+//     demo_data is k_size 31): the marching kernel from 2560^2 cells up (C = 3, 4096^2: 784 us against 848 us), the hybrid below
+//     (its fused kernel sums the sources in registers; the marching kernel accumulates through the output planes, one launch
+//     per source: 140 us against 61 us at 1024^2);
 //   whatever the preferred path cannot do falls to the next one, the direct convolution last.
 extern "C" int b200ca_lenia_pick_algo_ks(int B, int NS, int H, int W, int ks) {
     const bool march_ok = b200ca_lenia_march_supported(H, W) != 0, rows_ok = b200ca_lenia_fft_length(H, W) > 0;
-    const bool small = (long long)B * H * W <= 1536LL * 1536LL;
-    if (ks <= 7) return B200CA_ALGO_DIRECT;
-    if (ks <= 11 && !(NS == 1 && !small && march_ok) && !(NS > 1 && small && rows_ok)) return B200CA_ALGO_DIRECT;
+    const long long cells = (long long)B * H * W;
+    const bool small = cells <= 1536LL * 1536LL;
     if (NS == 1) {
-        if (rows_ok && small) return B200CA_ALGO_FFT_ROWS;
-        return march_ok ? B200CA_ALGO_MARCH : (rows_ok ? B200CA_ALGO_FFT_ROWS : B200CA_ALGO_DIRECT);
+        if (!small && march_ok) return B200CA_ALGO_MARCH;
+        if (ks <= 11) return B200CA_ALGO_DIRECT;
+        return rows_ok ? B200CA_ALGO_FFT_ROWS : (march_ok ? B200CA_ALGO_MARCH : B200CA_ALGO_DIRECT);
     }
+    if (ks <= 7) return B200CA_ALGO_DIRECT;
+    if (ks <= 11 && !(small && rows_ok)) return B200CA_ALGO_DIRECT;
+    if (cells >= 2560LL * 2560LL && march_ok && ks > 11) return B200CA_ALGO_MARCH;
     if (rows_ok) return B200CA_ALGO_FFT_ROWS;
     return march_ok ? B200CA_ALGO_MARCH : B200CA_ALGO_DIRECT;
 }

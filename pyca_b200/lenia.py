@@ -54,14 +54,16 @@ def garbi_tables(p, B, C, k_mult):
 def pick_conv_algo(B, NS, H, W, march_ok=True, rows_ok=True, k_size=31):
     """conv_path='auto': which convolution kernel steps a (B, C, H, W) world with NS = C * k_mult source kernels per
     destination.  Measured on B200 (profiles/r02_conv_paths.md; all paths agree with the oracle to <= 1e-5):
-      * one source (C = 1): the marching kernel (lenia_march.cu) wins from 4096^2 up (118 vs 140 us at 4096^2, 1.26 vs 1.58 ms
-        at 16384^2: the spectra never leave shared memory); at 1024^2 the whole world is a single wave of CTAs and the
-        two-kernel hybrid (lenia_fft.cu, 512-thread small-world variant) has the shorter serial chain: 19.6 vs 22.1 us;
+      * one source (C = 1): the marching kernel (lenia_march.cu; the spectra never leave shared memory, one balanced wave of
+        CTAs) takes every launch of more than 1536^2 cells (95 us at 4096^2 against 141 us for the hybrid and 104 us for the
+        direct kernel at k_size 5; 1.27 ms at 16384^2); at 1024^2 the whole world is a single wave of CTAs and the two-kernel
+        hybrid (lenia_fft.cu, 512-thread small-world variant) has the shorter serial chain: 19.7 vs 22.0 us;
       * several sources: the hybrid's fused kernel keeps the per-destination sum over sources in registers, the marching kernel
-        accumulates it through the output planes, one launch per source (843 vs 932 us at 4096^2, C = 3);
+        accumulates it through the output planes, one launch per source: 61 vs 140 us at 1024^2 (C = 3), but 848 vs 784 us at
+        4096^2 -- the marching kernel from 2560^2 cells up;
       * the direct convolution (lenia.cu) is FMA-bound at R = 15 (385 us at 4096^2) but evaluates only the radius class of the
-        kernel: k_size <= 7 runs in 104 us at 4096^2 and beats both FFT paths, whose cost does not depend on the radius; it also
-        serves what the FFT paths do not (Fourier growth functions, worlds narrower than 32)."""
+        kernel: small kernels on small worlds (k_size <= 11 at 1024^2: 16.5-18.5 us); it also serves what the FFT paths do not
+        (Fourier growth functions, worlds narrower than 32)."""
     del march_ok, rows_ok   # (the library applies the same support checks)
     return ("direct", "fft_rows", "march")[_lib.lib().b200ca_lenia_pick_algo_ks(int(B), int(NS), int(H), int(W), int(k_size))]
 

@@ -112,20 +112,22 @@ def test_xchan_1k_vs_oracle():
     assert torch.allclose(m0.sum(), a.total_mass().cpu().sum(), rtol=1e-6)
 
 
-def test_xchan_4k_periodic_tiling():
-    """BASELINE configs[2]: 4096x4096 C=3 MaCE-XChan as 4x4 copies of a 1024^2 torus."""
+@pytest.mark.parametrize("path", ["auto", "fft_rows"])
+def test_xchan_4k_periodic_tiling(path):
+    """BASELINE configs[2]: 4096x4096 C=3 MaCE-XChan as 4x4 copies of a 1024^2 torus -- on the path `auto` picks (the marching
+    kernel, three source launches) and on the two-kernel hybrid (the big-world instantiations of its fused kernel)."""
     import pyca_b200
 
     P, K, mu, sg, w = xchan_params()
     g = torch.Generator().manual_seed(4)
     s0 = torch.rand(1, 3, 1024, 1024, generator=g)
     big = s0.cuda().repeat(1, 1, 4, 4)
-    a = pyca_b200.MaCELeniaXChan((4096, 4096), params=P, state_init=big, device="cuda")
+    a = pyca_b200.MaCELeniaXChan((4096, 4096), params=P, state_init=big, device="cuda", conv_path=path)
     m0 = float(a.total_mass().sum())
     launched()
     a.step()
     got = launched()
-    assert_variants(got, "xchan_4k")
+    assert_variants(got, "xchan_4k" if path == "auto" else "xchan_4k_hybrid")
     ref = orc.xchan_step(s0, K, mu, sg, w, 6.0, 0.03)
     err = tiles_err(a.state, ref)
     assert err <= TOL * max(1.0, float(ref.max())), f"{err:.2e}"

@@ -97,9 +97,11 @@ def test_conv_path_rule_and_band_heights_without_a_gpu():
     assert L.b200ca_lenia_pick_algo_ks(1, 1, 1024, 1024, 31) == ROWS          # one small world: two-kernel hybrid
     assert L.b200ca_lenia_pick_algo_ks(24, 1, 1024, 1024, 31) == MARCH        # the headline batch
     assert L.b200ca_lenia_pick_algo_ks(1, 1, 16384, 16384, 31) == MARCH
-    assert L.b200ca_lenia_pick_algo_ks(1, 3, 4096, 4096, 31) == ROWS          # several source channels
+    assert L.b200ca_lenia_pick_algo_ks(1, 3, 4096, 4096, 31) == MARCH         # several source channels: big worlds march,
+    assert L.b200ca_lenia_pick_algo_ks(1, 3, 1024, 1024, 31) == ROWS          # small ones take the hybrid
     assert L.b200ca_lenia_pick_algo_ks(1, 3, 4097, 4096, 31) == MARCH         # odd height: the hybrid cannot, the marching kernel can
-    assert L.b200ca_lenia_pick_algo_ks(1, 1, 4096, 4096, 7) == DIRECT         # small kernels: direct, whatever the world
+    assert L.b200ca_lenia_pick_algo_ks(1, 1, 4096, 4096, 7) == MARCH          # big single-channel worlds: marching at every kernel size
+    assert L.b200ca_lenia_pick_algo_ks(1, 1, 1024, 1024, 7) == DIRECT         # small kernels on small worlds: direct
     assert L.b200ca_lenia_pick_algo_ks(1, 3, 4096, 4096, 5) == DIRECT
     assert L.b200ca_lenia_pick_algo_ks(1, 1, 4096, 4096, 11) == MARCH and L.b200ca_lenia_pick_algo_ks(1, 1, 1024, 1024, 11) == DIRECT
     assert L.b200ca_lenia_pick_algo_ks(1, 1, 24, 24, 31) == DIRECT            # too small for the FFT paths
