@@ -57,6 +57,9 @@
 #ifndef MARCH_PRO_UNITS
 #define MARCH_PRO_UNITS 4
 #endif
+#ifndef MARCH_EARLY_U
+#define MARCH_EARLY_U 0      // the epilogue takes its 8 filtered samples into registers first; the barrier that frees `filt` for the
+#endif                       // next FIR follows those loads instead of the whole epilogue (its global loads / stores overlap the FIR)
 #ifndef MARCH_JOB_WAVES
 #define MARCH_JOB_WAVES 1    // balanced launches: grid = this many waves of CTAs (0: fixed-height bands for every launch)
 #endif
@@ -341,8 +344,8 @@ __device__ __forceinline__ void epilogue_prefetch(const EpiArgs &e, float2 (&st)
 // the first / last strip of a world (2 of the 5 strips of a 1024-wide world): the cells within 16 columns of the world edge store
 // their periodic x image as well (one predicated store per row -- as cheap as EDGE = 0, which matters because a balanced launch
 // ends when its slowest CTA does);  2: the general path (first / last 16 rows of a torus or a slab, rows beyond the world).
-template <int EDGE, bool ACC, bool EULER>
-__device__ __forceinline__ void epilogue(const EpiArgs &e, const float2 (&st)[FT]) {
+template <int EDGE, bool ACC, bool EULER, bool EARLY>
+__device__ __forceinline__ void epilogue(const EpiArgs &e, const float2 (&st)[FT], const float2 (&uu)[FT]) {
     float2 pv[FT];
     if (ACC) {
 #pragma unroll
@@ -355,7 +358,7 @@ __device__ __forceinline__ void epilogue(const EpiArgs &e, const float2 (&st)[FT
                  dt2 = make_float2(e.dt, e.dt);
 #pragma unroll
     for (int r = 0; r < FT; ++r) {
-        const float2 d = __fadd2_rn(e.u[r * 2 * ROWP4], nmu);
+        const float2 d = __fadd2_rn(EARLY ? uu[r] : e.u[r * 2 * ROWP4], nmu);
         const float2 q = __fmul2_rn(__fmul2_rn(d, d), nc2);
         float2 v = __ffma2_rn(make_float2(ex2_approx(q.x), ex2_approx(q.y)), w2, wn);
         if (ACC) v = __fadd2_rn(v, pv[r]);
@@ -438,6 +441,8 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
     }
     const int f = tid & 127, h = tid >> 7;
     const int fslot = 9 * (f >> 3) + (f & 7);            // this FIR thread's float4 in a padded spectra row
+    // single destination only: with the partial sums of earlier sources in registers as well the multi-destination kernel spills
+    constexpr bool EARLY_U = MARCH_EARLY_U && SINGLE;
     const bool lenia = a.mode == B200CA_MODE_LENIA;
     const bool edge_rows = a.row_wrap || a.peer_up_out || a.peer_dn_out;
     pdl_wait_then_release();  // the state is the previous step's output
@@ -600,7 +605,9 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
 #if MARCH_PREFETCH
                 if (do_fwd) forward_fetch(zf, vf);
 #endif
-                if (!pro) __syncthreads();  // ring rows of this iteration are complete; the previous epilogue is done with `filt`
+                // ring rows of this iteration are complete; the previous epilogue is done with `filt` (MARCH_EARLY_U: it said so itself,
+                // right after loading its samples -- only a band's first FIR still has to wait for the prologue's ring rows)
+                if (!pro && (!EARLY_U || (it == 0 && j == 0))) __syncthreads();
                 // ---- FIR: output pairs 4h .. 4h+3 of this block from ring rows (8 it + 4h) .. (+33), two frequencies per thread
                 if (!pro) {
                     const float4 *blk[NBLK];
@@ -674,12 +681,20 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
                 }
 #endif
                 // ---- epilogue: growth + weighted source sum (+ Euler / clamp), sample n = tid of the 8 row pairs
+                float2 uu[FT];
+                if (EARLY_U) {
+                    if (col_ok) {
+#pragma unroll
+                        for (int r = 0; r < FT; ++r) uu[r] = e.u[r * 2 * ROWP4];
+                    }
+                    __syncthreads();   // `filt` is free for the next FIR
+                }
                 if (col_ok) {
 #define MARCH_EPI(ACC, EUL)                                   \
     do {                                                      \
-        if (edge == 2) epilogue<2, ACC, EUL>(e, st);          \
-        else if (edge == 1) epilogue<1, ACC, EUL>(e, st);     \
-        else epilogue<0, ACC, EUL>(e, st);                    \
+        if (edge == 2) epilogue<2, ACC, EUL, EARLY_U>(e, st, uu);      \
+        else if (edge == 1) epilogue<1, ACC, EUL, EARLY_U>(e, st, uu); \
+        else epilogue<0, ACC, EUL, EARLY_U>(e, st, uu);                \
     } while (0)
                     if (SINGLE || !a.acc_in) {
                         if (euler) MARCH_EPI(false, true);
