@@ -172,6 +172,12 @@ int b200ca_lenia_march_supported(int H, int W);
 int64_t b200ca_lenia_march_kernel_elems(int B, int C, int k_mult);
 int b200ca_lenia_march_prepare_kernel(const float *K, float *Kf, int B, int C, int k_mult, int ks, void *stream);
 int b200ca_lenia_march_band_rows(int H, int W, int B, int C);
+/* Host-side copy of the plan of a whole-world launch (band_begin = band_end = 0), which is BALANCED: one wave of `grid` CTAs shares
+ * the `columns` = strips x B columns of bands, each `units` 16-row units tall, either in equal-cost runs (split_k = 0) or with
+ * every column cut into split_k equal bands.  b200ca_lenia_march_plan_bands writes the (column, first unit, units) triples of
+ * one CTA's bands exactly as the kernel derives them and returns their number (-1: bad arguments).  No device needed. */
+int b200ca_lenia_march_plan(int H, int W, int B, int *grid, int *split_k, int *units, int *columns);
+int b200ca_lenia_march_plan_bands(int H, int W, int B, int cta, int *bands, int cap);
 int b200ca_lenia_step_march(const float *state_in, float *state_out, const float *Kf, const float *mu, const float *sigma,
                             const float *weights, int B, int C, int k_mult, int H, int W, float dt, int mode, int row_wrap,
                             int band_begin, int band_end, void *stream);

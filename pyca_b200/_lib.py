@@ -54,6 +54,8 @@ SIGNATURES = {
     "b200ca_lenia_march_kernel_elems": (c_int64, [c_int, c_int, c_int]),
     "b200ca_lenia_march_prepare_kernel": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200ca_lenia_march_band_rows": (c_int, [c_int, c_int, c_int, c_int]),
+    "b200ca_lenia_march_plan": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200ca_lenia_march_plan_bands": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_int]),
     "b200ca_lenia_step_march": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                         c_int, c_float, c_int, c_int, c_int, c_int, c_void_p]),
     "b200ca_lenia_march_slab_ctas": (c_int, [c_int, c_int, c_int, c_int]),

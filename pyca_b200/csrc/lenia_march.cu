@@ -85,7 +85,7 @@ constexpr int ROW4 = N / 2;       // float4 of a spectra row (tap-table stride)
 //   sample layout    float2 index n               (inverse output: (row a, row b) of sample n)
 constexpr int ROWP4 = 144;        // float4 per padded row (2304 B >= 16*17 float2)
 constexpr int THREADS = 256;
-constexpr int PRO_UNITS = MARCH_PRO_UNITS;      // cost of a band's prologue (40 forward transforms on all 16 groups) in rounds of the marching loop
+constexpr int PRO_UNITS = MARCH_PRO_UNITS;      // what entering a column costs a run, in rounds of the marching loop: the prologue + the slow rounds at a world's first / last rows (fitted: 0..8 tried)
 constexpr size_t SMEM = (size_t)(RING + FT) * ROWP4 * sizeof(float4) + 16 * 17 * sizeof(float2);
 
 struct Args {
@@ -412,6 +412,40 @@ __device__ __forceinline__ void epilogue(const EpiArgs &e, const float2 (&st)[FT
     }
 }
 
+// The next band of CTA `cta` in a balanced launch (shared by the kernel and the host-side plan, b200ca_lenia_march_plan_bands):
+// `done` counts what the CTA has consumed so far (virtual units of its run, or 1 once its single split band is out).
+// split_k != 0: every column of bands is cut into split_k equal bands (chosen by the host when that leaves no CTA with more rows
+// than a run would get: e.g. 74 columns on 296 CTAs).  split_k == 0: runs that are equal in COST -- a column is `units` rounds of
+// the marching loop plus PRO_UNITS rounds' worth of prologue, so a run that crosses into the next column (a second prologue)
+// gets fewer rows than one that does not.
+__host__ __device__ __forceinline__ bool next_band(int units, long long ncols, int grid, int split_k, int cta, int &done, int &col, int &u0,
+                                                   int &nu) {
+    if (split_k) {
+        if (done) return false;
+        done = 1;
+        col = cta / split_k;
+        const int part = cta - col * split_k;
+        u0 = (int)((long long)units * part / split_k);
+        nu = (int)((long long)units * (part + 1) / split_k) - u0;
+        return nu > 0;
+    }
+    const int vunits = units + PRO_UNITS;
+    const long long total = (long long)vunits * ncols;
+    const long long v_end = total * (cta + 1) / grid;
+    for (;;) {
+        const long long v = total * cta / grid + done;
+        if (v >= v_end) return false;
+        col = (int)(v / vunits);
+        const int v0 = (int)(v - (long long)col * vunits);
+        const long long left = v_end - v;
+        const int nv = (long long)(vunits - v0) < left ? vunits - v0 : (int)left;
+        done += nv;
+        u0 = v0 > PRO_UNITS ? v0 - PRO_UNITS : 0;
+        nu = (v0 + nv > PRO_UNITS ? v0 + nv - PRO_UNITS : 0) - u0;
+        if (nu > 0) return true;
+    }
+}
+
 // block 256.  SINGLE: one destination plane (C == 1): taps stay in registers.
 // Two ways to hand out the bands:
 //   * balanced (a.jobs, every whole-world / whole-slab step): grid = ONE wave of CTAs (2 per SM).  The columns of bands -- (world,
@@ -462,31 +496,9 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
     for (;;) {
         // ---- the next band of this CTA
         int strip, b, y0, Lp, niter;
-        if (a.jobs && a.split_k) {
-            // every column of bands cut into split_k equal bands (chosen by the host when that leaves no CTA with more rows than
-            // the runs below would: e.g. 74 columns on 296 CTAs)
-            if (done) break;
-            done = 1;
-            const int col = blockIdx.x / a.split_k, part = blockIdx.x - col * a.split_k;
-            const int u0 = (int)((long long)a.units * part / a.split_k);
-            niter = (int)((long long)a.units * (part + 1) / a.split_k) - u0;
-            strip = col % a.strips;
-            b = col / a.strips;
-            y0 = 2 * FT * u0;
-            Lp = FT * niter;
-        } else if (a.jobs) {
-            // Runs are equal in COST: a column is `units` rounds of the marching loop plus PRO_UNITS rounds' worth of prologue, so a
-            // run that crosses into the next column (a second prologue) gets fewer rows than one that does not.
-            const int vunits = a.units + PRO_UNITS;
-            const long long total = (long long)vunits * a.strips * a.B;
-            const long long v = total * blockIdx.x / gridDim.x + done, v_end = total * (blockIdx.x + 1) / gridDim.x;
-            if (v >= v_end) break;
-            const int col = (int)(v / vunits), v0 = (int)(v - (long long)col * vunits);
-            const int nv = (int)min((long long)(vunits - v0), v_end - v);
-            done += nv;
-            const int u0 = max(v0 - PRO_UNITS, 0);
-            niter = max(v0 + nv - PRO_UNITS, 0) - u0;
-            if (niter == 0) continue;
+        if (a.jobs) {
+            int col, u0;
+            if (!next_band(a.units, (long long)a.strips * a.B, (int)gridDim.x, a.split_k, (int)blockIdx.x, done, col, u0, niter)) break;
             strip = col % a.strips;
             b = col / a.strips;
             y0 = 2 * FT * u0;
@@ -747,6 +759,35 @@ __global__ void march_prepare_kernel(const float *__restrict__ K, float2 *__rest
     }
 }
 
+// Launch plan of a balanced launch (host side; the kernel derives every CTA's bands from these numbers): grid size, and either
+// split_k = 0 -- equal-cost runs of the (column, unit) space, see the kernel -- or every column cut into split_k equal bands,
+// whichever leaves the busiest CTA with fewer rounds (a run pays PRO_UNITS rounds for every column it enters).
+static void plan_balanced(int H, int W, int B, int waves, int *grid, int *split_k, int *units, int *strips) {
+    *units = ceil_div(H, 2 * FT);
+    *strips = ceil_div(W, V);
+    const long long ncols = (long long)*strips * B, total = *units * ncols;
+    const long long G = std::min<long long>(total, 2LL * num_sms() * waves);
+    *grid = (int)G;
+    *split_k = 0;
+    if (ncols <= G) {
+        const long long k = std::min<long long>(G / ncols, *units);
+        const long long rounds_split = ceil_div64(*units, k), rounds_runs = ceil_div64((*units + PRO_UNITS) * ncols, G);
+        if (rounds_split <= rounds_runs) {
+            *split_k = (int)k;
+            *grid = (int)(k * ncols);
+        }
+    }
+}
+
+// The bands of CTA `cta` of a balanced launch, exactly as the kernel derives them (host copy: tests/test_host_logic.py checks that
+// the bands of all CTAs tile every column once): writes up to `cap` (column, first unit, units) triples, returns their number.
+static int bands_of_cta(int units, int ncols_strips_times_B, int grid, int split_k, int cta, int *out, int cap) {
+    int n = 0, done = 0, col, u0, nu;
+    while (next_band(units, ncols_strips_times_B, grid, split_k, cta, done, col, u0, nu))
+        if (n < cap) out[3 * n] = col, out[3 * n + 1] = u0, out[3 * n + 2] = nu, ++n;
+    return n;
+}
+
 // row pairs per band: tall bands amortise the 32 extra forward transforms; small worlds trade that for enough CTAs
 static int choose_lp(int H, int W, int B, int C) {
     const long long strips = ceil_div(W, V);
@@ -809,6 +850,21 @@ extern "C" int64_t b200ca_lenia_march_kernel_elems(int B, int C, int k_mult) {
 }
 
 extern "C" int b200ca_lenia_march_band_rows(int H, int W, int B, int C) { return 2 * march::choose_lp(H, W, B, C); }
+
+extern "C" int b200ca_lenia_march_plan(int H, int W, int B, int *grid, int *split_k, int *units, int *columns) {
+    B200CA_REQUIRE(grid && split_k && units && columns && H >= 1 && W >= 1 && B >= 1, "lenia_march_plan: bad arguments");
+    int strips = 0;
+    march::plan_balanced(H, W, B, MARCH_JOB_WAVES > 0 ? MARCH_JOB_WAVES : 1, grid, split_k, units, &strips);
+    *columns = strips * B;
+    return 0;
+}
+
+extern "C" int b200ca_lenia_march_plan_bands(int H, int W, int B, int cta, int *bands, int cap) {
+    int grid = 0, split_k = 0, units = 0, strips = 0;
+    march::plan_balanced(H, W, B, MARCH_JOB_WAVES > 0 ? MARCH_JOB_WAVES : 1, &grid, &split_k, &units, &strips);
+    if (!bands || cap < 1 || cta < 0 || cta >= grid) return -1;
+    return march::bands_of_cta(units, strips * B, grid, split_k, cta, bands, cap);
+}
 
 extern "C" int b200ca_lenia_march_prepare_kernel(const float *K, float *Kf, int B, int C, int k_mult, int ks, void *stream) {
     B200CA_REQUIRE(K && Kf && B >= 1 && C >= 1 && k_mult >= 1, "lenia_march_prepare_kernel: bad arguments");
@@ -874,21 +930,9 @@ static int march_launch(march::Args a, int B, int C, int k_mult, int H, int W, i
     if (band_begin == 0 && band_end == 0 && job_waves > 0) {
         // balanced launch: the whole world / slab, cut into equal runs of 16-row units for one wave of CTAs (see the kernel)
         a.jobs = 1;
-        a.units = ceil_div(H, 2 * march::FT);
-        a.strips = ceil_div(W, march::V);
-        const long long ncols = (long long)a.strips * B, total = a.units * ncols;
-        const long long G = std::min<long long>(total, 2LL * num_sms() * job_waves);
-        grid = dim3((unsigned)G, 1, 1);
-        // equal runs of the whole (column, unit) space, or every column cut into k equal bands: whichever leaves the busiest CTA
-        // with fewer rounds (a run pays march::PRO_UNITS rounds for every column it enters)
-        if (ncols <= G) {
-            const long long k = std::min<long long>(G / ncols, a.units);
-            const long long rounds_split = ceil_div64(a.units, k), rounds_runs = ceil_div64((a.units + march::PRO_UNITS) * ncols, G);
-            if (rounds_split <= rounds_runs) {
-                a.split_k = (int)k;
-                grid = dim3((unsigned)(k * ncols), 1, 1);
-            }
-        }
+        int g = 0;
+        march::plan_balanced(H, W, B, job_waves, &g, &a.split_k, &a.units, &a.strips);
+        grid = dim3((unsigned)g, 1, 1);
     } else {
         if (band_begin == 0 && band_end == 0) band_end = a.nbands;
         B200CA_REQUIRE(band_begin >= 0 && band_end <= a.nbands && band_begin <= band_end, "lenia_step_march: band range [%d,%d) outside [0,%d)",

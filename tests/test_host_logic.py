@@ -152,3 +152,43 @@ def test_both_bench_arms_print_the_same_config():
             c = ns["static_config"](name, n)
             assert c["workload"] == name and "l2" in c and "partition" in c
     assert ns["static_config"]("lenia_1k", 1)["shape"] == [ns["LENIA1K_BATCH"], 1, 1024, 1024]
+
+
+def test_marching_kernel_balanced_plan_tiles_every_column_once():
+    """b200ca_lenia_march_plan / _plan_bands: the host copy of how a balanced launch of the marching Lenia kernel hands the
+    (world, strip) columns of 16-row units to its CTAs (csrc/lenia_march.cu).  Every unit of every column must be in exactly
+    one band, a CTA's bands must be consecutive, and the busiest CTA must not carry much more than its share."""
+    import ctypes
+
+    from pyca_b200 import _lib
+
+    L = _lib.lib()
+    for H, W, B in [(1024, 1024, 24), (1000, 500, 5), (4096, 4096, 1), (16384, 16384, 1), (2048, 16384, 1), (40, 300, 9), (2056, 230, 2),
+                    (32, 32, 1), (1024, 1024, 1), (600, 460, 4)]:
+        g, k, units, cols = (ctypes.c_int() for _ in range(4))
+        assert L.b200ca_lenia_march_plan(H, W, B, ctypes.byref(g), ctypes.byref(k), ctypes.byref(units), ctypes.byref(cols)) == 0
+        g, k, units, cols = g.value, k.value, units.value, cols.value
+        assert units == -(-H // 16) and cols == -(-W // 224) * B and 1 <= g <= 296
+        seen = np.zeros((cols, units), dtype=np.int32)
+        buf = (ctypes.c_int * (3 * 64))()
+        load = []
+        for cta in range(g):
+            n = L.b200ca_lenia_march_plan_bands(H, W, B, cta, buf, 64)
+            assert 0 <= n < 64
+            rounds = 0
+            last = None
+            for i in range(n):
+                col, u0, nu = buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]
+                assert nu >= 1 and 0 <= u0 and u0 + nu <= units and 0 <= col < cols
+                seen[col, u0:u0 + nu] += 1
+                if last is not None:     # a run walks down a column and continues at the top of the next one
+                    assert (col, u0) == (last[0] + 1, 0) and last[1] == units
+                last = (col, u0 + nu)
+                rounds += nu + 4         # PRO_UNITS rounds per band entered
+            load.append(rounds)
+            if k:
+                assert n == 1
+        assert (seen == 1).all(), (H, W, B)
+        assert L.b200ca_lenia_march_plan_bands(H, W, B, g, buf, 64) == -1
+        if g == 296 and units * cols >= 8 * g:   # big launches: within a round or two of a perfect split
+            assert max(load) - min(load) <= 6, (H, W, B, max(load), min(load))
