@@ -60,6 +60,9 @@
 #ifndef MARCH_EARLY_U
 #define MARCH_EARLY_U 0      // the epilogue takes its 8 filtered samples into registers first; the barrier that frees `filt` for the
 #endif                       // next FIR follows those loads instead of the whole epilogue (its global loads / stores overlap the FIR)
+#ifndef MARCH_L2_PREFETCH
+#define MARCH_L2_PREFETCH 1  // the forward warps ask L2 for the rows they will transform after the FIR (prefetch.global.L2: no registers held)
+#endif
 #ifndef MARCH_JOB_WAVES
 #define MARCH_JOB_WAVES 1    // balanced launches: grid = this many waves of CTAs (0: fixed-height bands for every launch)
 #endif
@@ -616,6 +619,14 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
                 float2 vf[16];
 #if MARCH_PREFETCH
                 if (do_fwd) forward_fetch(zf, vf);
+#endif
+#if MARCH_L2_PREFETCH
+                if (do_fwd && !pro) {
+                    // 2 rows x 1 KB = 16 lines of 128 B: one per lane of the group (row a: lanes 0-7, row b: lanes 8-15)
+                    const int frow = min(y0 + ((lane16 & 8) ? Lp : 0) + zf - R + F, max_frow);
+                    const int colp = min(col0 + 32 * (lane16 & 7), a.pitch - 1);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(splane + (size_t)frow * a.pitch + colp));
+                }
 #endif
                 // ring rows of this iteration are complete; the previous epilogue is done with `filt` (MARCH_EARLY_U: it said so itself,
                 // right after loading its samples -- only a band's first FIR still has to wait for the prologue's ring rows)
