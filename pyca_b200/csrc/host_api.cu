@@ -50,7 +50,7 @@ namespace {
 
 struct Lane {
     cudaStream_t st = nullptr;
-    cudaEvent_t done = nullptr;
+    cudaEvent_t done = nullptr, up_done = nullptr, k_done = nullptr;
     float *dense = nullptr, *a = nullptr, *b = nullptr, *aff = nullptr, *ws = nullptr;
     bool busy = false;
 };
@@ -63,6 +63,10 @@ struct Pipe {
     size_t dbytes = 0;
     float *kprep = nullptr, *kfft = nullptr, *mu = nullptr, *sigma = nullptr, *weights = nullptr;
     Lane *lanes = nullptr;
+    // every host-to-device copy goes through ONE stream and every device-to-host copy through another: a lane's own stream
+    // may share its copy engine with another lane's opposite direction, and then the two directions queue behind each other
+    cudaStream_t st_up = nullptr, st_dn = nullptr;
+    int copy_mode = 3;   // bit 0: dedicated upload stream, bit 1: dedicated download stream (pageable / unmapped outputs)
 };
 
 void pipe_free(Pipe *p) {
@@ -77,10 +81,14 @@ void pipe_free(Pipe *p) {
             cudaFree(l.aff);
             cudaFree(l.ws);
             if (l.done) cudaEventDestroy(l.done);
+            if (l.up_done) cudaEventDestroy(l.up_done);
+            if (l.k_done) cudaEventDestroy(l.k_done);
             if (l.st) cudaStreamDestroy(l.st);
         }
         delete[] p->lanes;
     }
+    if (p->st_up) cudaStreamDestroy(p->st_up);
+    if (p->st_dn) cudaStreamDestroy(p->st_dn);
     cudaFree(p->kprep);
     cudaFree(p->kfft);
     cudaFree(p->mu);
@@ -120,11 +128,15 @@ int pipe_build(Pipe *p, const float *K, const float *mu, const float *sigma, con
     if (!rc) rc = check_cuda(cudaDeviceSynchronize(), "kernel preparation");
     cudaFree(dK);
     if (rc) return rc;
+    B200CA_CUDA(cudaStreamCreateWithFlags(&p->st_up, cudaStreamNonBlocking));
+    B200CA_CUDA(cudaStreamCreateWithFlags(&p->st_dn, cudaStreamNonBlocking));
     p->lanes = new Lane[p->depth];
     for (int i = 0; i < p->depth; ++i) {
         Lane &l = p->lanes[i];
         B200CA_CUDA(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
         B200CA_CUDA(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+        B200CA_CUDA(cudaEventCreateWithFlags(&l.up_done, cudaEventDisableTiming));
+        B200CA_CUDA(cudaEventCreateWithFlags(&l.k_done, cudaEventDisableTiming));
         B200CA_CUDA(cudaMalloc(&l.dense, p->dbytes));
         B200CA_CUDA(cudaMalloc(&l.a, fbytes));
         B200CA_CUDA(cudaMalloc(&l.b, fbytes));
@@ -192,10 +204,19 @@ extern "C" int b200ca_lenia_pipe_submit(void *pipe, const float *h_state_in, flo
         else
             (void)cudaGetLastError();
     }
+    int copy_mode = p->copy_mode;
 #ifdef B200CA_DEV
     if (const char *e = getenv("B200CA_PIPE_ZEROCOPY")) out_mapped = atoi(e) ? out_mapped : nullptr;
+    if (const char *e = getenv("B200CA_PIPE_COPY_MODE")) copy_mode = atoi(e);
 #endif
-    B200CA_CUDA(cudaMemcpyAsync(l.dense, h_state_in, p->dbytes, cudaMemcpyHostToDevice, l.st));
+    if (copy_mode & 1) {
+        // (the lane's previous world is complete -- cudaEventSynchronize above -- so its staging buffer is free)
+        B200CA_CUDA(cudaMemcpyAsync(l.dense, h_state_in, p->dbytes, cudaMemcpyHostToDevice, p->st_up));
+        B200CA_CUDA(cudaEventRecord(l.up_done, p->st_up));
+        B200CA_CUDA(cudaStreamWaitEvent(l.st, l.up_done, 0));
+    } else {
+        B200CA_CUDA(cudaMemcpyAsync(l.dense, h_state_in, p->dbytes, cudaMemcpyHostToDevice, l.st));
+    }
     int rc = b200ca_frame_load(l.dense, l.a, B, C, H, W, 1, l.st);
     float *src = l.a, *dst = l.b;
     for (int i = 0; i < nsteps && !rc; ++i) {
@@ -214,11 +235,19 @@ extern "C" int b200ca_lenia_pipe_submit(void *pipe, const float *h_state_in, flo
     if (rc) return rc;
     if (out_mapped) {
         if ((rc = b200ca_frame_store(src, out_mapped, B, C, H, W, l.st))) return rc;
+        B200CA_CUDA(cudaEventRecord(l.done, l.st));
     } else {
         if ((rc = b200ca_frame_store(src, l.dense, B, C, H, W, l.st))) return rc;
-        B200CA_CUDA(cudaMemcpyAsync(h_state_out, l.dense, p->dbytes, cudaMemcpyDeviceToHost, l.st));
+        if (copy_mode & 2) {
+            B200CA_CUDA(cudaEventRecord(l.k_done, l.st));
+            B200CA_CUDA(cudaStreamWaitEvent(p->st_dn, l.k_done, 0));
+            B200CA_CUDA(cudaMemcpyAsync(h_state_out, l.dense, p->dbytes, cudaMemcpyDeviceToHost, p->st_dn));
+            B200CA_CUDA(cudaEventRecord(l.done, p->st_dn));
+        } else {
+            B200CA_CUDA(cudaMemcpyAsync(h_state_out, l.dense, p->dbytes, cudaMemcpyDeviceToHost, l.st));
+            B200CA_CUDA(cudaEventRecord(l.done, l.st));
+        }
     }
-    B200CA_CUDA(cudaEventRecord(l.done, l.st));
     l.busy = true;
     return 0;
 }

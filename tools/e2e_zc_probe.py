@@ -36,9 +36,9 @@ for depth in (3, 6, 8):
     print(f"  depth {depth}: {us:.1f} us/world = {H * W / us / 1e3:.2f} GCUPS  checksum {float(hout[3].double().sum()):.6f}", flush=True)
     cp.close()
 '''
-for spec in sys.argv[1:] or ["0:1", "1:1", "1:0"]:      # <store straight to the host buffer>:<16-byte stores>
-    zc, vec = spec.split(":")
-    print(f"=== B200CA_PIPE_ZEROCOPY={zc} B200CA_STORE_VEC={vec}", flush=True)
-    env = dict(os.environ, B200CA_LIB=os.path.join(ROOT, "pyca_b200", "libb200ca_dev.so"), B200CA_PIPE_ZEROCOPY=zc, B200CA_STORE_VEC=vec)
+for spec in sys.argv[1:] or ["0:0", "0:3", "1:0", "1:1"]:      # <store straight to the host buffer>:<copy mode: 1 upload stream, 2 download stream>
+    zc, cm = spec.split(":")
+    print(f"=== B200CA_PIPE_ZEROCOPY={zc} B200CA_PIPE_COPY_MODE={cm}", flush=True)
+    env = dict(os.environ, B200CA_LIB=os.path.join(ROOT, "pyca_b200", "libb200ca_dev.so"), B200CA_PIPE_ZEROCOPY=zc, B200CA_PIPE_COPY_MODE=cm)
     r = subprocess.run([sys.executable, "-c", CODE % ROOT], env=env, capture_output=True, text=True)
     print(r.stdout.rstrip() or r.stderr[-1500:], flush=True)
