@@ -190,11 +190,35 @@ struct Row4 {
     uint32_t c[4], s0[4], s1[4];
 };
 
+// EVF: loads marked evict-first in L2.  The generation just read is dead (its buffer is overwritten two launches later) while the
+// one being written is the next launch's input: when one buffer fits the 126 MB L2 -- a row slab of a sharded world -- the
+// default policy streams both through the cache and keeps neither, evict-first reads leave the written generation resident.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <bool EVF>
+__device__ __forceinline__ uint4 gol_ld4(const uint32_t *p, uint64_t pol) {
+    if (!EVF) return __ldg(reinterpret_cast<const uint4 *>(p));
+    uint4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+template <bool EVF>
+__device__ __forceinline__ uint32_t gol_ld1(const uint32_t *p, uint64_t pol) {
+    if (!EVF) return __ldg(p);
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
+template <bool EVF = false>
 __device__ __forceinline__ void gol_fast_load(Row4 &R, const uint32_t *__restrict__ base, uint32_t off_main, uint32_t off_edge,
-                                              bool edge_l, bool edge_r, uint32_t live_mask) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base + off_main));
+                                              bool edge_l, bool edge_r, uint32_t live_mask, uint64_t pol = 0) {
+    const uint4 v = gol_ld4<EVF>(base + off_main, pol);
     uint32_t ev = 0u;
-    if (edge_l || edge_r) ev = __ldg(base + off_edge);
+    if (edge_l || edge_r) ev = gol_ld1<EVF>(base + off_edge, pol);
     uint32_t left = __shfl_up_sync(0xffffffffu, v.w, 1);
     uint32_t right = __shfl_down_sync(0xffffffffu, v.x, 1);
     left = edge_l ? ev : left;
@@ -245,7 +269,7 @@ __device__ __forceinline__ uint32_t gol_rule9(uint32_t p0, uint32_t p1, uint32_t
     }
 }
 
-template <bool LIFE, bool OPEN, int RPT>
+template <bool LIFE, bool OPEN, int RPT, bool EVF>
 __global__ void __launch_bounds__(128, 6) gol_fast_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int H, int wpr,
                                                            int stride, uint32_t s_mask, uint32_t b_mask) {
     const int lane = threadIdx.x & 31;
@@ -267,6 +291,7 @@ __global__ void __launch_bounds__(128, 6) gol_fast_kernel(const uint32_t *__rest
             rm.b[k] = ((b_mask >> k) & 1u) ? 0xffffffffu : 0u;
         }
     }
+    const uint64_t pol = EVF ? l2_evict_first_policy() : 0;
     pdl_wait_then_release();  // generations are chained with programmatic dependent launch
     // rows r0 .. r0+RPT-1 are contiguous; only the row above the first and below the last may wrap / be dead
     const int ra = r0 == 0 ? (OPEN ? 0 : H - 1) : r0 - 1;
@@ -277,20 +302,20 @@ __global__ void __launch_bounds__(128, 6) gol_fast_kernel(const uint32_t *__rest
     uint32_t row_off = (uint32_t)r0 * ustride;  // H * stride < 2^32 words is guaranteed by the launcher
     Row4 Q, N;
     uint32_t a0[4], a1[4];
-    gol_fast_load(N, in, (uint32_t)ra * ustride + j0, (uint32_t)ra * ustride + je, edge_l, edge_r, ma);
+    gol_fast_load<EVF>(N, in, (uint32_t)ra * ustride + j0, (uint32_t)ra * ustride + je, edge_l, edge_r, ma, pol);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         a0[k] = N.s0[k];
         a1[k] = N.s1[k];
     }
-    gol_fast_load(Q, in, row_off + j0, row_off + je, edge_l, edge_r, 0xffffffffu);
+    gol_fast_load<EVF>(Q, in, row_off + j0, row_off + je, edge_l, edge_r, 0xffffffffu, pol);
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
         const uint32_t next_off = row_off + ustride;
         if (i == RPT - 1)
-            gol_fast_load(N, in, (uint32_t)rb * ustride + j0, (uint32_t)rb * ustride + je, edge_l, edge_r, mb);
+            gol_fast_load<EVF>(N, in, (uint32_t)rb * ustride + j0, (uint32_t)rb * ustride + je, edge_l, edge_r, mb, pol);
         else
-            gol_fast_load(N, in, next_off + j0, next_off + je, edge_l, edge_r, 0xffffffffu);
+            gol_fast_load<EVF>(N, in, next_off + j0, next_off + je, edge_l, edge_r, 0xffffffffu, pol);
         uint32_t o[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -579,8 +604,15 @@ static int launch_fast_t(const uint32_t *in, uint32_t *out, const GolGeom &g, ui
     const int units = g.wpr / 4;
     const int bx = units >= 128 ? 128 : ceil_div(units, 32) * 32;
     dim3 grid(ceil_div(units, bx), ceil_div(g.H, RPT));
-    B200CA_CUDA(launch_pdl(gol_fast_kernel<LIFE, OPEN, RPT>, grid, dim3(bx), 0, st, in, out, g.H, g.wpr, g.stride, s, b));
-    note_variant("gol_fast<%d,%d,%d>", (int)LIFE, (int)OPEN, RPT);
+    // one buffer fits L2 with room to spare (but the pair does not anyway fit trivially): read the dying generation evict-first
+    const long long bytes = (long long)g.H * g.stride * 4;
+    bool evf = bytes <= (100LL << 20) && bytes >= (24LL << 20);
+#ifdef B200CA_DEV
+    if (const char *e = getenv("B200CA_GOL_EVF")) evf = atoi(e) != 0;
+#endif
+    if (evf) B200CA_CUDA(launch_pdl(gol_fast_kernel<LIFE, OPEN, RPT, true>, grid, dim3(bx), 0, st, in, out, g.H, g.wpr, g.stride, s, b));
+    else B200CA_CUDA(launch_pdl(gol_fast_kernel<LIFE, OPEN, RPT, false>, grid, dim3(bx), 0, st, in, out, g.H, g.wpr, g.stride, s, b));
+    note_variant("gol_fast<%d,%d,%d%s>", (int)LIFE, (int)OPEN, RPT, evf ? ",evict-first" : "");
     return 0;
 }
 

@@ -108,26 +108,32 @@ def test_open_rows_mode_vs_oracle():
     assert np.array_equal(got, ref)
 
 
-def test_periodic_tiling_identity_16k():
-    """a torus tiled PxP from a small torus stays tiled; every tile equals the small-torus run
-    (checked against the oracle).  Size-independent parity property used for worlds the oracle cannot hold."""
+@pytest.mark.parametrize("P,Q,variant", [(8, 8, "gol_fast<1,0,16>"), (16, 16, "gol_fast<1,0,16,evict-first>")])
+def test_periodic_tiling_identity_16k(P, Q, variant):
+    """a torus tiled PxQ from a small torus stays tiled; every tile equals the small-torus run
+    (checked against the oracle).  Size-independent parity property used for worlds the oracle cannot hold.  The second size
+    (16384 x 32768 cells = 64 MB per buffer, the size class of an 8-GPU slab of the 65536^2 world) takes the variant whose loads
+    are marked evict-first in L2."""
     import pyca_b200
 
     rng = np.random.default_rng(17)
-    h, w, P, steps = 1024, 2048, 8, 12
+    h, w, steps = 1024, 2048, 12
     small = (rng.random((h, w)) < 0.5).astype(np.uint8)
     ref = orc.gol_run(small, steps)
-    big = torch.from_numpy(small).cuda().repeat(P, P)
-    pw = pyca_b200.PackedWorld(h * P, w * P, "cuda")
+    big = torch.from_numpy(small).cuda().repeat(P, Q)
+    pw = pyca_b200.PackedWorld(h * P, w * Q, "cuda")
     pw.pack_from(big)
+    del big
     pop0 = pw.population()
-    assert pop0 == int(small.sum()) * P * P
+    assert pop0 == int(small.sum()) * P * Q
+    pyca_b200._lib.variants(reset=True)
     pw.step(0b1100, 0b1000, steps)
+    assert variant in pyca_b200._lib.variants(reset=True)
     out = pw.unpack(torch.uint8)
     ref_t = torch.from_numpy(ref.astype(np.uint8)).cuda()
-    tiles = out.view(P, h, P, w).permute(0, 2, 1, 3)
+    tiles = out.view(P, h, Q, w).permute(0, 2, 1, 3)
     assert bool((tiles == ref_t[None, None]).all())
-    assert pw.population() == int(ref.sum()) * P * P
+    assert pw.population() == int(ref.sum()) * P * Q
 
 
 def test_random_fill_and_population():
