@@ -63,6 +63,9 @@
 #ifndef MARCH_L2_PREFETCH
 #define MARCH_L2_PREFETCH 1  // the forward warps ask L2 for the rows they will transform after the FIR (prefetch.global.L2: no registers held)
 #endif
+#ifndef MARCH_EDGE_UNITS
+#define MARCH_EDGE_UNITS 2
+#endif
 #ifndef MARCH_JOB_WAVES
 #define MARCH_JOB_WAVES 1    // balanced launches: grid = this many waves of CTAs (0: fixed-height bands for every launch)
 #endif
@@ -88,6 +91,7 @@ constexpr int ROW4 = N / 2;       // float4 of a spectra row (tap-table stride)
 //   sample layout    float2 index n               (inverse output: (row a, row b) of sample n)
 constexpr int ROWP4 = 144;        // float4 per padded row (2304 B >= 16*17 float2)
 constexpr int THREADS = 256;
+constexpr int EDGE_UNITS = MARCH_EDGE_UNITS;    // split launches: what the slow rounds at a column's first / last rows cost their band, in rounds
 constexpr int PRO_UNITS = MARCH_PRO_UNITS;      // what entering a column costs a run, in rounds of the marching loop: the prologue + the slow rounds at a world's first / last rows (fitted: 0..8 tried)
 constexpr size_t SMEM = (size_t)(RING + FT) * ROWP4 * sizeof(float4) + 16 * 17 * sizeof(float2);
 
@@ -424,12 +428,17 @@ __device__ __forceinline__ void epilogue(const EpiArgs &e, const float2 (&st)[FT
 __host__ __device__ __forceinline__ bool next_band(int units, long long ncols, int grid, int split_k, int cta, int &done, int &col, int &u0,
                                                    int &nu) {
     if (split_k) {
+        // (the bands that hold a column's first / last rows run EDGE_UNITS rounds' worth of slow edge rounds -- periodic y images,
+        // a slab's halo stores and waits -- and get that many units less)
         if (done) return false;
         done = 1;
         col = cta / split_k;
         const int part = cta - col * split_k;
-        u0 = (int)((long long)units * part / split_k);
-        nu = (int)((long long)units * (part + 1) / split_k) - u0;
+        const int e = split_k > 1 && units >= 8 * split_k ? EDGE_UNITS : 0;
+        const long long vcol = units + 2 * e;
+        const int b0 = part == 0 ? 0 : (int)(vcol * part / split_k) - e, b1 = part == split_k - 1 ? units : (int)(vcol * (part + 1) / split_k) - e;
+        u0 = b0;
+        nu = b1 - b0;
         return nu > 0;
     }
     const int vunits = units + PRO_UNITS;
