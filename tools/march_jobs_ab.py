@@ -45,6 +45,8 @@ SPECS = [(1, 24, 1024, 1024, 60), (1, 1, 4096, 4096, 60), (1, 1, 2048, 16384, 40
          (3, 1, 1024, 1024, 100), (1, 1, 1024, 1024, 200)]
 if os.environ.get("MARCH_AB_SHORT"):
     SPECS = SPECS[:4]
+if os.environ.get("MARCH_AB_PRO"):
+    SPECS = [SPECS[0], SPECS[1], SPECS[4], (3, 1, 2048, 2048, 40)]
 
 if __name__ == "__main__":
     waves = sys.argv[1:] or ["0", "1", "2", "4"]      # "<waves>" or "<variant>:<waves>" (pyca_b200/variants/<variant>.so)
