@@ -7,23 +7,24 @@
 //
 //   * x direction: overlap-save strips of N = 256 samples, V = 224 valid outputs (16-sample halo on both sides, so the
 //     strip starts on a 64-byte boundary of the framed row and the frame's 16 periodic columns are exactly the halo).
-//   * y direction: a CTA owns a BAND of 2*Lp image rows of one strip and marches down it 8 row pairs at a time.  Rows
-//     y0+p and y0+Lp+p ride in one complex transform (real taps keep re and im apart), so a band needs Lp+30 forward
-//     transforms for 2*Lp output rows.  The last 40 spectra rows live in a shared-memory ring (5 blocks of 8 rows).
+//   * y direction: a CTA marches down a BAND of 2*Lp image rows of one strip, 8 row pairs at a time.  Rows y0+p and y0+Lp+p
+//     ride in one complex transform (real taps keep re and im apart), so a band needs Lp+30 forward transforms for 2*Lp
+//     output rows.  The last 40 spectra rows live in a shared-memory ring (5 blocks of 8 rows).
+//   * which bands a CTA gets: a whole-world / whole-slab step is a BALANCED launch -- one wave of CTAs (2 per SM) shares the
+//     columns of bands of all worlds and strips in equal-cost runs, or with every column cut into k bands (next_band() below,
+//     b200ca_lenia_march_plan* is its host copy); a launch restricted to a band range keeps fixed-height bands (choose_lp).
 //   * per iteration: FIR of 8 output row pairs from 38 ring rows (FFMA2 on (re0,re1)/(im0,im1) pairs, all 256 threads) ->
 //     [warps 0-3: 8 inverse transforms | warps 4-7: 8 forward transforms of the block needed 5 iterations later] ->
 //     epilogue on all threads (growth, source sum, Euler/clamp, coalesced stores + periodic frame).
 //   * the 256-point transform is 16 x 16 in registers: 16 lanes per row, 16 samples per lane, ONE shared-memory exchange
-//     (XOR-swizzled, conflict free), constants of the 16-point kernels as immediates; two rows per warp, __syncwarp only.
-// HBM traffic per cell and step: the state once (+14 % strip halo, + (Lp+30)/Lp band halo, mostly L2 hits), the Euler
-// operand (an L2 hit: the same CTA loaded that row <= 38 rows earlier) and the output: ~1.1-1.3x the algorithmic 8 B.
+//     (padded rows: every access is base + immediate), constants of the 16-point kernels as immediates; two rows per warp,
+//     __syncwarp only.
+// HBM traffic per cell and step: the state once (+14 % strip halo and the band halo, mostly L2 hits), the Euler operand (an L2
+// hit: the same CTA loaded that row <= 38 rows earlier) and the output: 1.0x the algorithmic 8 B at 16384^2 (ncu).
 // tools/march_proto.py is the numpy model of the index arithmetic below.
-// Code size: everything below is inlined into the kernel (12.8 K instructions = 204 KB for the single-destination variant), and
-// the short CTAs of small worlds pay for it in instruction-cache misses (ncu `no_instruction` 2.1 of 7 stall cycles per issue on
-// the 24 x 1024^2 batch, 0.2 at 16384^2).  Shrinking it to 3.8 K instructions -- one shared forward routine called from a
-// prologue folded into the marching loop, no per-edge-case epilogue instantiations, a separate out-of-line pass for the frame
-// images -- measured 20 % SLOWER at every size (1.58 vs 1.30 ms at 16384^2): the out-of-line calls cost registers and spills
-// around every call site, real `__noinline__` transforms 50 %.  Not kept.
+// Code size: everything below is inlined into the kernel (one copy of the forward transform: the prologue runs as extra rounds of
+// the marching loop).  A version with out-of-line transforms / frame routines (3.8 K instructions) measured 20-50 % slower: the
+// calls cost registers and spills around every call site.  Not kept.
 #include "common.cuh"
 
 // A/B switches of the developer builds (tools/march_ab.sh); the defaults are what ships
@@ -123,7 +124,6 @@ struct Args {
     unsigned wait_target;                        // arrivals expected before this step may read its ghost rows
     int nbands;                                  // bands of the whole slab (blockIdx.y is permuted: boundary bands first)
     unsigned *err_flag;                          // set if a wait timed out (no hang: the step then reads stale ghost rows)
-    unsigned stagger_ns;                         // developer builds: the second half of the grid starts this much later (phase experiment)
 };
 
 // Every fp32 instruction with three register operands -- scalar or packed -- occupies the FMA pipe for two cycles per warp
@@ -492,15 +492,6 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
     const bool lenia = a.mode == B200CA_MODE_LENIA;
     const bool edge_rows = a.row_wrap || a.peer_up_out || a.peer_dn_out;
     pdl_wait_then_release();  // the state is the previous step's output
-#ifdef B200CA_DEV
-    if (a.stagger_ns && blockIdx.x >= gridDim.x / 2 && tid == 0) {
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        do {
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        } while (t1 - t0 < a.stagger_ns);
-    }
-#endif
     __syncthreads();          // twiddle table
 
     int done = 0;             // balanced launches: units of this CTA's run that are finished
@@ -944,7 +935,6 @@ static int march_launch(march::Args a, int B, int C, int k_mult, int H, int W, i
     int job_waves = MARCH_JOB_WAVES;
 #ifdef B200CA_DEV
     if (const char *e = getenv("B200CA_MARCH_WAVES")) job_waves = atoi(e);
-    if (const char *e = getenv("B200CA_MARCH_STAGGER")) a.stagger_ns = (unsigned)atoi(e);
 #endif
     dim3 grid;
     if (band_begin == 0 && band_end == 0 && job_waves > 0) {
