@@ -67,6 +67,9 @@
 #ifndef MARCH_EDGE_UNITS
 #define MARCH_EDGE_UNITS 2
 #endif
+#ifndef MARCH_SKEW
+#define MARCH_SKEW 0         // per-mille share of a co-resident CTA pair's rows given to the first-placed CTA (see next_band; 0: even split)
+#endif
 #ifndef MARCH_JOB_WAVES
 #define MARCH_JOB_WAVES 1    // balanced launches: grid = this many waves of CTAs (0: fixed-height bands for every launch)
 #endif
@@ -107,6 +110,7 @@ struct Args {
     int jobs;           // 1: balanced launch -- the grid is ONE wave of CTAs that share the (world, strip, 16-row unit) space evenly
     int units, strips;  // 16-row units per column of bands (ceil(H / 16)), strips per world
     int split_k;        // balanced launches: != 0: every column is cut into split_k equal bands, one CTA each (no run crosses a column)
+    int skew;           // balanced launches on a full wave: per-mille share of a CTA pair's rows that goes to the first-placed CTA (0: even)
     int src;            // source-kernel index i*k_mult + m of this launch
     int acc_in;         // 1: add to the partial sums already in `out` (sources after the first)
     int final_src;      // 1: last source -> Euler step / clamp (LENIA) or plain sum (AFF)
@@ -124,6 +128,9 @@ struct Args {
     unsigned wait_target;                        // arrivals expected before this step may read its ghost rows
     int nbands;                                  // bands of the whole slab (blockIdx.y is permuted: boundary bands first)
     unsigned *err_flag;                          // set if a wait timed out (no hang: the step then reads stale ghost rows)
+#ifdef B200CA_DEV
+    unsigned long long *trace;                   // developer builds: per CTA (start ns, end ns, SM id) of the last launch, or null
+#endif
 };
 
 // Every fp32 instruction with three register operands -- scalar or packed -- occupies the FMA pipe for two cycles per warp
@@ -425,27 +432,60 @@ __device__ __forceinline__ void epilogue(const EpiArgs &e, const float2 (&st)[FT
 // than a run would get: e.g. 74 columns on 296 CTAs).  split_k == 0: runs that are equal in COST -- a column is `units` rounds of
 // the marching loop plus PRO_UNITS rounds' worth of prologue, so a run that crosses into the next column (a second prologue)
 // gets fewer rows than one that does not.
-__host__ __device__ __forceinline__ bool next_band(int units, long long ncols, int grid, int split_k, int cta, int &done, int &col, int &u0,
-                                                   int &nu) {
+// `skew` (per mille, 0 = off, and off by default): on a full wave the two CTAs that share an SM do not share it evenly.  The per-CTA
+// trace (tools/march_trace.py) shows, on every one of the 148 SMs, one CTA running at its SOLO rate and its sibling on the issue
+// slots that are left (0.58 : 0.42 of the SM), so that the favoured CTA ends at 916 us of a 16384^2 step and the other one
+// finishes alone at 1173 us, well under the SM's two-CTA throughput: 9 % of the launch.  With `skew` the grid is handled as
+// grid/2 PAIRS -- CTA i and CTA i + grid/2, the block scheduler deals blockIdx 0 .. nSM-1 one per SM first -- and a pair's share
+// of the rows is cut skew : 1000 - skew.  Measured: 540 gains 2 % on the batch and 0.4 % at 16384^2; at 580, where both CTAs
+// should end together, which CTA is favoured flips from SM to SM (it follows the warp slots freed by the PREVIOUS launch) and
+// the step is 15 % slower.  Left off; the robust fix is a pair of sub-CTAs inside one 512-thread CTA that split a band's
+// remaining rounds when the first of them runs out of work.
+__host__ __device__ __forceinline__ bool next_band(int units, long long ncols, int grid, int split_k, int skew, int cta, int &done, int &col,
+                                                   int &u0, int &nu) {
+    const int half = grid >> 1;
+    const bool paired = skew > 0;
+    const int pair = paired ? (cta < half ? cta : cta - half) : 0;
+    const bool fast = cta < half;
     if (split_k) {
         // (the bands that hold a column's first / last rows run EDGE_UNITS rounds' worth of slow edge rounds -- periodic y images,
         // a slab's halo stores and waits -- and get that many units less)
         if (done) return false;
         done = 1;
-        col = cta / split_k;
-        const int part = cta - col * split_k;
         const int e = split_k > 1 && units >= 8 * split_k ? EDGE_UNITS : 0;
         const long long vcol = units + 2 * e;
-        const int b0 = part == 0 ? 0 : (int)(vcol * part / split_k) - e, b1 = part == split_k - 1 ? units : (int)(vcol * (part + 1) / split_k) - e;
-        u0 = b0;
-        nu = b1 - b0;
+        long long v0, v1;   // this CTA's piece of the column's virtual units [0, vcol)
+        if (paired) {       // split_k even: split_k / 2 pairs per column
+            const int ppc = split_k >> 1;
+            col = pair / ppc;
+            const int pp = pair - col * ppc;
+            const long long lo = vcol * pp / ppc, hi = vcol * (pp + 1) / ppc, mid = lo + (hi - lo) * skew / 1000;
+            v0 = fast ? lo : mid;
+            v1 = fast ? mid : hi;
+        } else {
+            col = cta / split_k;
+            const int part = cta - col * split_k;
+            v0 = vcol * part / split_k;
+            v1 = vcol * (part + 1) / split_k;
+        }
+        const int b0 = v0 <= 0 ? 0 : (int)v0 - e, b1 = v1 >= vcol ? units : (int)v1 - e;
+        u0 = b0 < 0 ? 0 : b0;
+        nu = (b1 > units ? units : b1) - u0;
         return nu > 0;
     }
     const int vunits = units + PRO_UNITS;
     const long long total = (long long)vunits * ncols;
-    const long long v_end = total * (cta + 1) / grid;
+    long long v_begin, v_end;
+    if (paired) {
+        const long long lo = total * pair / half, hi = total * (pair + 1) / half, mid = lo + (hi - lo) * skew / 1000;
+        v_begin = fast ? lo : mid;
+        v_end = fast ? mid : hi;
+    } else {
+        v_begin = total * cta / grid;
+        v_end = total * (cta + 1) / grid;
+    }
     for (;;) {
-        const long long v = total * cta / grid + done;
+        const long long v = v_begin + done;
         if (v >= v_end) return false;
         col = (int)(v / vunits);
         const int v0 = (int)(v - (long long)col * vunits);
@@ -493,6 +533,16 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
     const bool edge_rows = a.row_wrap || a.peer_up_out || a.peer_dn_out;
     pdl_wait_then_release();  // the state is the previous step's output
     __syncthreads();          // twiddle table
+#ifdef B200CA_DEV
+    if (a.trace && tid == 0) {
+        unsigned long long t0;
+        unsigned sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        a.trace[3 * blockIdx.x] = t0;
+        a.trace[3 * blockIdx.x + 2] = sm;
+    }
+#endif
 
     int done = 0;             // balanced launches: units of this CTA's run that are finished
 #pragma unroll 1
@@ -501,7 +551,7 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
         int strip, b, y0, Lp, niter;
         if (a.jobs) {
             int col, u0;
-            if (!next_band(a.units, (long long)a.strips * a.B, (int)gridDim.x, a.split_k, (int)blockIdx.x, done, col, u0, niter)) break;
+            if (!next_band(a.units, (long long)a.strips * a.B, (int)gridDim.x, a.split_k, a.skew, (int)blockIdx.x, done, col, u0, niter)) break;
             strip = col % a.strips;
             b = col / a.strips;
             y0 = 2 * FT * u0;
@@ -740,6 +790,16 @@ __global__ void __launch_bounds__(THREADS, 2) lenia_march_kernel(const Args a) {
             }
         }
     }
+#ifdef B200CA_DEV
+    if (a.trace) {
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            a.trace[3 * blockIdx.x + 1] = t1;
+        }
+    }
+#endif
 }
 
 // Tap table: kf[pair][dy][f] = (Khat[dy][k0(f)], Khat[dy][k1(f)]),  Khat[dy][k] = (1/N) sum_dx K[R+dy][R+dx] cos(2 pi k dx / N)
@@ -773,7 +833,7 @@ __global__ void march_prepare_kernel(const float *__restrict__ K, float2 *__rest
 // Launch plan of a balanced launch (host side; the kernel derives every CTA's bands from these numbers): grid size, and either
 // split_k = 0 -- equal-cost runs of the (column, unit) space, see the kernel -- or every column cut into split_k equal bands,
 // whichever leaves the busiest CTA with fewer rounds (a run pays PRO_UNITS rounds for every column it enters).
-static void plan_balanced(int H, int W, int B, int waves, int *grid, int *split_k, int *units, int *strips) {
+static void plan_balanced(int H, int W, int B, int waves, int *grid, int *split_k, int *units, int *strips, int *skew) {
     *units = ceil_div(H, 2 * FT);
     *strips = ceil_div(W, V);
     const long long ncols = (long long)*strips * B, total = *units * ncols;
@@ -788,13 +848,19 @@ static void plan_balanced(int H, int W, int B, int waves, int *grid, int *split_
             *grid = (int)(k * ncols);
         }
     }
+    // a full wave of two CTAs per SM, long enough for the skew to matter and (split launches) an even number of bands per column
+    int sk = MARCH_SKEW;
+#ifdef B200CA_DEV
+    if (const char *e = getenv("B200CA_MARCH_SKEW")) sk = atoi(e);
+#endif
+    *skew = (waves == 1 && *grid == 2 * num_sms() && total >= 8LL * *grid && (*split_k == 0 || *split_k % 2 == 0)) ? sk : 0;
 }
 
 // The bands of CTA `cta` of a balanced launch, exactly as the kernel derives them (host copy: tests/test_host_logic.py checks that
 // the bands of all CTAs tile every column once): writes up to `cap` (column, first unit, units) triples, returns their number.
-static int bands_of_cta(int units, int ncols_strips_times_B, int grid, int split_k, int cta, int *out, int cap) {
+static int bands_of_cta(int units, int ncols_strips_times_B, int grid, int split_k, int skew, int cta, int *out, int cap) {
     int n = 0, done = 0, col, u0, nu;
-    while (next_band(units, ncols_strips_times_B, grid, split_k, cta, done, col, u0, nu))
+    while (next_band(units, ncols_strips_times_B, grid, split_k, skew, cta, done, col, u0, nu))
         if (n < cap) out[3 * n] = col, out[3 * n + 1] = u0, out[3 * n + 2] = nu, ++n;
     return n;
 }
@@ -864,17 +930,17 @@ extern "C" int b200ca_lenia_march_band_rows(int H, int W, int B, int C) { return
 
 extern "C" int b200ca_lenia_march_plan(int H, int W, int B, int *grid, int *split_k, int *units, int *columns) {
     B200CA_REQUIRE(grid && split_k && units && columns && H >= 1 && W >= 1 && B >= 1, "lenia_march_plan: bad arguments");
-    int strips = 0;
-    march::plan_balanced(H, W, B, MARCH_JOB_WAVES > 0 ? MARCH_JOB_WAVES : 1, grid, split_k, units, &strips);
+    int strips = 0, skew = 0;
+    march::plan_balanced(H, W, B, MARCH_JOB_WAVES > 0 ? MARCH_JOB_WAVES : 1, grid, split_k, units, &strips, &skew);
     *columns = strips * B;
     return 0;
 }
 
 extern "C" int b200ca_lenia_march_plan_bands(int H, int W, int B, int cta, int *bands, int cap) {
-    int grid = 0, split_k = 0, units = 0, strips = 0;
-    march::plan_balanced(H, W, B, MARCH_JOB_WAVES > 0 ? MARCH_JOB_WAVES : 1, &grid, &split_k, &units, &strips);
+    int grid = 0, split_k = 0, units = 0, strips = 0, skew = 0;
+    march::plan_balanced(H, W, B, MARCH_JOB_WAVES > 0 ? MARCH_JOB_WAVES : 1, &grid, &split_k, &units, &strips, &skew);
     if (!bands || cap < 1 || cta < 0 || cta >= grid) return -1;
-    return march::bands_of_cta(units, strips * B, grid, split_k, cta, bands, cap);
+    return march::bands_of_cta(units, strips * B, grid, split_k, skew, cta, bands, cap);
 }
 
 extern "C" int b200ca_lenia_march_prepare_kernel(const float *K, float *Kf, int B, int C, int k_mult, int ks, void *stream) {
@@ -935,13 +1001,14 @@ static int march_launch(march::Args a, int B, int C, int k_mult, int H, int W, i
     int job_waves = MARCH_JOB_WAVES;
 #ifdef B200CA_DEV
     if (const char *e = getenv("B200CA_MARCH_WAVES")) job_waves = atoi(e);
+    if (const char *e = getenv("B200CA_MARCH_TRACE")) a.trace = reinterpret_cast<unsigned long long *>(strtoull(e, nullptr, 0));   // device pointer, >= 3 x grid u64
 #endif
     dim3 grid;
     if (band_begin == 0 && band_end == 0 && job_waves > 0) {
         // balanced launch: the whole world / slab, cut into equal runs of 16-row units for one wave of CTAs (see the kernel)
         a.jobs = 1;
         int g = 0;
-        march::plan_balanced(H, W, B, job_waves, &g, &a.split_k, &a.units, &a.strips);
+        march::plan_balanced(H, W, B, job_waves, &g, &a.split_k, &a.units, &a.strips, &a.skew);
         grid = dim3((unsigned)g, 1, 1);
     } else {
         if (band_begin == 0 && band_end == 0) band_end = a.nbands;

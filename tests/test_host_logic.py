@@ -190,5 +190,10 @@ def test_marching_kernel_balanced_plan_tiles_every_column_once():
                 assert n == 1
         assert (seen == 1).all(), (H, W, B)
         assert L.b200ca_lenia_march_plan_bands(H, W, B, g, buf, 64) == -1
-        if g == 296 and units * cols >= 8 * g:   # big launches: within a round or two of a perfect split
-            assert max(load) - min(load) <= 6, (H, W, B, max(load), min(load))
+        if g == 296 and units * cols >= 8 * g:
+            # big launches: within a round or two of a perfect split inside each half of the grid; the first half (the CTA placed
+            # first on every SM, which gets the larger share of its SM) carries 58 % of the rounds, or the split is even
+            lo, hi = load[:g // 2], load[g // 2:]
+            assert max(lo) - min(lo) <= 8 and max(hi) - min(hi) <= 8, (H, W, B, max(lo), min(lo), max(hi), min(hi))
+            share = sum(lo) / (sum(lo) + sum(hi))
+            assert abs(share - 0.5) < 0.01 or abs(share - 0.58) < 0.02, (H, W, B, share)

@@ -52,11 +52,15 @@ if __name__ == "__main__":
     waves = sys.argv[1:] or ["0", "1", "2", "4"]      # "<waves>" or "<variant>:<waves>" (pyca_b200/variants/<variant>.so)
     for w in waves:
         lib = os.path.join(ROOT, "pyca_b200", "libb200ca_dev.so")
-        if ":" in w:                                   # "<variant>:<waves>"; variant "" = the developer library
-            v, w, *_ = w.split(":")
+        skew = None
+        if ":" in w:                                   # "<variant>:<waves>[:<skew per mille>]"; variant "" = the developer library
+            v, w, *rest = w.split(":")
             if v:
                 lib = os.path.join(ROOT, "pyca_b200", "variants", v + ".so")
-        print(f"=== {os.path.basename(lib)} B200CA_MARCH_WAVES={w}", flush=True)
+            skew = rest[0] if rest else None
+        print(f"=== {os.path.basename(lib)} B200CA_MARCH_WAVES={w} B200CA_MARCH_SKEW={skew}", flush=True)
         env = dict(os.environ, B200CA_LIB=lib, B200CA_MARCH_WAVES=w)
+        if skew is not None:
+            env["B200CA_MARCH_SKEW"] = skew
         r = subprocess.run([sys.executable, "-c", CODE % (ROOT, SPECS)], env=env, capture_output=True, text=True)
         print(r.stdout.rstrip() or r.stderr[-1500:], flush=True)
