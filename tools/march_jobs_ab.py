@@ -50,17 +50,25 @@ if os.environ.get("MARCH_AB_PRO"):
 
 if __name__ == "__main__":
     waves = sys.argv[1:] or ["0", "1", "2", "4"]      # "<waves>" or "<variant>:<waves>" (pyca_b200/variants/<variant>.so)
-    for w in waves:
+    for w0 in waves:
+        w = w0
         lib = os.path.join(ROOT, "pyca_b200", "libb200ca_dev.so")
-        skew = None
+        skew, rest = None, []
         if ":" in w:                                   # "<variant>:<waves>[:<skew per mille>]"; variant "" = the developer library
             v, w, *rest = w.split(":")
             if v:
                 lib = os.path.join(ROOT, "pyca_b200", "variants", v + ".so")
             skew = rest[0] if rest else None
-        print(f"=== {os.path.basename(lib)} B200CA_MARCH_WAVES={w} B200CA_MARCH_SKEW={skew}", flush=True)
+        duo = rest[1] if len(rest) > 1 else None        # "<variant>:<waves>:<skew>:<duo 0/1>"
+        print(f"=== {os.path.basename(lib)} B200CA_MARCH_WAVES={w} B200CA_MARCH_SKEW={skew} B200CA_MARCH_DUO={duo}", flush=True)
         env = dict(os.environ, B200CA_LIB=lib, B200CA_MARCH_WAVES=w)
-        if skew is not None:
+        if skew:
             env["B200CA_MARCH_SKEW"] = skew
-        r = subprocess.run([sys.executable, "-c", CODE % (ROOT, SPECS)], env=env, capture_output=True, text=True)
+        if duo is not None:
+            env["B200CA_MARCH_DUO"] = duo
+        try:
+            r = subprocess.run([sys.executable, "-c", CODE % (ROOT, SPECS)], env=env, capture_output=True, text=True, timeout=50)
+        except subprocess.TimeoutExpired:
+            print("  TIMEOUT", flush=True)
+            continue
         print(r.stdout.rstrip() or r.stderr[-1500:], flush=True)
