@@ -233,12 +233,14 @@ __global__ void __launch_bounds__(128) mace_fast_kernel(const MaceArgs a) {
 
 template <int C>
 static int launch_mace_fast(const MaceArgs &a, cudaStream_t st) {
-    // 32 rows per warp (12 % halo re-reads) when that still gives every SM several blocks, else 8 rows
-    const long long blocks32 = (long long)ceil_div(ceil_div(a.W, MCOLS), 4) * ceil_div(a.H, 32) * a.B;
-    if (blocks32 >= (long long)num_sms() * 8) {
-        dim3 grid(ceil_div(ceil_div(a.W, MCOLS), 4), ceil_div(a.H, 32), a.B);
-        mace_fast_kernel<C, 32><<<grid, 128, 0, st>>>(a);
-        note_variant("mace_fast<%d,32>", C);
+    // 16 rows per warp (25 % halo re-reads, all of them L2 hits) when that still gives every SM several blocks, else 8 rows.
+    // (4096^2, C = 3, tools/mace_ab.py: 16 rows 177 us, 32 rows 184 us, 64 rows 212 us -- the shorter marches walk memory in a
+    // tighter front)
+    const long long blocks16 = (long long)ceil_div(ceil_div(a.W, MCOLS), 4) * ceil_div(a.H, 16) * a.B;
+    if (blocks16 >= (long long)num_sms() * 16) {
+        dim3 grid(ceil_div(ceil_div(a.W, MCOLS), 4), ceil_div(a.H, 16), a.B);
+        mace_fast_kernel<C, 16><<<grid, 128, 0, st>>>(a);
+        note_variant("mace_fast<%d,16>", C);
     } else {
         dim3 grid(ceil_div(ceil_div(a.W, MCOLS), 4), ceil_div(a.H, 8), a.B);
         mace_fast_kernel<C, 8><<<grid, 128, 0, st>>>(a);

@@ -12,8 +12,8 @@ EXPECT = {
     "lenia3_1k_direct": ["lenia_conv<"],
     # MaCE-XChan (BASELINE configs[2])
     "xchan_1k": ["lenia_fft_rows<", "lenia_fft_firinv<", "mace_fast<3,"],
-    "xchan_4k": ["lenia_march<multi,balanced:", "mace_fast<3,32>"],
-    "xchan_4k_hybrid": ["lenia_fft_rows<2,1024,split>", "lenia_fft_firinv<8,multi,2,256>", "mace_fast<3,32>"],
+    "xchan_4k": ["lenia_march<multi,balanced:", "mace_fast<3,16>"],
+    "xchan_4k_hybrid": ["lenia_fft_rows<2,1024,split>", "lenia_fft_firinv<8,multi,2,256>", "mace_fast<3,16>"],
     # overlap-save segments / the 16384^2 world of BASELINE configs[4]
     "lenia_seg_4k": ["lenia_march<single,balanced:"],
     "lenia_16k": ["lenia_march<single,balanced:"],

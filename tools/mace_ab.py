@@ -12,7 +12,7 @@ sys.path.insert(0, %r)
 import pyca_b200
 from pyca_b200 import _lib
 from tools.march_check import params
-for H, W in [(4096, 4096)]:
+for H, W in [(4096, 4096), (512, 4096), (1024, 1024)]:
     P, *_ = params(3)
     g = torch.Generator().manual_seed(1)
     a = pyca_b200.MaCELeniaXChan((H, W), num_channels=3, params=P, state_init=torch.rand(1, 3, H, W, generator=g), device="cuda")
